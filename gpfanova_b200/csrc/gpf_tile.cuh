@@ -1,0 +1,409 @@
+// Tile engine: blocked right-looking FP64 Cholesky of one n x n matrix per CTA (n <= 512),
+// with optional "augmented rows" that ride along the factorisation:
+//   AUG_RHS   : rows R appended below the matrix come out as R L^-T, i.e. row v = (L^-1 b_v)^T
+//               -> forward solves / quadratic forms for free (slice log-likelihoods, base.py:233-238;
+//               b of function.py:32)
+//   AUG_IDENT : identity rows come out as U = L^-T; the engine accumulates U U^T = (L L^T)^-1
+//               tile by tile -> Kernel.K_inv (kernel/kernel.pyx:51-64)
+// Matrix tiles are 32x32 FP64, row-major, packed lower-triangular by tile (plt), kept in a per-CTA
+// global workspace that stays L2-resident (one slot per persistent CTA); the current panel lives in
+// shared memory.  Trailing updates are mma.sync m8n8k4 f64 (DMMA.8x8x4 on sm_100a: measured
+// 37.1 TFLOP/s on B200, profiles/fp64_peak_r01.json); the 32x32 diagonal factorisation and the panel
+// solves are warp-level (registers + shuffles / broadcast shared-memory reads).
+// Replaces linalg.jitchol's dpotrf (linalg.py:35-37).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gpf {
+
+constexpr int TB = 32;            // tile edge
+constexpr int TILE = TB * TB;     // doubles per tile
+constexpr int PS = 36;            // row stride of a panel slot in shared memory (conflict-free DMMA fragment loads)
+constexpr int DS = 33;            // row stride of the diagonal tile in shared memory
+constexpr int NW = 8;             // warps per CTA
+constexpr int NTHR = NW * 32;
+constexpr unsigned FULLMASK = 0xffffffffu;
+constexpr int MAX_NT = 16;
+
+enum { AUG_NONE = 0, AUG_RHS = 1, AUG_IDENT = 2 };
+
+__host__ __device__ __forceinline__ int plt(int bi, int bj) { return (bi * (bi + 1)) / 2 + bj; }
+__host__ __device__ __forceinline__ int plt_tiles(int NT) { return NT * (NT + 1) / 2; }
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1},{%2},{%3},{%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// rows appended below the matrix (AUG_RHS): element (r, c) = base[idx(r) * ld + c] for r < nrows, c < ncols, else 0
+struct RowSrc {
+  const double* base;
+  const int* rowidx;   // may be nullptr (identity)
+  int ld, nrows, ncols;
+  __device__ __forceinline__ double at(int r, int c) const {
+    if (r >= nrows || c >= ncols) return 0.0;
+    const int rr = rowidx ? rowidx[r] : r;
+    return base[(size_t)rr * ld + c];
+  }
+};
+
+// ---- C fragment (32x32 tile in DMMA accumulator layout): c[ti][tj][e] = C[8ti+g][8tj+2tig+e] ----
+struct CFrag { double c[4][4][2]; };
+
+__device__ __forceinline__ void cfrag_zero(CFrag& f) {
+#pragma unroll
+  for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+    for (int tj = 0; tj < 4; ++tj) { f.c[ti][tj][0] = 0.0; f.c[ti][tj][1] = 0.0; }
+}
+__device__ __forceinline__ void cfrag_load(CFrag& f, const double* tile, int g, int tig, int nti) {
+#pragma unroll
+  for (int ti = 0; ti < 4; ++ti)
+    if (ti < nti) {
+#pragma unroll
+      for (int tj = 0; tj < 4; ++tj) {
+        double2 v = *reinterpret_cast<const double2*>(tile + (8 * ti + g) * TB + 8 * tj + 2 * tig);
+        f.c[ti][tj][0] = v.x; f.c[ti][tj][1] = v.y;
+      }
+    }
+}
+__device__ __forceinline__ void cfrag_store(const CFrag& f, double* tile, int g, int tig, int nti) {
+#pragma unroll
+  for (int ti = 0; ti < 4; ++ti)
+    if (ti < nti) {
+#pragma unroll
+      for (int tj = 0; tj < 4; ++tj)
+        *reinterpret_cast<double2*>(tile + (8 * ti + g) * TB + 8 * tj + 2 * tig) = make_double2(f.c[ti][tj][0], f.c[ti][tj][1]);
+    }
+}
+// add dv[8ti+g] on the diagonal of a diagonal tile
+__device__ __forceinline__ void cfrag_add_diag(CFrag& f, const double* dv, int g, int tig) {
+#pragma unroll
+  for (int ti = 0; ti < 4; ++ti) {
+    // element (8ti+g, 8ti+2tig+e) is diagonal iff g == 2tig+e
+    const double d = dv[8 * ti + g];
+    if (g == 2 * tig) f.c[ti][ti][0] += d;
+    if (g == 2 * tig + 1) f.c[ti][ti][1] += d;
+  }
+}
+__device__ __forceinline__ void cfrag_from_rows(CFrag& f, const RowSrc& s, int r0, int c0, int g, int tig, int nti) {
+#pragma unroll
+  for (int ti = 0; ti < 4; ++ti)
+    if (ti < nti) {
+#pragma unroll
+      for (int tj = 0; tj < 4; ++tj) {
+        f.c[ti][tj][0] = s.at(r0 + 8 * ti + g, c0 + 8 * tj + 2 * tig);
+        f.c[ti][tj][1] = s.at(r0 + 8 * ti + g, c0 + 8 * tj + 2 * tig + 1);
+      }
+    }
+}
+
+// C (+/-)= Pa * Pb^T, Pa/Pb panel slots in shared memory (32 x PS), 128 DMMA.8x8x4 for a full tile
+template <bool NEG>
+__device__ __forceinline__ void tile_mma(CFrag& f, const double* __restrict__ Pa, const double* __restrict__ Pb,
+                                         int g, int tig, int nti) {
+  const double* pa = Pa + g * PS + tig;
+  const double* pb = Pb + g * PS + tig;
+#pragma unroll
+  for (int kk = 0; kk < 8; ++kk) {
+    double a[4], b[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      b[t] = pb[(8 * t) * PS + 4 * kk];
+      a[t] = 0.0;
+      if (t < nti) { double v = pa[(8 * t) * PS + 4 * kk]; a[t] = NEG ? -v : v; }
+    }
+#pragma unroll
+    for (int ti = 0; ti < 4; ++ti)
+      if (ti < nti) {
+#pragma unroll
+        for (int tj = 0; tj < 4; ++tj) dmma884(f.c[ti][tj][0], f.c[ti][tj][1], a[ti], b[tj]);
+      }
+  }
+}
+
+// ---- lane = row helpers ----
+__device__ __forceinline__ void rows_load(double (&a)[32], const double* tile, int lane) {
+  const double2* p = reinterpret_cast<const double2*>(tile + lane * TB);
+#pragma unroll
+  for (int c = 0; c < 16; ++c) { double2 v = p[c]; a[2 * c] = v.x; a[2 * c + 1] = v.y; }
+}
+__device__ __forceinline__ void rows_store(const double (&a)[32], double* tile, int lane) {
+  double2* p = reinterpret_cast<double2*>(tile + lane * TB);
+#pragma unroll
+  for (int c = 0; c < 16; ++c) p[c] = make_double2(a[2 * c], a[2 * c + 1]);
+}
+
+// In-register Cholesky of a 32x32 tile, lane = row.  dpotf2's failure rule: pivot <= 0 or NaN.
+// Returns false on failure.  On success a[c] (c <= lane) = L[lane][c]; rinv = 1/L[lane][lane];
+// piv = pivot value before the square root (for the log-determinant).
+__device__ __forceinline__ bool potrf_warp(double (&a)[32], int lane, double& rinv_out, double& piv_out) {
+  bool ok = true;
+  rinv_out = 1.0; piv_out = 1.0;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    double dcc = __shfl_sync(FULLMASK, a[c], c);
+    if (!(dcc > 0.0) || !(dcc < 1.0e300)) ok = false;
+    double rinv = rsqrt(dcc);
+    double l = a[c] * rinv;
+    a[c] = l;
+    if (lane == c) { rinv_out = rinv; piv_out = dcc; }
+#pragma unroll
+    for (int c2 = c + 1; c2 < 32; ++c2) {
+      double l2 = __shfl_sync(FULLMASK, l, c2);
+      a[c2] = fma(-l, l2, a[c2]);
+    }
+  }
+  return ok;
+}
+
+// X <- X L^-T for one 32-row block, lane = row of X.  sD: L (row-major, stride DS), sRinv[c] = 1/L[c][c]
+__device__ __forceinline__ void trsm_warp(double (&a)[32], const double* __restrict__ sD, const double* __restrict__ sRinv) {
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    double x = a[c] * sRinv[c];
+    a[c] = x;
+#pragma unroll
+    for (int c2 = c + 1; c2 < 32; ++c2) a[c2] = fma(-x, sD[c2 * DS + c], a[c2]);
+  }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+  return v;
+}
+
+// deterministic CTA-wide sum (fixed order); red: NW doubles of shared memory.  All threads get the result.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) s += red[w];
+  return s;
+}
+
+// shared-memory footprint (doubles) of the engine for NT matrix tile rows + NE extra panel slots
+__host__ __device__ inline size_t engine_smem_doubles(int NT, int NE) {
+  return (size_t)TB * DS + (size_t)(NT + NE) * TB * PS + (size_t)NT * TB /*rinv*/ + (size_t)NT * TB /*dvec*/ +
+         (size_t)(NE > 0 ? NE : 1) * NT /*quadpart*/ + 16;
+}
+
+struct EngineSmem {
+  double* D;      // 32 x DS
+  double* P;      // (NT+NE) slots of 32 x PS
+  double* rinv;   // NT*32 reciprocal diagonal of L
+  double* dvec;   // NT*32 additive diagonal applied at first touch (jitter, offset, n_t/sigma_y; 0 on padding)
+  double* quad;   // NE*NT partial sums of squares of finished augmented rows (deterministic reduction)
+  double* scal;   // [0] logdet, [1] fail flag (as double), [2..9] block_sum scratch, spare
+  __device__ EngineSmem(double* base, int NT, int NE) {
+    D = base;
+    P = D + TB * DS;
+    rinv = P + (size_t)(NT + NE) * TB * PS;
+    dvec = rinv + NT * TB;
+    quad = dvec + NT * TB;
+    scal = quad + (size_t)(NE > 0 ? NE : 1) * NT;
+  }
+  __device__ double* red() const { return scal + 2; }
+};
+
+struct EngineIO {
+  const double* A0;   // first-touch source of the matrix tiles (plt layout, padded rows = identity); may alias W
+  double* W;          // plt_tiles(NT) tiles of workspace; with KEEPL the final L tiles are left there
+  double* Wx;         // AUG_RHS: NE*NT tiles; AUG_IDENT: NT*NT tiles
+  double* Kout;       // AUG_IDENT: plt_tiles(NT) output tiles of (L L^T)^-1 (lower tiles, full diagonal tiles)
+  RowSrc rows;        // AUG_RHS: first-touch source of the extra rows
+  double* vout;       // AUG_RHS: finished rows r < rows.nrows are written to vout[r*ldv + col] (may be nullptr)
+  int ldv;
+};
+
+/* The engine.  All NTHR threads of the CTA call it with identical arguments.
+ *   AUG_RHS  : NE extra tile rows; the last extra tile row uses only nti_last 8-row strips.
+ * Returns false if a pivot failed (matrix not PD); logdet (= 2 sum log L_ii) is in sm.scal[0] on success,
+ * sm.quad[e*NT+k] hold the sums of squares of the finished augmented rows. */
+template <int AUG, bool KEEPL>
+__device__ bool chol_engine(const EngineIO& io, int NT, int NE, int nti_last, const EngineSmem& sm) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
+  const double* A0 = io.A0;
+  double* W = io.W;
+  double* Wx = io.Wx;
+  if (tid == 0) { sm.scal[0] = 0.0; sm.scal[1] = 0.0; }
+  __syncthreads();
+  for (int k = 0; k < NT; ++k) {
+    const double* S = (k == 0) ? A0 : W;
+    // ---------------- phase 1: factor the diagonal tile (warp 0) ----------------
+    if (warp == 0) {
+      double a[32];
+      rows_load(a, S + (size_t)plt(k, k) * TILE, lane);
+      if (k == 0) {
+        const double dv = sm.dvec[lane];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) if (c == lane) a[c] += dv;
+      }
+      double rinv, piv;
+      bool ok = potrf_warp(a, lane, rinv, piv);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        double v = (c <= lane) ? a[c] : 0.0;
+        a[c] = v;
+        sm.D[lane * DS + c] = v;
+      }
+      sm.rinv[k * TB + lane] = rinv;
+      double lg = warp_sum(log(piv));
+      if (KEEPL) rows_store(a, W + (size_t)plt(k, k) * TILE, lane);
+      if (lane == 0) { sm.scal[0] += lg; if (!ok) sm.scal[1] = 1.0; }
+    }
+    __syncthreads();
+    if (sm.scal[1] != 0.0) return false;
+    // ---------------- phase 2: panel solves  X <- X L_kk^-T ----------------
+    const int nreg = NT - 1 - k;
+    const int nx = (AUG == AUG_RHS) ? NE : ((AUG == AUG_IDENT) ? (k + 1) : 0);
+    for (int t = warp; t < nreg + nx; t += NW) {
+      double a[32];
+      int slot;
+      if (t < nreg) {
+        const int i = k + 1 + t;
+        slot = i;
+        rows_load(a, S + (size_t)plt(i, k) * TILE, lane);
+      } else {
+        const int e = t - nreg;
+        if (AUG == AUG_RHS) {
+          slot = NT + e;
+          if (k == 0) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) a[c] = io.rows.at(e * TB + lane, c);
+          } else rows_load(a, Wx + (size_t)(e * NT + k) * TILE, lane);
+        } else {
+          slot = e;
+          if (e == k) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) a[c] = (c == lane) ? 1.0 : 0.0;
+          } else rows_load(a, Wx + (size_t)(e * NT + k) * TILE, lane);
+        }
+      }
+      trsm_warp(a, sm.D, sm.rinv + k * TB);
+      double* ps = sm.P + (size_t)slot * TB * PS + lane * PS;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) ps[c] = a[c];
+      if (t < nreg) {
+        if (KEEPL) rows_store(a, W + (size_t)plt(k + 1 + t, k) * TILE, lane);
+      } else if (AUG == AUG_RHS) {
+        const int e = t - nreg;
+        double ss = 0.0;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) ss = fma(a[c], a[c], ss);
+        ss = warp_sum(ss);
+        if (lane == 0) sm.quad[e * NT + k] = ss;
+        const int r = e * TB + lane;
+        if (io.vout != nullptr && r < io.rows.nrows) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) io.vout[(size_t)r * io.ldv + k * TB + c] = a[c];
+        }
+      }
+    }
+    __syncthreads();
+    // ---------------- phase 3: trailing updates (DMMA) ----------------
+    const int T1 = nreg * (nreg + 1) / 2;
+    const int T2 = nx * nreg;
+    const int T3 = (AUG == AUG_IDENT) ? (k + 1) * (k + 2) / 2 : 0;
+    for (int t = warp; t < T1 + T2 + T3; t += NW) {
+      CFrag f;
+      if (t < T1) {
+        int ii = 0, tt = t;
+        while (tt > ii) { tt -= ii + 1; ++ii; }
+        const int i = k + 1 + ii, j = k + 1 + tt;
+        cfrag_load(f, S + (size_t)plt(i, j) * TILE, g, tig, 4);
+        if (k == 0 && i == j) cfrag_add_diag(f, sm.dvec + i * TB, g, tig);
+        tile_mma<true>(f, sm.P + (size_t)i * TB * PS, sm.P + (size_t)j * TB * PS, g, tig, 4);
+        cfrag_store(f, W + (size_t)plt(i, j) * TILE, g, tig, 4);
+      } else if (t < T1 + T2) {
+        const int u = t - T1;
+        const int e = u / nreg, j = k + 1 + (u % nreg);
+        double* wt = Wx + (size_t)(e * NT + j) * TILE;
+        if (AUG == AUG_RHS) {
+          const int nti = (e == NE - 1) ? nti_last : 4;
+          if (k == 0) cfrag_from_rows(f, io.rows, e * TB, j * TB, g, tig, nti);
+          else cfrag_load(f, wt, g, tig, nti);
+          tile_mma<true>(f, sm.P + (size_t)(NT + e) * TB * PS, sm.P + (size_t)j * TB * PS, g, tig, nti);
+          cfrag_store(f, wt, g, tig, nti);
+        } else {
+          if (k == e) cfrag_zero(f);
+          else cfrag_load(f, wt, g, tig, 4);
+          tile_mma<true>(f, sm.P + (size_t)e * TB * PS, sm.P + (size_t)j * TB * PS, g, tig, 4);
+          cfrag_store(f, wt, g, tig, 4);
+        }
+      } else {
+        // (L L^T)^-1 tile (a,b) += U_ak U_bk^T, first touched at k == a
+        int aa = 0, tt = t - T1 - T2;
+        while (tt > aa) { tt -= aa + 1; ++aa; }
+        const int bb = tt;
+        double* kt = io.Kout + (size_t)plt(aa, bb) * TILE;
+        if (k == aa) cfrag_zero(f);
+        else cfrag_load(f, kt, g, tig, 4);
+        tile_mma<false>(f, sm.P + (size_t)aa * TB * PS, sm.P + (size_t)bb * TB * PS, g, tig, 4);
+        cfrag_store(f, kt, g, tig, 4);
+      }
+    }
+    __syncthreads();
+  }
+  return true;
+}
+
+// sum of sm.quad over the NE*NT partials in fixed order (call after the engine; all threads get the value)
+__device__ __forceinline__ double engine_quad_total(const EngineSmem& sm, int NT, int NE) {
+  double s = 0.0;
+  for (int i = 0; i < NE * NT; ++i) s += sm.quad[i];
+  return s;
+}
+
+/* Back substitution  L^T x = w  for NRHS vectors held in shared memory (xs[v*ldx + i], i < NT*32, in place).
+ * L: tiles left in W by the engine (KEEPL); sm.rinv holds 1/L_ii.  red: NW*NRHS*32 doubles of shared memory. */
+template <int NRHS>
+__device__ void back_solve(const double* W, int NT, double* xs, int ldx, const EngineSmem& sm, double* red) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int k = NT - 1; k >= 0; --k) {
+    double acc[NRHS];
+#pragma unroll
+    for (int v = 0; v < NRHS; ++v) acc[v] = 0.0;
+    for (int i = k + 1 + warp; i < NT; i += NW) {
+      const double* tile = W + (size_t)plt(i, k) * TILE;
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) {
+        const double l = tile[r * TB + lane];
+#pragma unroll
+        for (int v = 0; v < NRHS; ++v) acc[v] = fma(l, xs[v * ldx + i * TB + r], acc[v]);
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < NRHS; ++v) red[(warp * NRHS + v) * 32 + lane] = acc[v];
+    __syncthreads();
+    if (warp == 0) {
+      const double* tile = W + (size_t)plt(k, k) * TILE;
+      double a[32];   // a[r] = L[r][lane]
+#pragma unroll
+      for (int r = 0; r < 32; ++r) a[r] = tile[r * TB + lane];
+      const double* rinv = sm.rinv + k * TB;
+#pragma unroll
+      for (int v = 0; v < NRHS; ++v) {
+        double t = xs[v * ldx + k * TB + lane];
+#pragma unroll
+        for (int w = 0; w < NW; ++w) t -= red[(w * NRHS + v) * 32 + lane];
+        double x = 0.0;
+#pragma unroll
+        for (int c = 31; c >= 0; --c) {
+          const double xc = __shfl_sync(FULLMASK, t, c) * rinv[c];
+          if (lane == c) x = xc;
+          if (lane < c) t = fma(-a[c], xc, t);
+        }
+        xs[v * ldx + k * TB + lane] = x;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace gpf

@@ -1,0 +1,157 @@
+/*
+ * gpfanova_b200 -- C ABI of the B200-native Gibbs-sampling hot path of ptonner/gpfanova.
+ *
+ * The reference (pure Python) has no FFI layer; its hot path sits behind a Python class
+ * protocol.  This header is the boundary a maintainer would bind with
+ * ctypes; every entry point names the reference code it replaces
+ * (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - all arithmetic is IEEE double; matrices are row-major; "log10" hyper-parameters are
+ *     the values the reference keeps in parameter_cache (kernel.pyx:35-37 applies 10**).
+ *   - pointers named d_* are DEVICE pointers (e.g. torch tensor.data_ptr()); h_* are HOST.
+ *   - every call returns 0 on success, >0 on error (gpf_last_error gives the text);
+ *     per-chain numerical status (jitter retries / not-PD) is reported through
+ *     gpf_get_status so the host can raise numpy.linalg.LinAlgError like linalg.py:54.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - one gpf_ctx per GPU; a ctx is not thread-safe; different ctxs are independent.
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with
+ *     GPF_ERR_CUDA.
+ */
+#ifndef GPFANOVA_B200_H
+#define GPFANOVA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPF_OK 0
+#define GPF_ERR_ARG 1
+#define GPF_ERR_CUDA 2
+#define GPF_ERR_UNSUPPORTED 3
+#define GPF_ERR_NOT_PD 4
+
+/* per-matrix status words written by the factorisation kernels */
+#define GPF_STATUS_OK 0            /* >0: number of jitter retries that were needed (linalg.py:44-51) */
+#define GPF_STATUS_NONPOS_DIAG -1  /* linalg.py:42-43  "not pd: non-positive diagonal elements"      */
+#define GPF_STATUS_NOT_PD -2       /* linalg.py:54     "not positive definite, even with jitter."    */
+
+#define GPF_MAX_N 512              /* time points per function (tile engine limit, 16 tiles of 32)   */
+
+typedef struct gpf_ctx gpf_ctx;
+
+int gpf_version(void);
+const char* gpf_build_info(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Stateless batched operators (kernel objects and linalg of the reference)
+ * ---------------------------------------------------------------------------------------- */
+
+/* RBF.dist + RBF._K, kernel/rbf.pyx:8-19, with Kernel.build_params' 10** (kernel/kernel.pyx:16-44).
+ * d_x: n x p.  d_log10_sigma, d_log10_ls: batch values.  d_K: batch x n x n (full, symmetric).
+ * K[b] = 10^s_b * exp(-0.5 * r2),  r2 = clip(-2 X X^T + |X_i|^2 + |X_j|^2, 0),  X = x / 10^l_b. */
+int gpf_rbf_K(const double* d_x, int n, int p, const double* d_log10_sigma, const double* d_log10_ls,
+              int batch, double* d_K, void* stream);
+
+/* linalg.jitchol, linalg.py:35-54: lower Cholesky with the jitter-retry ladder, per matrix.
+ * d_A: batch x n x n (lower triangle read).  d_L: batch x n x n (lower, upper zeroed).
+ * d_logdet (may be NULL): log det(A + jitter I) = 2 sum log L_ii.  d_status: batch ints (GPF_STATUS_*). */
+int gpf_jitchol(const double* d_A, int n, int batch, int maxtries, double* d_L, double* d_logdet,
+                int* d_status, void* stream);
+
+/* Kernel.K_inv, kernel/kernel.pyx:51-64: (A + offset*I)^-1 = L^-T L^-1, L = jitchol(A + offset I).
+ * d_A, d_Ainv: batch x n x n full matrices. */
+int gpf_kinv(const double* d_A, int n, int batch, double offset, double* d_Ainv, int* d_status, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Sampler context: C chains of one model  y (n x m) = F (n x f) X^T (f x m) + noise
+ * replaces Base.__init__ state + SamplerContainer.parameter_cache (base.py:16-86, container.py:8-20)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct gpf_model_desc {
+  int n, p, m, f, P;          /* time points, input dims, observations, functions, prior groups   */
+  int chains;                 /* C independent chains held by this ctx                              */
+  int device;                 /* CUDA device ordinal                                                */
+  int chain_offset;           /* global index of this ctx's first chain (Philox key; multi-GPU)     */
+  uint64_t seed;              /* Philox4x32-10 key                                                  */
+  const double* h_x;          /* n x p                                                              */
+  const double* h_y;          /* n x m, NaN = missing (function.py:23-25, base.py:208-209)          */
+  const double* h_X;          /* m x f design matrix (fanova.py:283-310)                            */
+  const int* h_group_of_fn;   /* f entries: prior group of each function (fanova.py:266-281)        */
+  const double* h_slice_w;    /* 1+2P slice widths   (base.py:52-56,75-82), order = hyper layout    */
+  const int* h_slice_m;       /* 1+2P slice step-out limits                                         */
+  double offset;              /* K_inv jitter, kernel.pyx:7 (1e-9)                                  */
+  double prior_jitter;        /* prior_likelihood jitter factor, base.py:222 (1e-6)                 */
+  double prior_lb, prior_ub;  /* uniform prior bounds, base.py:57,78,83 (-2, 2)                     */
+} gpf_model_desc;
+
+int gpf_create(gpf_ctx** out, const gpf_model_desc* desc);
+void gpf_destroy(gpf_ctx* ctx);
+const char* gpf_last_error(gpf_ctx* ctx);
+void* gpf_stream(gpf_ctx* ctx);   /* the ctx's cudaStream_t */
+int gpf_sync(gpf_ctx* ctx);
+
+/* state = parameter_cache of every chain.  hyper layout (log10): [y_sigma, prior0_sigma,
+ * prior0_lengthscale, prior1_sigma, ...] (H = 1+2P per chain);  F: chains x f x n. */
+int gpf_set_state(gpf_ctx* ctx, const double* h_F, const double* h_hyper);
+int gpf_get_state(gpf_ctx* ctx, double* h_F, double* h_hyper);
+double* gpf_device_F(gpf_ctx* ctx);       /* device pointers to the live state (chains x f x n) */
+double* gpf_device_hyper(gpf_ctx* ctx);   /* chains x H */
+
+/* per-chain status of the last factorisations (max |code| since last clear); h_status: chains ints.
+ * returns GPF_ERR_NOT_PD if any chain holds a negative code. */
+int gpf_get_status(gpf_ctx* ctx, int* h_status, int clear);
+
+/* counters since creation/clear: [0] factorisations, [1] log-density evaluations in slice steps,
+ * [2] jitter retries, [3] function draws, [4] inverse (potri) count, [5] slice steps. */
+int gpf_get_counters(gpf_ctx* ctx, unsigned long long* h_counters6, int clear);
+
+/* Kernel.K_inv for prior group g of every chain at the current hyper-parameters (kernel.pyx:51-64
+ * with rbf.pyx:16-19); result kept inside the ctx for gpf_function_step.  g = -1: all groups.
+ * d_out (may be NULL): chains x n x n full copy for inspection (only for g >= 0). */
+int gpf_group_kinv(gpf_ctx* ctx, int g, double* d_out);
+
+/* Function._sample, sample/function.py:14-40 (+ base.functionResidual, base.py:180-190) for function
+ * fn of every chain: m_t, n_t, A = diag(n_t)/(sigma_y+offset) + K_inv, b, L_A = jitchol(A),
+ * mu = A^-1 b, draw beta = mu + L_A^-T z, written into the state.
+ *   sampler_id, sweep : Philox counter words (position in the reference's sampler list; sweep number)
+ *   d_z_inject (may be NULL): chains x n standard normals used instead of Philox
+ *   d_mu_out, d_LA_out, d_mt_out, d_nt_out (may be NULL): chains x n, chains x n x n, chains x n (x2).
+ * Requires gpf_group_kinv for the function's group at the current hyper-parameters. */
+int gpf_function_step(gpf_ctx* ctx, int fn, unsigned sampler_id, unsigned sweep, const double* d_z_inject,
+                      double* d_mu_out, double* d_LA_out, double* d_mt_out, double* d_nt_out);
+
+/* Base.observationLikelihood, base.py:196-214, at candidate log10 y_sigma per chain. d_cand,d_out: chains */
+int gpf_obs_loglik(gpf_ctx* ctx, const double* d_cand, double* d_out);
+
+/* Base.prior_likelihood, base.py:216-243, for group g; which = 0: candidate replaces sigma,
+ * 1: candidate replaces lengthscale.  d_cand, d_out: chains. */
+int gpf_prior_loglik(gpf_ctx* ctx, int g, int which, const double* d_cand, double* d_out);
+
+/* Slice._sample, sample/slice.pyx:24-62, on hyper-parameter h (index in the hyper layout) of every chain,
+ * with the log densities above; new value written into the state.
+ *   d_u_inject (may be NULL): chains x n_inject uniforms used instead of Philox (u0 -> level, u1 -> placement,
+ *   u2 -> step split, u3.. -> proposals);  d_nevals_out (may be NULL): chains ints, log-density evaluations. */
+int gpf_slice_step(gpf_ctx* ctx, int h, unsigned sampler_id, unsigned sweep, const double* d_u_inject,
+                   int n_inject, int* d_nevals_out);
+
+/* SamplerContainer.sample/_sample/store, sample/container.py:29-78: n_sweeps sweeps over the sampler list
+ * in the reference's fixed order (base.py:57-84), or in h_order (permutation of sampler ids, container.py:34-35:
+ * n_sweeps x n_samplers entries) when non-NULL.  Every `thin`-th sweep (thin<=0: every sweep) the state row
+ * [hyper(H), F(f*n)] of every chain is appended to d_history (rows x chains x (H + f*n)); returns rows stored
+ * through *rows_out.  sweep0 = index of the first sweep (Philox counter word). */
+int gpf_sweep(gpf_ctx* ctx, int n_sweeps, int thin, unsigned sweep0, const int* h_order, double* d_history,
+              long long history_capacity_rows, long long* rows_out);
+
+/* timing/accounting of the last gpf_sweep call, measured with CUDA events on the ctx stream:
+ * h_ms[0] total, [1] kinv kernels, [2] function kernels, [3] slice kernels, [4] y_sigma kernel, [5] store.
+ * Only filled when profiling was enabled with gpf_set_profile(ctx, 1) (adds event overhead). */
+int gpf_set_profile(gpf_ctx* ctx, int on);
+int gpf_get_profile(gpf_ctx* ctx, double* h_ms6, unsigned long long* h_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
