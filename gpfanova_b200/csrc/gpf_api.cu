@@ -1,0 +1,523 @@
+// C ABI of gpfanova_b200 (include/gpfanova_b200.h): host-side context, launch logic and the sweep driver
+// (SamplerContainer.sample/_sample/store, sample/container.py:29-92; sampler order of base.py:57-84).
+// There is no CPU path in this file: every compute entry point launches sm_100a kernels or fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gpfanova_b200.h"
+#include "gpf_kernels.cuh"
+
+using namespace gpf;
+
+namespace {
+
+thread_local std::string g_err;   // for the stateless operators (no ctx)
+
+struct Samp { int kind; int arg; };   // kind 0: slice on hyper `arg`; kind 1: function `arg`
+
+size_t smem_limit() { return 227 * 1024; }
+
+template <class K>
+cudaError_t allow_smem(K kernel, size_t bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+}  // namespace
+
+struct gpf_ctx {
+  CtxDev dev{};
+  int device = 0;
+  int sms = 148;
+  int grid = 1;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  std::vector<double> slice_w;
+  std::vector<int> slice_m;
+  std::vector<int> group_of_fn;
+  std::vector<std::vector<int>> groups;
+  std::vector<Samp> order;
+  std::vector<char> kinv_valid;
+  std::vector<void*> allocs;
+  size_t smem_kinv = 0, smem_fn = 0;
+  std::vector<size_t> smem_prior;
+  unsigned long long launches = 0;
+  bool profile = false;
+  double ms[6] = {0, 0, 0, 0, 0, 0};
+  struct Ev { cudaEvent_t a, b; int cat; };
+  std::vector<Ev> evs;
+  std::vector<cudaEvent_t> ev_pool;
+};
+
+#define CK(ctx, call)                                                                        \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess) {                                                                 \
+      char buf_[512];                                                                        \
+      snprintf(buf_, sizeof buf_, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      (ctx)->err = buf_;                                                                     \
+      return GPF_ERR_CUDA;                                                                   \
+    }                                                                                        \
+  } while (0)
+
+#define CKS(call)                                                                            \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess) {                                                                 \
+      char buf_[512];                                                                        \
+      snprintf(buf_, sizeof buf_, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      g_err = buf_;                                                                          \
+      return GPF_ERR_CUDA;                                                                   \
+    }                                                                                        \
+  } while (0)
+
+namespace {
+
+struct Timer {   // optional per-launch CUDA-event bracket (gpf_set_profile)
+  gpf_ctx* c;
+  int cat;
+  cudaEvent_t a = nullptr, b = nullptr;
+  Timer(gpf_ctx* ctx, int category) : c(ctx), cat(category) {
+    if (!c->profile) return;
+    auto get = [&]() {
+      cudaEvent_t e;
+      if (!c->ev_pool.empty()) { e = c->ev_pool.back(); c->ev_pool.pop_back(); }
+      else cudaEventCreate(&e);
+      return e;
+    };
+    a = get(); b = get();
+    cudaEventRecord(a, c->stream);
+  }
+  ~Timer() {
+    if (!c->profile) return;
+    cudaEventRecord(b, c->stream);
+    c->evs.push_back({a, b, cat});
+  }
+};
+
+void collect_profile(gpf_ctx* c) {
+  for (auto& e : c->evs) {
+    float t = 0.f;
+    cudaEventSynchronize(e.b);
+    cudaEventElapsedTime(&t, e.a, e.b);
+    c->ms[e.cat] += t;
+    c->ev_pool.push_back(e.a);
+    c->ev_pool.push_back(e.b);
+  }
+  c->evs.clear();
+}
+
+template <class T>
+int dev_alloc(gpf_ctx* c, T** p, size_t count) {
+  void* q = nullptr;
+  CK(c, cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+  c->allocs.push_back(q);
+  *p = (T*)q;
+  return GPF_OK;
+}
+
+int launch_kinv(gpf_ctx* c, int g) {
+  Timer t(c, 1);
+  k_group_kinv<<<c->grid, NTHR, c->smem_kinv, c->stream>>>(c->dev, g);
+  ++c->launches;
+  CK(c, cudaGetLastError());
+  c->kinv_valid[g] = 1;
+  return GPF_OK;
+}
+
+int launch_function(gpf_ctx* c, int fn, unsigned sampler_id, unsigned sweep, const double* z, FnOut out) {
+  const int g = c->group_of_fn[fn];
+  if (!c->kinv_valid[g]) {
+    int rc = launch_kinv(c, g);
+    if (rc) return rc;
+  }
+  Timer t(c, 2);
+  k_function<<<c->grid, NTHR, c->smem_fn, c->stream>>>(c->dev, fn, sampler_id, sweep, z, out);
+  ++c->launches;
+  CK(c, cudaGetLastError());
+  return GPF_OK;
+}
+
+int launch_slice(gpf_ctx* c, int h, int mode, const double* cand, double* outv, unsigned sampler_id, unsigned sweep,
+                 const double* u, int nu, int* nev) {
+  if (h == 0) {
+    Timer t(c, 4);
+    k_obs<<<std::min(c->dev.C, c->sms * 8), NTHR, 0, c->stream>>>(c->dev, mode, cand, outv, c->slice_w[0], c->slice_m[0],
+                                                                 sampler_id, sweep, u, nu, nev);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    return GPF_OK;
+  }
+  const int g = (h - 1) / 2, which = (h - 1) % 2;
+  Timer t(c, 3);
+  k_prior<<<c->grid, NTHR, c->smem_prior[g], c->stream>>>(c->dev, g, which, mode, cand, outv, c->slice_w[h], c->slice_m[h],
+                                                         sampler_id, sweep, u, nu, nev);
+  ++c->launches;
+  CK(c, cudaGetLastError());
+  if (mode == 1) c->kinv_valid[g] = 0;
+  return GPF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gpf_version(void) { return 100; }
+
+const char* gpf_build_info(void) {
+  return "gpfanova_b200 sm_100a fp64 (mma.sync m8n8k4 f64 tile engine), built " __DATE__ " " __TIME__;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// stateless operators
+// ---------------------------------------------------------------------------------------------------------
+int gpf_rbf_K(const double* d_x, int n, int p, const double* d_log10_sigma, const double* d_log10_ls, int batch,
+              double* d_K, void* stream) {
+  if (n < 1 || p < 1 || batch < 0 || !d_x || !d_K) { g_err = "gpf_rbf_K: bad argument"; return GPF_ERR_ARG; }
+  if (batch == 0) return GPF_OK;
+  const size_t smem = ((size_t)n * p + n) * sizeof(double);
+  if (smem > smem_limit()) { g_err = "gpf_rbf_K: n*p too large for shared memory"; return GPF_ERR_UNSUPPORTED; }
+  CKS(allow_smem(k_rbf_dense, smem));
+  k_rbf_dense<<<batch, NTHR, smem, (cudaStream_t)stream>>>(d_x, n, p, d_log10_sigma, d_log10_ls, d_K);
+  CKS(cudaGetLastError());
+  return GPF_OK;
+}
+
+static int dense_factor_common(const double* d_A, int n, int batch, int maxtries, double add, double* d_out,
+                               double* d_logdet, int* d_status, void* stream, bool inverse) {
+  if (n < 1 || n > GPF_MAX_N || batch < 0 || !d_A || !d_out || !d_status) { g_err = "bad argument (1 <= n <= 512)"; return GPF_ERR_ARG; }
+  if (batch == 0) return GPF_OK;
+  const int NT = (n + TB - 1) / TB;
+  const size_t smem = engine_smem_doubles(NT, 0) * sizeof(double);
+  if (smem > smem_limit()) { g_err = "n too large for the tile engine"; return GPF_ERR_UNSUPPORTED; }
+  int dev = 0, sms = 148;
+  CKS(cudaGetDevice(&dev));
+  CKS(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = std::min(batch, 2 * sms);
+  const size_t stride = (size_t)plt_tiles(NT) * TILE;
+  double* ws = nullptr;
+  CKS(cudaMalloc(&ws, (size_t)grid * stride * sizeof(double)));
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e;
+  if (inverse) {
+    e = allow_smem(k_kinv_dense, smem);
+    if (e == cudaSuccess) {
+      k_kinv_dense<<<grid, NTHR, smem, st>>>(d_A, n, NT, batch, maxtries, add, d_out, d_status, ws, stride);
+      e = cudaGetLastError();
+    }
+  } else {
+    e = allow_smem(k_jitchol_dense, smem);
+    if (e == cudaSuccess) {
+      k_jitchol_dense<<<grid, NTHR, smem, st>>>(d_A, n, NT, batch, maxtries, add, d_out, d_logdet, d_status, ws, stride);
+      e = cudaGetLastError();
+    }
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(ws);
+  if (e != cudaSuccess) { g_err = cudaGetErrorString(e); return GPF_ERR_CUDA; }
+  return GPF_OK;
+}
+
+int gpf_jitchol(const double* d_A, int n, int batch, int maxtries, double* d_L, double* d_logdet, int* d_status,
+                void* stream) {
+  return dense_factor_common(d_A, n, batch, maxtries, 0.0, d_L, d_logdet, d_status, stream, false);
+}
+
+int gpf_kinv(const double* d_A, int n, int batch, double offset, double* d_Ainv, int* d_status, void* stream) {
+  return dense_factor_common(d_A, n, batch, 5, offset, d_Ainv, nullptr, d_status, stream, true);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------------
+int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
+  if (!out || !d) { g_err = "gpf_create: null argument"; return GPF_ERR_ARG; }
+  *out = nullptr;
+  if (d->n < 1 || d->n > GPF_MAX_N || d->p < 1 || d->m < 1 || d->f < 1 || d->P < 1 || d->chains < 1 || !d->h_x || !d->h_y ||
+      !d->h_X || !d->h_group_of_fn || !d->h_slice_w || !d->h_slice_m) {
+    g_err = "gpf_create: bad model description (1 <= n <= 512, positive sizes, non-null arrays)";
+    return GPF_ERR_ARG;
+  }
+  gpf_ctx* c = new gpf_ctx();
+  auto fail = [&](int rc) { g_err = c->err; gpf_destroy(c); return rc; };
+  c->device = d->device;
+  {
+    cudaError_t e = cudaSetDevice(d->device);
+    if (e != cudaSuccess) { c->err = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return fail(GPF_ERR_CUDA); }
+    e = cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, d->device);
+    if (e != cudaSuccess) { c->err = cudaGetErrorString(e); return fail(GPF_ERR_CUDA); }
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { c->err = cudaGetErrorString(e); return fail(GPF_ERR_CUDA); }
+  }
+  CtxDev& v = c->dev;
+  v.n = d->n; v.p = d->p; v.m = d->m; v.f = d->f; v.P = d->P; v.C = d->chains; v.H = 1 + 2 * d->P;
+  v.NT = (d->n + TB - 1) / TB;
+  v.chain_offset = d->chain_offset;
+  v.maxtries = 5;
+  v.offset = d->offset; v.prior_jitter = d->prior_jitter; v.prior_lb = d->prior_lb; v.prior_ub = d->prior_ub;
+  v.k0 = (unsigned)d->seed; v.k1 = (unsigned)(d->seed >> 32);
+  c->group_of_fn.assign(d->h_group_of_fn, d->h_group_of_fn + d->f);
+  c->groups.assign(d->P, {});
+  for (int i = 0; i < d->f; ++i) {
+    const int g = c->group_of_fn[i];
+    if (g < 0 || g >= d->P) { c->err = "gpf_create: group_of_fn out of range"; return fail(GPF_ERR_ARG); }
+    c->groups[g].push_back(i);
+  }
+  c->slice_w.assign(d->h_slice_w, d->h_slice_w + v.H);
+  c->slice_m.assign(d->h_slice_m, d->h_slice_m + v.H);
+  // sampler list in the reference's order (base.py:57-84)
+  c->order.push_back({0, 0});
+  int ngmax = 1;
+  for (int g = 0; g < d->P; ++g) {
+    if (c->groups[g].empty()) { c->err = "gpf_create: empty prior group"; return fail(GPF_ERR_ARG); }
+    for (int fn : c->groups[g]) c->order.push_back({1, fn});
+    c->order.push_back({0, 1 + 2 * g});
+    c->order.push_back({0, 2 + 2 * g});
+    ngmax = std::max(ngmax, (int)c->groups[g].size());
+  }
+  v.NEmax = (ngmax + TB - 1) / TB;
+  c->kinv_valid.assign(d->P, 0);
+  // shared-memory budgets
+  const size_t xsd = (size_t)d->n * d->p + d->n;
+  c->smem_kinv = (engine_smem_doubles(v.NT, 0) + xsd) * sizeof(double);
+  c->smem_fn = (engine_smem_doubles(v.NT, 1) + 3 * (size_t)v.NT * TB + NW * 2 * 32) * sizeof(double);
+  c->smem_prior.resize(d->P);
+  size_t smax = std::max(c->smem_kinv, c->smem_fn);
+  for (int g = 0; g < d->P; ++g) {
+    const int NE = ((int)c->groups[g].size() + TB - 1) / TB;
+    c->smem_prior[g] = (engine_smem_doubles(v.NT, NE) + xsd) * sizeof(double);
+    smax = std::max(smax, c->smem_prior[g]);
+  }
+  if (smax > smem_limit()) {
+    c->err = "gpf_create: n / prior-group size exceed the shared-memory budget of the tile engine";
+    return fail(GPF_ERR_UNSUPPORTED);
+  }
+  {
+    cudaError_t e = allow_smem(k_group_kinv, c->smem_kinv);
+    if (e == cudaSuccess) e = allow_smem(k_function, c->smem_fn);
+    if (e == cudaSuccess) e = allow_smem(k_prior, *std::max_element(c->smem_prior.begin(), c->smem_prior.end()));
+    if (e != cudaSuccess) { c->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return fail(GPF_ERR_CUDA); }
+  }
+  c->grid = std::min(v.C, 2 * c->sms);
+  // device buffers
+  const size_t tstride = (size_t)plt_tiles(v.NT) * TILE;
+  v.ws_stride = tstride + (size_t)v.NEmax * v.NT * TILE;
+  double *dx, *dyT, *dX, *dF, *dh, *dK, *dws;
+  int *dgof, *dgf, *dgo, *dst;
+  unsigned long long* dcn;
+  int rc;
+  if ((rc = dev_alloc(c, &dx, (size_t)d->n * d->p)) || (rc = dev_alloc(c, &dyT, (size_t)d->n * d->m)) ||
+      (rc = dev_alloc(c, &dX, (size_t)d->m * d->f)) || (rc = dev_alloc(c, &dF, (size_t)v.C * d->f * d->n)) ||
+      (rc = dev_alloc(c, &dh, (size_t)v.C * v.H)) || (rc = dev_alloc(c, &dK, (size_t)d->P * v.C * tstride)) ||
+      (rc = dev_alloc(c, &dws, (size_t)c->grid * v.ws_stride)) || (rc = dev_alloc(c, &dgof, (size_t)d->f)) ||
+      (rc = dev_alloc(c, &dgf, (size_t)d->f)) || (rc = dev_alloc(c, &dgo, (size_t)d->P + 1)) ||
+      (rc = dev_alloc(c, &dst, (size_t)v.C)) || (rc = dev_alloc(c, &dcn, (size_t)CNT_N)))
+    return fail(rc);
+  std::vector<double> yT((size_t)d->n * d->m);
+  for (int t = 0; t < d->n; ++t)
+    for (int o = 0; o < d->m; ++o) yT[(size_t)o * d->n + t] = d->h_y[(size_t)t * d->m + o];
+  std::vector<int> gf, go(1, 0);
+  for (int g = 0; g < d->P; ++g) {
+    gf.insert(gf.end(), c->groups[g].begin(), c->groups[g].end());
+    go.push_back((int)gf.size());
+  }
+  cudaError_t e = cudaMemcpy(dx, d->h_x, sizeof(double) * d->n * d->p, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dyT, yT.data(), sizeof(double) * yT.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dX, d->h_X, sizeof(double) * d->m * d->f, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dgof, c->group_of_fn.data(), sizeof(int) * d->f, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dgf, gf.data(), sizeof(int) * gf.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dgo, go.data(), sizeof(int) * go.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemset(dF, 0, sizeof(double) * v.C * d->f * d->n);
+  if (e == cudaSuccess) e = cudaMemset(dh, 0, sizeof(double) * v.C * v.H);
+  if (e == cudaSuccess) e = cudaMemset(dst, 0, sizeof(int) * v.C);
+  if (e == cudaSuccess) e = cudaMemset(dcn, 0, sizeof(unsigned long long) * CNT_N);
+  if (e != cudaSuccess) { c->err = std::string("gpf_create: upload: ") + cudaGetErrorString(e); return fail(GPF_ERR_CUDA); }
+  v.x = dx; v.yT = dyT; v.X = dX; v.F = dF; v.hyper = dh; v.Kinv = dK; v.ws = dws;
+  v.group_of_fn = dgof; v.group_fns = dgf; v.group_off = dgo; v.status = dst; v.counters = dcn;
+  *out = c;
+  return GPF_OK;
+}
+
+void gpf_destroy(gpf_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  collect_profile(c);
+  for (auto e : c->ev_pool) cudaEventDestroy(e);
+  for (void* p : c->allocs) cudaFree(p);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char* gpf_last_error(gpf_ctx* c) { return c ? c->err.c_str() : g_err.c_str(); }
+void* gpf_stream(gpf_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int gpf_sync(gpf_ctx* c) {
+  CK(c, cudaSetDevice(c->device));
+  CK(c, cudaStreamSynchronize(c->stream));
+  return GPF_OK;
+}
+
+int gpf_set_state(gpf_ctx* c, const double* h_F, const double* h_hyper) {
+  CK(c, cudaSetDevice(c->device));
+  const CtxDev& v = c->dev;
+  if (h_F) CK(c, cudaMemcpyAsync(v.F, h_F, sizeof(double) * v.C * v.f * v.n, cudaMemcpyHostToDevice, c->stream));
+  if (h_hyper) {
+    CK(c, cudaMemcpyAsync(v.hyper, h_hyper, sizeof(double) * v.C * v.H, cudaMemcpyHostToDevice, c->stream));
+    std::fill(c->kinv_valid.begin(), c->kinv_valid.end(), 0);
+  }
+  CK(c, cudaStreamSynchronize(c->stream));
+  return GPF_OK;
+}
+
+int gpf_get_state(gpf_ctx* c, double* h_F, double* h_hyper) {
+  CK(c, cudaSetDevice(c->device));
+  const CtxDev& v = c->dev;
+  if (h_F) CK(c, cudaMemcpyAsync(h_F, v.F, sizeof(double) * v.C * v.f * v.n, cudaMemcpyDeviceToHost, c->stream));
+  if (h_hyper) CK(c, cudaMemcpyAsync(h_hyper, v.hyper, sizeof(double) * v.C * v.H, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  return GPF_OK;
+}
+
+double* gpf_device_F(gpf_ctx* c) { return c->dev.F; }
+double* gpf_device_hyper(gpf_ctx* c) { return c->dev.hyper; }
+
+int gpf_invalidate(gpf_ctx* c) {   // call after writing gpf_device_hyper() directly
+  std::fill(c->kinv_valid.begin(), c->kinv_valid.end(), 0);
+  return GPF_OK;
+}
+
+int gpf_get_status(gpf_ctx* c, int* h_status, int clear) {
+  CK(c, cudaSetDevice(c->device));
+  std::vector<int> tmp(c->dev.C);
+  CK(c, cudaMemcpyAsync(tmp.data(), c->dev.status, sizeof(int) * c->dev.C, cudaMemcpyDeviceToHost, c->stream));
+  if (clear) CK(c, cudaMemsetAsync(c->dev.status, 0, sizeof(int) * c->dev.C, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  bool bad = false;
+  for (int i = 0; i < c->dev.C; ++i) {
+    if (h_status) h_status[i] = tmp[i];
+    if (tmp[i] < 0) bad = true;
+  }
+  if (bad) { c->err = "not positive definite, even with jitter."; return GPF_ERR_NOT_PD; }
+  return GPF_OK;
+}
+
+int gpf_get_counters(gpf_ctx* c, unsigned long long* h, int clear) {
+  CK(c, cudaSetDevice(c->device));
+  unsigned long long tmp[CNT_N];
+  CK(c, cudaMemcpyAsync(tmp, c->dev.counters, sizeof tmp, cudaMemcpyDeviceToHost, c->stream));
+  if (clear) CK(c, cudaMemsetAsync(c->dev.counters, 0, sizeof tmp, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < 6; ++i) h[i] = tmp[i];
+  return GPF_OK;
+}
+
+int gpf_group_kinv(gpf_ctx* c, int g, double* d_out) {
+  CK(c, cudaSetDevice(c->device));
+  const CtxDev& v = c->dev;
+  if (g < -1 || g >= v.P || (g < 0 && d_out)) { c->err = "gpf_group_kinv: bad group"; return GPF_ERR_ARG; }
+  for (int q = (g < 0 ? 0 : g); q < (g < 0 ? v.P : g + 1); ++q) {
+    int rc = launch_kinv(c, q);
+    if (rc) return rc;
+  }
+  if (d_out) {
+    const size_t tstride = (size_t)plt_tiles(v.NT) * TILE;
+    k_tiles_to_dense<<<std::min(v.C, 1024), NTHR, 0, c->stream>>>(v.Kinv + (size_t)g * v.C * tstride, tstride, v.n, v.NT, v.C,
+                                                                d_out, 1);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+  }
+  return GPF_OK;
+}
+
+int gpf_function_step(gpf_ctx* c, int fn, unsigned sampler_id, unsigned sweep, const double* d_z_inject, double* d_mu_out,
+                      double* d_LA_out, double* d_mt_out, double* d_nt_out) {
+  CK(c, cudaSetDevice(c->device));
+  if (fn < 0 || fn >= c->dev.f) { c->err = "gpf_function_step: bad function index"; return GPF_ERR_ARG; }
+  return launch_function(c, fn, sampler_id, sweep, d_z_inject, FnOut{d_mu_out, d_LA_out, d_mt_out, d_nt_out});
+}
+
+int gpf_obs_loglik(gpf_ctx* c, const double* d_cand, double* d_out) {
+  CK(c, cudaSetDevice(c->device));
+  if (!d_cand || !d_out) { c->err = "gpf_obs_loglik: null argument"; return GPF_ERR_ARG; }
+  return launch_slice(c, 0, 0, d_cand, d_out, 0, 0, nullptr, 0, nullptr);
+}
+
+int gpf_prior_loglik(gpf_ctx* c, int g, int which, const double* d_cand, double* d_out) {
+  CK(c, cudaSetDevice(c->device));
+  if (g < 0 || g >= c->dev.P || which < 0 || which > 1 || !d_cand || !d_out) { c->err = "gpf_prior_loglik: bad argument"; return GPF_ERR_ARG; }
+  return launch_slice(c, 1 + 2 * g + which, 0, d_cand, d_out, 0, 0, nullptr, 0, nullptr);
+}
+
+int gpf_slice_step(gpf_ctx* c, int h, unsigned sampler_id, unsigned sweep, const double* d_u_inject, int n_inject,
+                   int* d_nevals_out) {
+  CK(c, cudaSetDevice(c->device));
+  if (h < 0 || h >= c->dev.H) { c->err = "gpf_slice_step: bad hyper-parameter index"; return GPF_ERR_ARG; }
+  return launch_slice(c, h, 1, nullptr, nullptr, sampler_id, sweep, d_u_inject, d_u_inject ? n_inject : 0, d_nevals_out);
+}
+
+int gpf_n_samplers(gpf_ctx* c) { return (int)c->order.size(); }
+
+int gpf_sweep(gpf_ctx* c, int n_sweeps, int thin, unsigned sweep0, const int* h_order, double* d_history,
+              long long history_capacity_rows, long long* rows_out) {
+  CK(c, cudaSetDevice(c->device));
+  const CtxDev& v = c->dev;
+  const int ns = (int)c->order.size();
+  const size_t cols = (size_t)v.H + (size_t)v.f * v.n;
+  long long rows = 0;
+  if (h_order)
+    for (long long i = 0; i < (long long)n_sweeps * ns; ++i)
+      if (h_order[i] < 0 || h_order[i] >= ns) { c->err = "gpf_sweep: sampler id out of range in h_order"; return GPF_ERR_ARG; }
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  if (c->profile) {
+    for (double& m : c->ms) m = 0.0;
+    cudaEventCreate(&t0); cudaEventCreate(&t1);
+    cudaEventRecord(t0, c->stream);
+  }
+  for (int s = 0; s < n_sweeps; ++s) {
+    const unsigned sweep = sweep0 + (unsigned)s;
+    for (int k = 0; k < ns; ++k) {
+      const int sid = h_order ? h_order[(size_t)s * ns + k] : k;
+      const Samp& sp = c->order[sid];
+      int rc;
+      if (sp.kind == 1) rc = launch_function(c, sp.arg, (unsigned)sid, sweep, nullptr, FnOut{nullptr, nullptr, nullptr, nullptr});
+      else rc = launch_slice(c, sp.arg, 1, nullptr, nullptr, (unsigned)sid, sweep, nullptr, 0, nullptr);
+      if (rc) return rc;
+    }
+    if (d_history && (thin <= 0 || (s + 1) % thin == 0)) {
+      if (rows >= history_capacity_rows) { c->err = "gpf_sweep: history buffer full"; return GPF_ERR_ARG; }
+      Timer t(c, 5);
+      double* row = d_history + (size_t)rows * v.C * cols;
+      CK(c, cudaMemcpy2DAsync(row, cols * sizeof(double), v.hyper, v.H * sizeof(double), v.H * sizeof(double), v.C,
+                              cudaMemcpyDeviceToDevice, c->stream));
+      CK(c, cudaMemcpy2DAsync(row + v.H, cols * sizeof(double), v.F, (size_t)v.f * v.n * sizeof(double),
+                              (size_t)v.f * v.n * sizeof(double), v.C, cudaMemcpyDeviceToDevice, c->stream));
+      ++rows;
+    }
+  }
+  if (rows_out) *rows_out = rows;
+  if (c->profile) {
+    cudaEventRecord(t1, c->stream);
+    cudaEventSynchronize(t1);
+    float t = 0.f;
+    cudaEventElapsedTime(&t, t0, t1);
+    collect_profile(c);
+    c->ms[0] = t;
+    cudaEventDestroy(t0); cudaEventDestroy(t1);
+  }
+  return GPF_OK;
+}
+
+int gpf_set_profile(gpf_ctx* c, int on) { c->profile = on != 0; return GPF_OK; }
+
+int gpf_get_profile(gpf_ctx* c, double* h_ms6, unsigned long long* h_launches) {
+  if (h_ms6) for (int i = 0; i < 6; ++i) h_ms6[i] = c->ms[i];
+  if (h_launches) *h_launches = c->launches;
+  return GPF_OK;
+}
+
+}  // extern "C"

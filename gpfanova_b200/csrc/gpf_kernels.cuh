@@ -1,0 +1,443 @@
+// Kernels of the Gibbs hot path.  One CTA (NTHR threads) works on one chain at a time (grid-stride over chains);
+// every n x n matrix is factorised by the tile engine (gpf_tile.cuh) in a per-CTA workspace that stays L2-resident.
+#pragma once
+#include "gpf_common.cuh"
+
+namespace gpf {
+
+// shared-memory carve-up common to all kernels: [engine | extra]
+__device__ __forceinline__ double* smem_base() {
+  extern __shared__ __align__(16) double gpf_smem[];
+  return gpf_smem;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Stateless operators (dense row-major in/out)
+// ---------------------------------------------------------------------------------------------------------
+
+// RBF.dist + RBF._K (kernel/rbf.pyx:8-19) with 10** of kernel.pyx:35-37.  grid.x = batch, dense output.
+__global__ void __launch_bounds__(NTHR) k_rbf_dense(const double* __restrict__ x, int n, int p,
+                                                     const double* __restrict__ lsig, const double* __restrict__ lls,
+                                                     double* __restrict__ K) {
+  double* xs = smem_base();
+  double* xsq = xs + (size_t)n * p;
+  const int b = blockIdx.x;
+  const double sigma = exp10(lsig[b]), ls = exp10(lls[b]);
+  rbf_scale_inputs(x, n, p, ls, xs, xsq);
+  __syncthreads();
+  double* out = K + (size_t)b * n * n;
+  for (size_t e = threadIdx.x; e < (size_t)n * n; e += NTHR) {
+    const int R = (int)(e / n), Cc = (int)(e % n);
+    out[e] = rbf_elem(xs, xsq, n, p, sigma, R, Cc);
+  }
+}
+
+// mean of the diagonal of a dense matrix + any non-positive flag (linalg.py:41-44); all threads get the results
+__device__ inline double dense_diag_mean(const double* A, int n, double* red, bool& nonpos) {
+  double s = 0.0, bad = 0.0;
+  for (int t = threadIdx.x; t < n; t += NTHR) {
+    const double d = A[(size_t)t * n + t];
+    s += d;
+    if (d <= 0.0) bad += 1.0;
+  }
+  s = block_sum(s, red);
+  bad = block_sum(bad, red);
+  nonpos = bad > 0.0;
+  return s / n;
+}
+
+// linalg.jitchol (linalg.py:35-54) per matrix; ws: grid.x workspaces of plt_tiles(NT) tiles.
+__global__ void __launch_bounds__(NTHR, 2) k_jitchol_dense(const double* __restrict__ A, int n, int NT, int batch,
+                                                           int maxtries, double add_diag, double* __restrict__ L,
+                                                           double* __restrict__ logdet, int* __restrict__ status,
+                                                           double* ws, size_t ws_stride) {
+  EngineSmem sm(smem_base(), NT, 0);
+  double* W = ws + (size_t)blockIdx.x * ws_stride;
+  for (int b = blockIdx.x; b < batch; b += gridDim.x) {
+    const double* Ab = A + (size_t)b * n * n;
+    int tries = 0, code = 0;
+    double jitter = 0.0;
+    for (;;) {
+      __syncthreads();
+      dense_to_tiles(Ab, n, NT, W);
+      for (int t = threadIdx.x; t < NT * TB; t += NTHR) sm.dvec[t] = (t < n) ? add_diag + jitter : 0.0;
+      __syncthreads();
+      EngineIO io{W, W, nullptr, RowSrc{nullptr, nullptr, 0, 0, 0}, nullptr, 0};
+      if (chol_engine<AUG_NONE, true>(io, NT, 0, 0, sm)) { code = tries; break; }
+      if (tries == 0) {
+        bool nonpos;
+        const double dm = dense_diag_mean(Ab, n, sm.red(), nonpos) + add_diag;
+        if (nonpos) { code = GPF_STATUS_NONPOS_DIAG; break; }
+        jitter = dm * 1e-6;
+      } else jitter *= 10.0;
+      ++tries;
+      if (tries > maxtries || !isfinite(jitter)) { code = GPF_STATUS_NOT_PD; break; }
+    }
+    __syncthreads();
+    if (code >= 0) {
+      tiles_to_dense(W, n, NT, L + (size_t)b * n * n, 0);
+      if (threadIdx.x == 0 && logdet) logdet[b] = sm.scal[0];
+    } else if (threadIdx.x == 0 && logdet) logdet[b] = nan("");
+    if (threadIdx.x == 0) status[b] = code;
+  }
+}
+
+// Kernel.K_inv (kernel/kernel.pyx:51-64) on dense input: (A + offset I)^-1 through jitchol + in-place inversion
+__global__ void __launch_bounds__(NTHR, 2) k_kinv_dense(const double* __restrict__ A, int n, int NT, int batch,
+                                                        int maxtries, double offset, double* __restrict__ Ainv,
+                                                        int* __restrict__ status, double* ws, size_t ws_stride) {
+  EngineSmem sm(smem_base(), NT, 0);
+  double* W = ws + (size_t)blockIdx.x * ws_stride;
+  for (int b = blockIdx.x; b < batch; b += gridDim.x) {
+    const double* Ab = A + (size_t)b * n * n;
+    int tries = 0, code = 0;
+    double jitter = 0.0;
+    for (;;) {
+      __syncthreads();
+      dense_to_tiles(Ab, n, NT, W);
+      for (int t = threadIdx.x; t < NT * TB; t += NTHR) sm.dvec[t] = (t < n) ? offset + jitter : 0.0;
+      __syncthreads();
+      EngineIO io{W, W, nullptr, RowSrc{nullptr, nullptr, 0, 0, 0}, nullptr, 0};
+      if (chol_engine<AUG_IDENT, false>(io, NT, 0, 0, sm)) { code = tries; break; }
+      if (tries == 0) {
+        bool nonpos;
+        const double dm = dense_diag_mean(Ab, n, sm.red(), nonpos) + offset;
+        if (nonpos) { code = GPF_STATUS_NONPOS_DIAG; break; }
+        jitter = dm * 1e-6;
+      } else jitter *= 10.0;
+      ++tries;
+      if (tries > maxtries || !isfinite(jitter)) { code = GPF_STATUS_NOT_PD; break; }
+    }
+    __syncthreads();
+    if (code >= 0) tiles_to_dense(W, n, NT, Ainv + (size_t)b * n * n, 1);
+    if (threadIdx.x == 0) status[b] = code;
+  }
+}
+
+// packed tiles of one chain -> dense symmetric (inspection output of gpf_group_kinv / L_A of gpf_function_step)
+__global__ void __launch_bounds__(NTHR) k_tiles_to_dense(const double* tiles, size_t tile_stride, int n, int NT, int batch,
+                                                         double* __restrict__ out, int mode) {
+  for (int b = blockIdx.x; b < batch; b += gridDim.x)
+    tiles_to_dense(tiles + (size_t)b * tile_stride, n, NT, out + (size_t)b * n * n, mode);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Kernel.K_inv of prior group g for every chain at the current hyper-parameters
+//   kernel/kernel.pyx:51-64 (K + 1e-9 I, jitchol, L^-T L^-1) with rbf.pyx:16-19 generated on chip.
+// The inverse is built in place in its destination (c.Kinv), never as a separate L / L^-1.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHR, 2) k_group_kinv(CtxDev c, int g) {
+  EngineSmem sm(smem_base(), c.NT, 0);
+  double* xs = smem_base() + engine_smem_doubles(c.NT, 0);
+  double* xsq = xs + (size_t)c.n * c.p;
+  const size_t tstride = (size_t)plt_tiles(c.NT) * TILE;
+  for (int ch = blockIdx.x; ch < c.C; ch += gridDim.x) {
+    const double sigma = exp10(c.hyper[(size_t)ch * c.H + 1 + 2 * g]);
+    const double ls = exp10(c.hyper[(size_t)ch * c.H + 2 + 2 * g]);
+    double* W = c.Kinv + ((size_t)g * c.C + ch) * tstride;
+    __syncthreads();
+    rbf_scale_inputs(c.x, c.n, c.p, ls, xs, xsq);
+    int tries = 0, code = 0;
+    double jitter = 0.0;
+    for (;;) {
+      __syncthreads();
+      rbf_fill_tiles(W, c.NT, c.n, c.p, xs, xsq, sigma, sm.red());
+      for (int t = threadIdx.x; t < c.NT * TB; t += NTHR) sm.dvec[t] = (t < c.n) ? c.offset + jitter : 0.0;
+      __syncthreads();
+      EngineIO io{W, W, nullptr, RowSrc{nullptr, nullptr, 0, 0, 0}, nullptr, 0};
+      if (chol_engine<AUG_IDENT, false>(io, c.NT, 0, 0, sm)) { code = tries; break; }
+      // jitchol ladder (linalg.py:41-54): diag(K + offset I) = sigma + offset everywhere
+      const double dm = sigma + c.offset;
+      if (tries == 0) {
+        if (!(dm > 0.0)) { code = GPF_STATUS_NONPOS_DIAG; break; }
+        jitter = dm * 1e-6;
+      } else jitter *= 10.0;
+      ++tries;
+      if (tries > c.maxtries || !isfinite(jitter)) { code = GPF_STATUS_NOT_PD; break; }
+    }
+    if (threadIdx.x == 0) {
+      status_merge(c.status + ch, code);
+      atomicAdd(c.counters + CNT_CHOL, 1ull + (unsigned long long)tries);
+      atomicAdd(c.counters + CNT_INV, 1ull);
+      if (tries) atomicAdd(c.counters + CNT_JITTER, (unsigned long long)tries);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Function._sample (sample/function.py:14-40) + base.functionResidual (base.py:180-190), fused:
+//   m_t, n_t  ->  A = K_inv + diag(n_t)/(sigma_y + offset), b = m_t/(sigma_y + offset)  ->  L_A = jitchol(A) with
+//   w = L_A^-1 b riding along  ->  mu = L_A^-T w, beta = L_A^-T (w + z)  (draw contract: beta = mu + L_A^-T z).
+// ---------------------------------------------------------------------------------------------------------
+struct FnOut { double *mu, *LA, *mt, *nt; };
+
+__global__ void __launch_bounds__(NTHR, 2) k_function(CtxDev c, int fn, unsigned sampler_id, unsigned sweep,
+                                                      const double* __restrict__ z_inject, FnOut out) {
+  const int NT = c.NT, n = c.n, npad = NT * TB;
+  EngineSmem sm(smem_base(), NT, 1);
+  double* xs = smem_base() + engine_smem_doubles(NT, 1);   // 2 x npad: w -> mu, w+z -> beta
+  double* brow = xs + 2 * npad;                            // npad
+  double* red = brow + npad;                               // NW*2*32
+  const int g = c.group_of_fn[fn];
+  const size_t tstride = (size_t)plt_tiles(NT) * TILE;
+  double* W = c.ws + (size_t)blockIdx.x * c.ws_stride;
+  double* Wx = W + tstride;
+  const Stream rng{c.k0, c.k1};
+  for (int ch = blockIdx.x; ch < c.C; ch += gridDim.x) {
+    const double* Fc = c.F + (size_t)ch * c.f * n;
+    const double* A0 = c.Kinv + ((size_t)g * c.C + ch) * tstride;
+    const double yinv = 1.0 / (exp10(c.hyper[(size_t)ch * c.H]) + c.offset);   // white.py:7-9 through kernel.pyx:51-64
+    __syncthreads();
+    // ---- residual projection (base.py:180-190, function.py:16-25) ----
+    for (int t = threadIdx.x; t < npad; t += NTHR) {
+      double mt = 0.0, nt = 0.0;
+      if (t < n) {
+        for (int o = 0; o < c.m; ++o) {
+          const double xf = c.X[o * c.f + fn];
+          if (xf == 0.0) continue;
+          const double yv = c.yT[(size_t)o * n + t];
+          if (isnan(yv)) continue;
+          double pred = 0.0;
+          for (int q = 0; q < c.f; ++q)
+            if (q != fn) pred = fma(c.X[o * c.f + q], Fc[(size_t)q * n + t], pred);
+          mt = fma(xf, yv - pred, mt);
+          nt = fma(xf, xf, nt);
+        }
+        if (out.mt) out.mt[(size_t)ch * n + t] = mt;
+        if (out.nt) out.nt[(size_t)ch * n + t] = nt;
+      }
+      sm.dvec[t] = (t < n) ? nt * yinv : 0.0;   // function.py:30
+      brow[t] = (t < n) ? yinv * mt : 0.0;      // function.py:32
+      xs[t] = 0.0;
+      xs[npad + t] = 0.0;
+    }
+    int tries = 0, code = 0;
+    double jitter = 0.0;
+    for (;;) {
+      __syncthreads();
+      EngineIO io{A0, W, Wx, RowSrc{brow, nullptr, npad, 1, n}, xs, npad};
+      if (chol_engine<AUG_RHS, true>(io, NT, 1, 1, sm)) { code = tries; break; }
+      // jitchol ladder on A (linalg.py:41-54)
+      if (tries == 0) {
+        double s = 0.0, bad = 0.0;
+        for (int t = threadIdx.x; t < n; t += NTHR) {
+          const double d = A0[(size_t)plt(t >> 5, t >> 5) * TILE + (t & 31) * TB + (t & 31)] + sm.dvec[t];
+          s += d;
+          if (d <= 0.0) bad += 1.0;
+        }
+        s = block_sum(s, sm.red());
+        bad = block_sum(bad, sm.red());
+        if (bad > 0.0) { code = GPF_STATUS_NONPOS_DIAG; break; }
+        jitter = s / n * 1e-6;
+        for (int t = threadIdx.x; t < n; t += NTHR) sm.dvec[t] += jitter;
+      } else {
+        for (int t = threadIdx.x; t < n; t += NTHR) sm.dvec[t] += 9.0 * jitter;
+        jitter *= 10.0;
+      }
+      ++tries;
+      if (tries > c.maxtries || !isfinite(jitter)) { code = GPF_STATUS_NOT_PD; break; }
+    }
+    __syncthreads();
+    if (code >= 0) {
+      // ---- z: injected or Philox Box-Muller (counter = (pair, sampler, sweep, chain)) ----
+      if (z_inject) {
+        for (int t = threadIdx.x; t < n; t += NTHR) xs[npad + t] = xs[t] + z_inject[(size_t)ch * n + t];
+      } else {
+        for (int pr = threadIdx.x; 2 * pr < n; pr += NTHR) {
+          double z0, z1;
+          rng.normal_pair((unsigned)(ch + c.chain_offset), sweep, sampler_id, (unsigned)pr, z0, z1);
+          xs[npad + 2 * pr] = xs[2 * pr] + z0;
+          if (2 * pr + 1 < n) xs[npad + 2 * pr + 1] = xs[2 * pr + 1] + z1;
+        }
+      }
+      __syncthreads();
+      back_solve<2>(W, NT, xs, npad, sm, red);
+      for (int t = threadIdx.x; t < n; t += NTHR) {
+        c.F[((size_t)ch * c.f + fn) * n + t] = xs[npad + t];
+        if (out.mu) out.mu[(size_t)ch * n + t] = xs[t];
+      }
+      if (out.LA) tiles_to_dense(W, n, NT, out.LA + (size_t)ch * n * n, 0);
+    }
+    if (threadIdx.x == 0) {
+      status_merge(c.status + ch, code);
+      atomicAdd(c.counters + CNT_CHOL, 1ull + (unsigned long long)tries);
+      atomicAdd(c.counters + CNT_DRAW, 1ull);
+      if (tries) atomicAdd(c.counters + CNT_JITTER, (unsigned long long)tries);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Base.observationLikelihood (base.py:196-214): the sum of squared residuals is computed once per chain, after
+// which every candidate is O(1):  -N (log sd + log(2 pi)/2) - SSE / (2 sd^2) + log U(lb,ub)(sd),  sd = sqrt(10^x).
+// mode 0: evaluate at cand[ch] -> out[ch].   mode 1: slice step on y_sigma (sample/slice.pyx:24-62).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double obs_loglik_eval(double sse, double nobs, double x, double lb, double ub) {
+  const double sd = sqrt(exp10(x));
+  if (sd < lb || sd > ub) return -(double)INFINITY;
+  return -0.5 * sse / (sd * sd) - nobs * (log(sd) + 0.5 * LOG2PI) - log(ub - lb);
+}
+
+__global__ void __launch_bounds__(NTHR) k_obs(CtxDev c, int mode, const double* __restrict__ cand, double* __restrict__ outv,
+                                              double w, int mstep, unsigned sampler_id, unsigned sweep,
+                                              const double* __restrict__ u_inject, int n_inject, int* __restrict__ nevals) {
+  __shared__ double red[NW];
+  const int n = c.n;
+  const Stream rng{c.k0, c.k1};
+  for (int ch = blockIdx.x; ch < c.C; ch += gridDim.x) {
+    const double* Fc = c.F + (size_t)ch * c.f * n;
+    double sse = 0.0, cnt = 0.0;
+    for (int t = threadIdx.x; t < n; t += NTHR) {
+      for (int o = 0; o < c.m; ++o) {
+        const double yv = c.yT[(size_t)o * n + t];
+        if (isnan(yv)) continue;
+        double pred = 0.0;
+        for (int q = 0; q < c.f; ++q) pred = fma(c.X[o * c.f + q], Fc[(size_t)q * n + t], pred);
+        const double r = yv - pred;
+        sse = fma(r, r, sse);
+        cnt += 1.0;
+      }
+    }
+    sse = block_sum(sse, red);
+    cnt = block_sum(cnt, red);
+    if (mode == 0) {
+      if (threadIdx.x == 0) outv[ch] = obs_loglik_eval(sse, cnt, cand[ch], c.prior_lb, c.prior_ub);
+    } else {
+      const unsigned gch = (unsigned)(ch + c.chain_offset);
+      int nev;
+      const double x0 = c.hyper[(size_t)ch * c.H];
+      const double x1 = slice_step(
+          x0, w, mstep, [&](double v) { return obs_loglik_eval(sse, cnt, v, c.prior_lb, c.prior_ub); },
+          [&](int k) { return (u_inject && k < n_inject) ? u_inject[(size_t)ch * n_inject + k] : rng.uniform(gch, sweep, sampler_id, (unsigned)k); },
+          nev);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        c.hyper[(size_t)ch * c.H] = x1;
+        if (nevals) nevals[ch] = nev;
+        atomicAdd(c.counters + CNT_LOGP, (unsigned long long)nev);
+        atomicAdd(c.counters + CNT_SLICE, 1ull);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Base.prior_likelihood (base.py:216-243) and the slice steps on prior{g}_sigma / prior{g}_lengthscale.
+//   cov = K(sigma, ls) + mean(K) 1e-6 I;  ll = 1 + sum_{f in g} log N(beta_f; 0, cov) + log U(lb,ub)(cand)
+// Every evaluation that changes the lengthscale is one factorisation with the group's functions riding along as
+// right-hand sides (quadratic forms) and the log-determinant from the pivots.  Candidates that only change sigma
+// rescale cov exactly, cov(s') = (s'/s) cov(s), so they cost O(1) after one factorisation.
+// mode 0: evaluate cand[ch] -> out[ch].  mode 1: slice step on hyper-parameter 1+2g+which.
+// ---------------------------------------------------------------------------------------------------------
+struct PriorEval {
+  const CtxDev& c;
+  const EngineSmem& sm;
+  double *xs, *xsq, *W, *Wx;
+  int g, ch, ng, NE, nti_last;
+  const int* fns;
+  int nfact;     // factorisations executed
+  int failed;    // a factorisation met a non-positive pivot
+
+  // log N terms at (lsig, lls): returns logdet and total quadratic form through references; false if not PD
+  __device__ __noinline__ bool factor(double lsig, double lls, double& logdet, double& quad) {
+    const int n = c.n, NT = c.NT;
+    __syncthreads();
+    rbf_scale_inputs(c.x, n, c.p, exp10(lls), xs, xsq);
+    __syncthreads();
+    const double tot = rbf_fill_tiles(W, NT, n, c.p, xs, xsq, exp10(lsig), sm.red());
+    const double jit = tot / ((double)n * (double)n) * c.prior_jitter;   // base.py:222
+    for (int t = threadIdx.x; t < NT * TB; t += NTHR) sm.dvec[t] = (t < n) ? jit : 0.0;
+    __syncthreads();
+    EngineIO io{W, W, Wx, RowSrc{c.F + (size_t)ch * c.f * n, fns, n, ng, n}, nullptr, 0};
+    ++nfact;
+    const bool ok = chol_engine<AUG_RHS, false>(io, NT, NE, nti_last, sm);
+    if (!ok) { failed = 1; return false; }
+    logdet = sm.scal[0];
+    quad = engine_quad_total(sm, NT, NE);
+    return true;
+  }
+  __device__ double prior_ll(double cand) const {
+    if (cand < c.prior_lb || cand > c.prior_ub) return -(double)INFINITY;
+    return -log(c.prior_ub - c.prior_lb);
+  }
+  __device__ double assemble(double logdet, double quad, double cand) const {
+    // base.py:235-243:  1 + sum_f [-(n log 2pi + logdet + quad_f)/2] + priorll
+    return 1.0 - 0.5 * ((double)ng * ((double)c.n * LOG2PI + logdet) + quad) + prior_ll(cand);
+  }
+};
+
+__global__ void __launch_bounds__(NTHR, 2) k_prior(CtxDev c, int g, int which, int mode, const double* __restrict__ cand,
+                                                   double* __restrict__ outv, double w, int mstep, unsigned sampler_id,
+                                                   unsigned sweep, const double* __restrict__ u_inject, int n_inject,
+                                                   int* __restrict__ nevals) {
+  const int NT = c.NT, n = c.n;
+  const int ng = c.group_off[g + 1] - c.group_off[g];
+  const int NE = (ng + TB - 1) / TB;
+  const int rem = ng - (NE - 1) * TB;
+  EngineSmem sm(smem_base(), NT, NE);
+  double* xs = smem_base() + engine_smem_doubles(NT, NE);
+  double* xsq = xs + (size_t)n * c.p;
+  double* W = c.ws + (size_t)blockIdx.x * c.ws_stride;
+  const Stream rng{c.k0, c.k1};
+  for (int ch = blockIdx.x; ch < c.C; ch += gridDim.x) {
+    PriorEval pe{c, sm, xs, xsq, W, W + (size_t)plt_tiles(NT) * TILE, g, ch, ng, NE, (rem + 7) / 8,
+                 c.group_fns + c.group_off[g], 0, 0};
+    const double cur_s = c.hyper[(size_t)ch * c.H + 1 + 2 * g];
+    const double cur_l = c.hyper[(size_t)ch * c.H + 2 + 2 * g];
+    int nev = 0;
+    if (which == 0) {
+      // sigma: factor once at the chain's current sigma, rescale for every candidate
+      double ld0 = 0.0, q0 = 0.0;
+      const bool ok = pe.factor(cur_s, cur_l, ld0, q0);
+      auto lp = [&](double v) -> double {
+        if (!ok) return -(double)INFINITY;
+        if (v < c.prior_lb || v > c.prior_ub) return -(double)INFINITY;
+        const double dl = v - cur_s;                       // log10(s'/s)
+        return pe.assemble(ld0 + (double)n * LN10 * dl, q0 * exp10(-dl), v);
+      };
+      if (mode == 0) {
+        if (threadIdx.x == 0) outv[ch] = lp(cand[ch]);
+      } else {
+        const unsigned gch = (unsigned)(ch + c.chain_offset);
+        const double x1 = slice_step(
+            cur_s, w, mstep, lp,
+            [&](int k) { return (u_inject && k < n_inject) ? u_inject[(size_t)ch * n_inject + k] : rng.uniform(gch, sweep, sampler_id, (unsigned)k); },
+            nev);
+        __syncthreads();
+        if (threadIdx.x == 0) c.hyper[(size_t)ch * c.H + 1 + 2 * g] = x1;
+      }
+    } else {
+      auto lp = [&](double v) -> double {
+        if (v < c.prior_lb || v > c.prior_ub) return -(double)INFINITY;   // base.py:224-231 (no factorisation needed)
+        double ld, q;
+        if (!pe.factor(cur_s, v, ld, q)) return -(double)INFINITY;
+        return pe.assemble(ld, q, v);
+      };
+      if (mode == 0) {
+        const double v = lp(cand[ch]);
+        if (threadIdx.x == 0) outv[ch] = v;
+      } else {
+        const unsigned gch = (unsigned)(ch + c.chain_offset);
+        const double x1 = slice_step(
+            cur_l, w, mstep, lp,
+            [&](int k) { return (u_inject && k < n_inject) ? u_inject[(size_t)ch * n_inject + k] : rng.uniform(gch, sweep, sampler_id, (unsigned)k); },
+            nev);
+        __syncthreads();
+        if (threadIdx.x == 0) c.hyper[(size_t)ch * c.H + 2 + 2 * g] = x1;
+      }
+    }
+    if (threadIdx.x == 0) {
+      if (pe.failed) status_merge(c.status + ch, GPF_STATUS_NOT_PD);
+      atomicAdd(c.counters + CNT_CHOL, (unsigned long long)pe.nfact);
+      if (mode == 1) {
+        if (nevals) nevals[ch] = nev;
+        atomicAdd(c.counters + CNT_LOGP, (unsigned long long)nev);
+        atomicAdd(c.counters + CNT_SLICE, 1ull);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace gpf

@@ -36,6 +36,7 @@ __host__ __device__ __forceinline__ double u01(uint32_t hi, uint32_t lo) {
 struct Stream {
   uint32_t k0, k1;
   __host__ __device__ Stream(uint64_t seed) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
+  __host__ __device__ Stream(uint32_t a, uint32_t b) : k0(a), k1(b) {}
   __device__ __forceinline__ double uniform(uint32_t chain, uint32_t sweep, uint32_t sampler, uint32_t draw) const {
     Philox4 r = philox4x32_10(draw, sampler, sweep, chain, k0, k1);
     return u01(r.x, r.y);

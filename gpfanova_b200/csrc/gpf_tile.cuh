@@ -4,7 +4,10 @@
 //               -> forward solves / quadratic forms for free (slice log-likelihoods, base.py:233-238;
 //               b of function.py:32)
 //   AUG_IDENT : identity rows come out as U = L^-T; the engine accumulates U U^T = (L L^T)^-1
-//               tile by tile -> Kernel.K_inv (kernel/kernel.pyx:51-64)
+//               tile by tile -> Kernel.K_inv (kernel/kernel.pyx:51-64).  Fully in place: at step k
+//               the live tiles are trailing A(i,j) (i>=j>k) at plt(i,j), pending U(e,j) (e<=k<j) at
+//               plt(j,e) (the slot of the dead panel tile L(j,e)) and partial inverse tiles (a,b)
+//               (b<=a<=k) at plt(a,b) -- always exactly NT(NT+1)/2 tiles.
 // Matrix tiles are 32x32 FP64, row-major, packed lower-triangular by tile (plt), kept in a per-CTA
 // global workspace that stays L2-resident (one slot per persistent CTA); the current panel lives in
 // shared memory.  Trailing updates are mma.sync m8n8k4 f64 (DMMA.8x8x4 on sm_100a: measured
@@ -214,8 +217,8 @@ struct EngineSmem {
 struct EngineIO {
   const double* A0;   // first-touch source of the matrix tiles (plt layout, padded rows = identity); may alias W
   double* W;          // plt_tiles(NT) tiles of workspace; with KEEPL the final L tiles are left there
-  double* Wx;         // AUG_RHS: NE*NT tiles; AUG_IDENT: NT*NT tiles
-  double* Kout;       // AUG_IDENT: plt_tiles(NT) output tiles of (L L^T)^-1 (lower tiles, full diagonal tiles)
+  double* Wx;         // AUG_RHS: NE*NT tiles of in-flight right-hand-side rows.  AUG_IDENT: unused; the inverse
+                      // (lower tiles, full diagonal tiles) is left in W
   RowSrc rows;        // AUG_RHS: first-touch source of the extra rows
   double* vout;       // AUG_RHS: finished rows r < rows.nrows are written to vout[r*ldv + col] (may be nullptr)
   int ldv;
@@ -277,12 +280,16 @@ __device__ bool chol_engine(const EngineIO& io, int NT, int NE, int nti_last, co
 #pragma unroll
             for (int c = 0; c < 32; ++c) a[c] = io.rows.at(e * TB + lane, c);
           } else rows_load(a, Wx + (size_t)(e * NT + k) * TILE, lane);
+          if (e * TB + lane >= io.rows.nrows) {   // unused rows of the last block: keep them exactly zero
+#pragma unroll
+            for (int c = 0; c < 32; ++c) a[c] = 0.0;
+          }
         } else {
           slot = e;
           if (e == k) {
 #pragma unroll
             for (int c = 0; c < 32; ++c) a[c] = (c == lane) ? 1.0 : 0.0;
-          } else rows_load(a, Wx + (size_t)(e * NT + k) * TILE, lane);
+          } else rows_load(a, W + (size_t)plt(k, e) * TILE, lane);
         }
       }
       trsm_warp(a, sm.D, sm.rinv + k * TB);
@@ -323,7 +330,7 @@ __device__ bool chol_engine(const EngineIO& io, int NT, int NE, int nti_last, co
       } else if (t < T1 + T2) {
         const int u = t - T1;
         const int e = u / nreg, j = k + 1 + (u % nreg);
-        double* wt = Wx + (size_t)(e * NT + j) * TILE;
+        double* wt = (AUG == AUG_RHS) ? Wx + (size_t)(e * NT + j) * TILE : W + (size_t)plt(j, e) * TILE;
         if (AUG == AUG_RHS) {
           const int nti = (e == NE - 1) ? nti_last : 4;
           if (k == 0) cfrag_from_rows(f, io.rows, e * TB, j * TB, g, tig, nti);
@@ -341,7 +348,7 @@ __device__ bool chol_engine(const EngineIO& io, int NT, int NE, int nti_last, co
         int aa = 0, tt = t - T1 - T2;
         while (tt > aa) { tt -= aa + 1; ++aa; }
         const int bb = tt;
-        double* kt = io.Kout + (size_t)plt(aa, bb) * TILE;
+        double* kt = W + (size_t)plt(aa, bb) * TILE;
         if (k == aa) cfrag_zero(f);
         else cfrag_load(f, kt, g, tig, 4);
         tile_mma<false>(f, sm.P + (size_t)aa * TB * PS, sm.P + (size_t)bb * TB * PS, g, tig, 4);

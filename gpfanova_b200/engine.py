@@ -1,0 +1,297 @@
+"""Device engine: C chains of one model on one GPU, driven through the C ABI (include/gpfanova_b200.h).
+
+Host-side counterpart of Base.__init__'s state + SamplerContainer.parameter_cache (base.py:16-86,
+container.py:8-20) with a leading chain axis.  Device memory is held in torch tensors; all arithmetic
+happens in the sm_100a kernels behind the ctypes boundary.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _capi
+
+OFFSET = 1e-9          # kernel/kernel.pyx:7
+PRIOR_JITTER = 1e-6    # base.py:222
+
+
+def _require_cuda(device):
+    if not torch.cuda.is_available():
+        raise RuntimeError("gpfanova_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", device if device is not None else torch.cuda.current_device())
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+# ----------------------------------------------------------------------------------------------
+# stateless batched operators
+# ----------------------------------------------------------------------------------------------
+def rbf_K(x, log10_sigma, log10_lengthscale, device=None):
+    """RBF._K (kernel/rbf.pyx:8-19) for a batch of (sigma, lengthscale) pairs given as log10 values
+    (kernel.pyx:35-37).  x: (n, p).  Returns a (batch, n, n) float64 CUDA tensor."""
+    dev = _require_cuda(device)
+    x = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64)).to(dev)
+    if x.dim() == 1:
+        x = x[:, None]
+    s = torch.as_tensor(np.atleast_1d(np.asarray(log10_sigma, dtype=np.float64))).to(dev)
+    l = torch.as_tensor(np.atleast_1d(np.asarray(log10_lengthscale, dtype=np.float64))).to(dev)
+    assert s.shape == l.shape
+    n, p = x.shape
+    K = torch.empty((s.numel(), n, n), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream().cuda_stream
+        _capi.check(_capi.lib().gpf_rbf_K(_ptr(x), n, p, _ptr(s), _ptr(l), s.numel(), _ptr(K), C.c_void_p(st)))
+    return K
+
+
+def _status_raise(status):
+    st = status.cpu().numpy()
+    if (st == _capi.STATUS_NONPOS_DIAG).any():
+        raise np.linalg.LinAlgError("not pd: non-positive diagonal elements")      # linalg.py:43
+    if (st < 0).any():
+        raise np.linalg.LinAlgError("not positive definite, even with jitter.")    # linalg.py:54
+    return st
+
+
+def jitchol(A, maxtries=5, device=None, return_info=False):
+    """linalg.jitchol (linalg.py:35-54) for a batch of matrices A: (batch, n, n) or (n, n).
+    Returns L (lower, upper zeroed) as a CUDA tensor; raises numpy.linalg.LinAlgError like the reference."""
+    dev = _require_cuda(device)
+    A = torch.as_tensor(A, dtype=torch.float64).to(dev).contiguous()
+    single = A.dim() == 2
+    if single:
+        A = A[None]
+    b, n, _ = A.shape
+    L = torch.empty_like(A)
+    logdet = torch.empty(b, dtype=torch.float64, device=dev)
+    status = torch.zeros(b, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream().cuda_stream
+        _capi.check(_capi.lib().gpf_jitchol(_ptr(A), n, b, maxtries, _ptr(L), _ptr(logdet), _ptr(status), C.c_void_p(st)))
+    tries = _status_raise(status)
+    if return_info:
+        return (L[0] if single else L), (logdet[0] if single else logdet), (tries[0] if single else tries)
+    return L[0] if single else L
+
+
+def kinv(A, offset=OFFSET, device=None):
+    """Kernel.K_inv (kernel/kernel.pyx:51-64) on given matrices: (A + offset I)^-1 through jitchol."""
+    dev = _require_cuda(device)
+    A = torch.as_tensor(A, dtype=torch.float64).to(dev).contiguous()
+    single = A.dim() == 2
+    if single:
+        A = A[None]
+    b, n, _ = A.shape
+    out = torch.empty_like(A)
+    status = torch.zeros(b, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream().cuda_stream
+        _capi.check(_capi.lib().gpf_kinv(_ptr(A), n, b, float(offset), _ptr(out), _ptr(status), C.c_void_p(st)))
+    _status_raise(status)
+    return out[0] if single else out
+
+
+# ----------------------------------------------------------------------------------------------
+# sampler context
+# ----------------------------------------------------------------------------------------------
+class ChainEngine(object):
+    """C chains of  y (n x m) = F (n x f) X^T + noise  on one GPU.
+
+    hyper layout (log10, per chain): [y_sigma, prior0_sigma, prior0_lengthscale, prior1_sigma, ...].
+    Sampler ids (Philox counter word, = position in the reference's sampler list, base.py:57-84):
+    0 = y_sigma; then per group: its functions, prior{g}_sigma, prior{g}_lengthscale.
+    """
+
+    def __init__(self, x, y, X, groups, chains=1, seed=0, device=None, chain_offset=0, slice_w=None, slice_m=None,
+                 prior_lb=-2.0, prior_ub=2.0):
+        self.dev = _require_cuda(device)
+        self.x = np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+        if self.x.ndim == 1:
+            self.x = self.x[:, None]
+        self.y = np.ascontiguousarray(np.asarray(y, dtype=np.float64))
+        self.X = np.ascontiguousarray(np.asarray(X, dtype=np.float64))
+        self.n, self.p = self.x.shape
+        self.m = self.y.shape[1]
+        self.f = self.X.shape[1]
+        assert self.y.shape[0] == self.n and self.X.shape[0] == self.m
+        self.groups = [list(g) for g in groups]
+        self.P = len(self.groups)
+        self.H = 1 + 2 * self.P
+        self.C = int(chains)
+        gof = np.full(self.f, -1, dtype=np.int32)
+        for g, grp in enumerate(self.groups):
+            for i in grp:
+                gof[i] = g
+        assert (gof >= 0).all(), "every function needs a prior group"
+        self.group_of_fn = gof
+        w = np.full(self.H, 0.1) if slice_w is None else np.ascontiguousarray(slice_w, dtype=np.float64)
+        mm = np.full(self.H, 10, dtype=np.int32) if slice_m is None else np.ascontiguousarray(slice_m, dtype=np.int32)
+        # sampler list (kind, arg) in the reference's order
+        self.order = [("slice", 0)]
+        for g, grp in enumerate(self.groups):
+            self.order += [("function", i) for i in grp]
+            self.order += [("slice", 1 + 2 * g), ("slice", 2 + 2 * g)]
+        self.sampler_id = {ka: i for i, ka in enumerate(self.order)}
+        d = _capi.ModelDesc()
+        d.n, d.p, d.m, d.f, d.P = self.n, self.p, self.m, self.f, self.P
+        d.chains, d.device, d.chain_offset, d.seed = self.C, self.dev.index, int(chain_offset), int(seed)
+        d.h_x = self.x.ctypes.data_as(_capi.c_dp)
+        d.h_y = self.y.ctypes.data_as(_capi.c_dp)
+        d.h_X = self.X.ctypes.data_as(_capi.c_dp)
+        d.h_group_of_fn = gof.ctypes.data_as(_capi.c_ip)
+        d.h_slice_w = w.ctypes.data_as(_capi.c_dp)
+        d.h_slice_m = mm.ctypes.data_as(_capi.c_ip)
+        d.offset, d.prior_jitter, d.prior_lb, d.prior_ub = OFFSET, PRIOR_JITTER, float(prior_lb), float(prior_ub)
+        self._lib = _capi.lib()
+        h = C.c_void_p()
+        _capi.check(self._lib.gpf_create(C.byref(h), C.byref(d)))
+        self._h = h
+        self.sweeps_done = 0
+
+    # -- lifetime ------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gpf_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        _capi.check(rc, self._h)
+
+    def sync(self):
+        self._ck(self._lib.gpf_sync(self._h))
+
+    def _new(self, *shape, dtype=torch.float64):
+        return torch.empty(shape, dtype=dtype, device=self.dev)
+
+    def _dev_in(self, a, shape):
+        if a is None:
+            return None
+        t = torch.as_tensor(np.ascontiguousarray(np.asarray(a, dtype=np.float64))).to(self.dev)
+        assert tuple(t.shape) == tuple(shape), (tuple(t.shape), shape)
+        torch.cuda.synchronize(self.dev)
+        return t
+
+    # -- state ---------------------------------------------------------------------------------
+    def set_state(self, F=None, hyper=None):
+        """F: (C, f, n) or (f, n) broadcast to all chains; hyper: (C, H) or (H,)"""
+        Fp = hp = None
+        if F is not None:
+            F = np.broadcast_to(np.asarray(F, dtype=np.float64), (self.C, self.f, self.n))
+            F = np.ascontiguousarray(F)
+            Fp = F.ctypes.data_as(C.c_void_p)
+        if hyper is not None:
+            hyper = np.broadcast_to(np.asarray(hyper, dtype=np.float64), (self.C, self.H))
+            hyper = np.ascontiguousarray(hyper)
+            hp = hyper.ctypes.data_as(C.c_void_p)
+        self._ck(self._lib.gpf_set_state(self._h, Fp, hp))
+
+    def get_state(self):
+        F = np.empty((self.C, self.f, self.n))
+        hyper = np.empty((self.C, self.H))
+        self._ck(self._lib.gpf_get_state(self._h, F.ctypes.data_as(C.c_void_p), hyper.ctypes.data_as(C.c_void_p)))
+        return F, hyper
+
+    def status(self, clear=True, raise_on_error=True):
+        st = np.zeros(self.C, dtype=np.int32)
+        rc = self._lib.gpf_get_status(self._h, st.ctypes.data_as(C.c_void_p), int(clear))
+        if rc == _capi.ERR_NOT_PD:
+            if raise_on_error:
+                bad = np.nonzero(st < 0)[0]
+                what = ("not pd: non-positive diagonal elements" if (st[bad] == _capi.STATUS_NONPOS_DIAG).any()
+                        else "not positive definite, even with jitter.")
+                raise np.linalg.LinAlgError("%s (chains %s)" % (what, bad[:8].tolist()))
+        else:
+            self._ck(rc)
+        return st
+
+    def counters(self, clear=False):
+        c = np.zeros(6, dtype=np.uint64)
+        self._ck(self._lib.gpf_get_counters(self._h, c.ctypes.data_as(C.c_void_p), int(clear)))
+        return dict(zip(["chol", "logp", "jitter", "draws", "inverses", "slice_steps"], [int(v) for v in c]))
+
+    # -- pieces of the sweep -------------------------------------------------------------------
+    def group_kinv(self, g, want=True):
+        out = self._new(self.C, self.n, self.n) if (want and g >= 0) else None
+        self._ck(self._lib.gpf_group_kinv(self._h, int(g), _ptr(out)))
+        self.sync()
+        return out
+
+    def function_step(self, fn, sweep=0, z=None, want=("mu", "LA", "mt", "nt")):
+        """Function._sample for function fn of every chain; returns dict of requested intermediates (CUDA tensors)"""
+        zt = self._dev_in(z, (self.C, self.n))
+        o = {k: None for k in ("mu", "LA", "mt", "nt")}
+        for k in want:
+            o[k] = self._new(self.C, self.n, self.n) if k == "LA" else self._new(self.C, self.n)
+        sid = self.sampler_id[("function", fn)]
+        self._ck(self._lib.gpf_function_step(self._h, int(fn), sid, int(sweep), _ptr(zt), _ptr(o["mu"]), _ptr(o["LA"]),
+                                             _ptr(o["mt"]), _ptr(o["nt"])))
+        self.sync()
+        return {k: v for k, v in o.items() if v is not None}
+
+    def obs_loglik(self, cand):
+        ct = self._dev_in(np.broadcast_to(np.asarray(cand, dtype=np.float64), (self.C,)), (self.C,))
+        out = self._new(self.C)
+        self._ck(self._lib.gpf_obs_loglik(self._h, _ptr(ct), _ptr(out)))
+        self.sync()
+        return out.cpu().numpy()
+
+    def prior_loglik(self, g, which, cand):
+        """which: 'sigma' | 'lengthscale' (base.py:216-243)"""
+        w = {"sigma": 0, "lengthscale": 1}[which]
+        ct = self._dev_in(np.broadcast_to(np.asarray(cand, dtype=np.float64), (self.C,)), (self.C,))
+        out = self._new(self.C)
+        self._ck(self._lib.gpf_prior_loglik(self._h, int(g), w, _ptr(ct), _ptr(out)))
+        self.sync()
+        return out.cpu().numpy()
+
+    def slice_step(self, h, sweep=0, u=None):
+        """Slice._sample on hyper-parameter h of every chain; u: (C, k) injected uniforms or None (Philox).
+        Returns the number of log-density evaluations per chain."""
+        ut = None
+        nu = 0
+        if u is not None:
+            u = np.ascontiguousarray(np.asarray(u, dtype=np.float64))
+            nu = u.shape[1]
+            ut = self._dev_in(u, (self.C, nu))
+        nev = torch.zeros(self.C, dtype=torch.int32, device=self.dev)
+        torch.cuda.synchronize(self.dev)
+        sid = self.sampler_id[("slice", h)]
+        self._ck(self._lib.gpf_slice_step(self._h, int(h), sid, int(sweep), _ptr(ut), nu, _ptr(nev)))
+        self.sync()
+        return nev.cpu().numpy()
+
+    def sweep(self, n_sweeps=1, thin=0, history=None, order=None, sweep0=None):
+        """SamplerContainer.sample (container.py:55-78) for every chain.  history: preallocated CUDA tensor
+        (rows, C, H + f*n) or None.  Returns the number of rows stored."""
+        if sweep0 is None:
+            sweep0 = self.sweeps_done
+        op = None
+        if order is not None:
+            order = np.ascontiguousarray(np.asarray(order, dtype=np.int32).reshape(n_sweeps, len(self.order)))
+            op = order.ctypes.data_as(C.c_void_p)
+        rows = C.c_longlong(0)
+        cap = 0
+        if history is not None:
+            assert history.is_cuda and history.dtype == torch.float64 and history.is_contiguous()
+            assert tuple(history.shape[1:]) == (self.C, self.H + self.f * self.n)
+            cap = history.shape[0]
+        self._ck(self._lib.gpf_sweep(self._h, int(n_sweeps), int(thin), int(sweep0), op, _ptr(history), cap, C.byref(rows)))
+        self.sweeps_done = sweep0 + n_sweeps
+        return int(rows.value)
+
+    def set_profile(self, on=True):
+        self._ck(self._lib.gpf_set_profile(self._h, int(on)))
+
+    def profile(self):
+        ms = np.zeros(6)
+        nl = C.c_ulonglong(0)
+        self._ck(self._lib.gpf_get_profile(self._h, ms.ctypes.data_as(C.c_void_p), C.byref(nl)))
+        return dict(zip(["total", "kinv", "function", "prior_slice", "y_sigma", "store"], ms.tolist())), int(nl.value)

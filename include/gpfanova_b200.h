@@ -99,6 +99,8 @@ int gpf_set_state(gpf_ctx* ctx, const double* h_F, const double* h_hyper);
 int gpf_get_state(gpf_ctx* ctx, double* h_F, double* h_hyper);
 double* gpf_device_F(gpf_ctx* ctx);       /* device pointers to the live state (chains x f x n) */
 double* gpf_device_hyper(gpf_ctx* ctx);   /* chains x H */
+int gpf_invalidate(gpf_ctx* ctx);         /* call after writing through gpf_device_hyper(): cached K_inv are stale */
+int gpf_n_samplers(gpf_ctx* ctx);         /* 1 + f + 2P: length of the non-Transform sampler list (base.py:57-84) */
 
 /* per-chain status of the last factorisations (max |code| since last clear); h_status: chains ints.
  * returns GPF_ERR_NOT_PD if any chain holds a negative code. */

@@ -199,3 +199,29 @@ def test_oracle_vs_live_reference_sweep_pieces():
             a = ref.prior_likelihood(prior_lb=-2, prior_ub=2, **kw)
             b = m.logp_hyper(h, list(kw.values())[1])
         assert abs(a - b) <= 1e-8 * max(1, abs(a))
+
+
+def test_reference_floor_against_arbiter():
+    """tests/golden/truth.npz (60-digit mpmath, oracle/make_truth.py): documents the FP64 floor of the reference's own
+    path on the conditioning-limited stages -- the allowance the GPU parity tests use."""
+    T = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "truth.npz")))
+    worst = dict(Kinv=0.0, mu=0.0, cov=0.0)
+    for k, v in T.items():
+        name, key = k.split("/")
+        if key.startswith("prior_ll"):
+            continue
+        c = load_case(name)
+        kind = key.split("_")[0]
+        worst[kind] = max(worst[kind], relerr(c[key], v))
+    assert 1e-8 < worst["Kinv"] < 5e-5          # K_inv is only good to ~1e-6
+    assert 1e-11 < worst["mu"] < 5e-9           # conditional mean: ~1e-10..1e-9
+    assert 1e-11 < worst["cov"] < 5e-9
+    c = load_case("oneway_n50")
+    m = oracle_model(c)
+    for which, key in (("sigma", "prior_ll_sigma_0"), ("lengthscale", "prior_ll_ls_0")):
+        tru = T["oneway_n50/prior_ll_%s_0" % which]
+        for i, cand in enumerate(c["cands"]):
+            if np.isfinite(tru[i]):
+                assert abs(c[key][i] - tru[i]) <= 5e-9 * max(1, abs(tru[i]))
+                o = orc.prior_loglik(m.x, m.F[:, m.groups[0]].T, m.hyper[1], m.hyper[2], cand, which)
+                assert abs(o - tru[i]) <= 5e-9 * max(1, abs(tru[i]))
