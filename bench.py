@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Benchmark of the gpfanova Gibbs-sampling hot path on B200 (contract: see the task statement / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step is one Gibbs sweep (all samplers of base.py:57-84: 1 + f + 2P blocks) of every chain.  Workload: BASELINE
+config 5 -- two-way 3x3 FANOVA with interaction, 5 replicates (m=45, f=9, P=4), n=256 time points, 4096 chains in total
+(strong scaling: chains are split across the N ranks, no collective on the sampling path).
+Metric: posterior function draws/s = chains * f * sweeps / time, FP64.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "posterior function draws/sec (FP64, n=256)"
+UNIT = "draws/s"
+WORKLOAD = "cfg5_twoway_n256"
+
+
+def problem(n=256):
+    from gpfanova_b200 import synthetic
+    levels, reps, n_, inter, hc, chains = synthetic.CONFIGS[WORKLOAD]
+    eff = synthetic.effects(levels, reps)
+    x = np.linspace(-1, 1, n)[:, None]
+    return x, eff, inter, hc, chains
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU arm: the reference itself (py3-importable copy in oracle/_ref, emitted by oracle/build_ref.py) or, if that is
+# absent, the oracle port.  One chain per process, single-threaded BLAS, one process per host core.
+# ----------------------------------------------------------------------------------------------------------
+def cpu_worker(args):
+    """child process: time `sweeps` sweeps of one chain after `warm` untimed ones; prints one JSON line"""
+    n, sweeps, warm, chain = args.n, args.cpu_sweeps, args.cpu_warm, args.cpu_chain
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    x, eff, inter, hc, _ = problem(n)
+    from gpfanova_b200 import synthetic
+    kind = "port"
+    try:
+        import build_ref
+        if not os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "gpfanova")):
+            build_ref.build(quiet=True)
+        gp = build_ref.import_ref()
+        kind = "reference"
+    except Exception:
+        gp = None
+    import gpfanova_oracle as orc
+    d = orc.Design(eff, interactions=inter, helmertConvert=hc)
+    y, _ = synthetic.prior_draw(x, d.X, d.prior_groups())
+    start = synthetic.chain_starts(1, len(d.prior_groups()), first=chain)[0]
+    np.random.seed(1000 + chain)
+    if gp is not None:
+        import logging
+        logging.disable(logging.CRITICAL)
+        m = gp.fanova.FANOVA(x, y, eff, interactions=inter, helmertConvert=hc)
+        names = ['y_sigma'] + [s % g for g in range(len(d.prior_groups())) for s in ('prior%d_sigma', 'prior%d_lengthscale')]
+        for nm, v in zip(names, start):
+            m.parameter_cache[nm] = v
+        m.sample(warm, thin=0)
+        t0 = time.perf_counter()
+        m.sample(sweeps, thin=10)
+        dt = time.perf_counter() - t0
+    else:
+        m = orc.Model(x, y, d.X, d.prior_groups())
+        m.hyper = start.copy()
+        st = orc.Stream(chain)
+        for s in range(warm):
+            m.sweep(st, chain, s)
+        t0 = time.perf_counter()
+        for s in range(sweeps):
+            m.sweep(st, chain, warm + s)
+        dt = time.perf_counter() - t0
+    print(json.dumps({"kind": kind, "sweeps": sweeps, "seconds": dt, "f": int(d.f)}), flush=True)
+
+
+def run_cpu_arm(n, sweeps, warm, procs=None):
+    """aggregate draws/s of `procs` single-threaded reference processes running concurrently"""
+    procs = procs or os.cpu_count() or 1
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="1", MKL_NUM_THREADS="1", CUDA_VISIBLE_DEVICES="")
+    t0 = time.perf_counter()
+    ps = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--cpu-worker", "--n", str(n), "--cpu-sweeps", str(sweeps),
+                            "--cpu-warm", str(warm), "--cpu-chain", str(c)], env=env, stdout=subprocess.PIPE,
+                           stderr=subprocess.DEVNULL, text=True) for c in range(procs)]
+    outs = []
+    for p in ps:
+        o, _ = p.communicate()
+        for line in o.splitlines():
+            if line.startswith("{"):
+                outs.append(json.loads(line))
+    wall = time.perf_counter() - t0
+    if not outs:
+        raise RuntimeError("CPU baseline workers produced no output")
+    rate = sum(o["f"] * o["sweeps"] / o["seconds"] for o in outs)
+    return {"value": rate, "unit": UNIT, "cores": len(outs), "kind": outs[0]["kind"],
+            "sample": "%d sweeps (after %d warm-up) of 1 chain per process, %d processes, single-threaded BLAS, same "
+                      "cfg5 data (n=%d, m=45, f=9, P=4); per-core %.2f draws/s; wall %.1f s" % (
+                          sweeps, warm, len(outs), n, rate / len(outs), wall),
+            "ms_per_sweep_per_chain": 1e3 * float(np.mean([o["seconds"] / o["sweeps"] for o in outs]))}
+
+
+# ----------------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200",
+                                       "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for l in self.lines:
+            parts = [q.strip() for q in l.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2])); pw.append(float(parts[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "power_w_max": max(pw), "samples": len(sm)}
+
+
+def fp64_peak():
+    """measured FP64 tensor (DMMA) peak of this pool's B200: MEASURED_PEAKS.json has no FP64 entry, so the denominator is
+    our own microbenchmark (tools/fp64_peak.cu, result committed as profiles/fp64_peak_r01.json)"""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak_r01.json")))
+        return float(d["dmma884_tflops"]), "profiles/fp64_peak_r01.json (tools/fp64_peak.cu, DMMA m8n8k4 burst, measured on this pool)"
+    except Exception:
+        return 37.0, "fallback 37 TFLOP/s (B200 FP64 datasheet order; profiles/fp64_peak_r01.json missing)"
+
+
+def flops_model(n, f, P, ng_list, counts, chains, sweeps):
+    """algorithmic FP64 flops: chol n^3/3, K_inv n^3 (chol + triangular inverse + L^-T L^-1),
+    function draw n^3/3 + 6 n^2, slice factorisation n^3/3 + |g| n^2"""
+    n3 = float(n) ** 3
+    inv = counts["inverses"] * n3
+    draws = counts["draws"] * (n3 / 3 + 6.0 * n * n)
+    prior_facts = counts["chol"] - counts["inverses"] - counts["draws"] - counts["jitter"]
+    gbar = float(np.mean(ng_list))
+    prior = prior_facts * (n3 / 3 + gbar * n * n)
+    return {"kinv": inv, "function": draws, "prior_slice": prior, "prior_factorisations": prior_facts,
+            "total": inv + draws + prior}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chains", type=int, default=0, help="total chains (default: the workload's 4096)")
+    ap.add_argument("--n", type=int, default=256)
+    ap.add_argument("--burnin", type=int, default=20, help="untimed sweeps before warm-up (chains leave their start state)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-worker", action="store_true")
+    ap.add_argument("--cpu-sweeps", type=int, default=5)
+    ap.add_argument("--cpu-warm", type=int, default=1)
+    ap.add_argument("--cpu-chain", type=int, default=0)
+    ap.add_argument("--cpu-procs", type=int, default=0)
+    args = ap.parse_args()
+    if args.cpu_worker:
+        return cpu_worker(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        # each step = one sweep of one chain per host core (bounded sample of the workload)
+        res = run_cpu_arm(args.n, max(1, args.steps), max(0, args.warmup), args.cpu_procs or None)
+        line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": res["ms_per_sweep_per_chain"], "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+                "config": {"workload": WORKLOAD, "n": args.n, "m": 45, "f": 9, "P": 4, "chains": res["cores"],
+                           "note": "reference CPU sampler, one chain per core"},
+                "cpu_baseline": res,
+                "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device: gpfanova_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from gpfanova_b200 import engine, fanova, synthetic
+
+    x, eff, inter, hc, total_chains = problem(args.n)
+    if args.chains:
+        total_chains = args.chains
+    C = total_chains // world                       # strong scaling: the workload's chains are split over the ranks
+    first = rank * C
+    model = fanova.FANOVA(x, np.zeros((args.n, eff.shape[0])), eff, interactions=inter, helmertConvert=hc, chains=C,
+                          seed=20261019, device=local, store_chains=True)
+    y, Ftrue = synthetic.prior_draw(x, model.design_matrix, model.priorGroups())
+    groups = [list(g) for g in model.priorGroups()]
+    P, f, n = len(groups), model.f, args.n
+    start = synthetic.chain_starts(C, P, first=first)
+
+    # ---------------- kernel-level arm: inputs resident in HBM ----------------
+    eng = engine.ChainEngine(x, y, model.design_matrix, groups, chains=C, seed=20261019, device=local, chain_offset=first)
+    eng.set_state(hyper=start)
+    eng.sweep(args.burnin)
+    eng.sweep(args.warmup)
+    eng.sync()
+    eng.status()
+    eng.counters(clear=True)
+    eng.set_profile(True)
+    _, launches0 = eng.profile()
+    clocks = ClockSampler(local)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks.start()
+    t0 = time.perf_counter()
+    eng.sweep(args.steps)
+    eng.sync()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    clk = clocks.stop()
+    prof, launches1 = eng.profile()
+    eng.set_profile(False)
+    eng.status()
+    counts = eng.counters()
+    dev_ms = prof["total"]
+    el = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    dev_ms_max = float(el.item())
+    value = total_chains * f * args.steps / (dev_ms_max * 1e-3)
+
+    # ---------------- roofline of the dominant kernel (k_prior: slice-sampler GP log-likelihood) ----------------
+    peak, peak_src = fp64_peak()
+    fm = flops_model(n, f, P, [len(g) for g in groups], counts, C, args.steps)
+    n_prior_launches = 2 * P * args.steps
+    prior_tf = fm["prior_slice"] / (prof["prior_slice"] * 1e-3) / 1e12 if prof["prior_slice"] > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "k_prior (sigma + lengthscale slice steps)", "achieved": prior_tf, "peak": peak,
+                "unit": "TFLOP/s", "frac": prior_tf / peak, "traffic": None, "peak_source": peak_src,
+                "flops_per_launch": fm["prior_slice"] / n_prior_launches,
+                "ms_per_launch": prof["prior_slice"] / n_prior_launches,
+                "share_of_step": prof["prior_slice"] / dev_ms if dev_ms else None,
+                "whole_step": {"achieved": fm["total"] / (dev_ms * 1e-3) / 1e12, "frac": fm["total"] / (dev_ms * 1e-3) / 1e12 / peak,
+                               "ms": {k: prof[k] / args.steps for k in prof},
+                               "tflops": {k: (fm[k] / (prof[k] * 1e-3) / 1e12 if prof[k] > 0 else None)
+                                          for k in ("kinv", "function", "prior_slice")}},
+                "counted": {"factorisations_per_sweep_per_chain": counts["chol"] / (C * args.steps),
+                            "logp_evals_per_slice_step": counts["logp"] / max(1, counts["slice_steps"]),
+                            "jitter_retries": counts["jitter"]}}
+    eng.close()
+
+    # ---------------- end to end through the public API with host buffers ----------------
+    e2e = None
+    if not args.no_e2e:
+        model.y = y                                  # host array -> uploaded inside the timed region
+        model.set_chain_state(hyper=start)
+        ksteps = args.steps
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        model.sample(ksteps, thin=1)                 # H2D: data + state; D2H: every stored sweep of every chain
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        el = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        e2e_s = float(el.item())
+        cols = model.H + f * n
+        e2e = {"value": total_chains * f * ksteps / e2e_s, "unit": UNIT,
+               "h2d_bytes_per_step": int((y.nbytes + x.nbytes + C * cols * 8) / ksteps),
+               "d2h_bytes_per_step": int(C * cols * 8 + C * cols * 8 / ksteps),
+               "seconds": e2e_s, "api": "FANOVA(...).sample(%d, thin=1): construction of the device context, upload of y / x / "
+                                        "design / chain states, %d sweeps, every sweep's state of every chain read back to host "
+                                        "and chain 0 appended to parameter_history" % (ksteps, ksteps)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu = run_cpu_arm(n, args.cpu_sweeps, args.cpu_warm, args.cpu_procs or None)
+        except Exception as e:  # noqa
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)[:200]}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "n": n, "m": int(eff.shape[0]), "f": int(f), "P": P, "chains": total_chains,
+                           "chains_per_gpu": C, "parallelism": "chains sharded over %d GPU(s), no collective" % world,
+                           "burnin_sweeps": args.burnin,
+                           "l2": "working set %.1f GB of per-chain K_inv tiles + state >> 126 MB L2; no flush needed" % (
+                               P * C * (n // 32) * (n // 32 + 1) / 2 * 8192 / 1e9)},
+                "wall_ms_per_step": 1e3 * wall / args.steps, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
+                "e2e": e2e, "gpu_launches": int(launches1 - launches0)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
