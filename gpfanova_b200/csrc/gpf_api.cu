@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -42,6 +43,7 @@ struct gpf_ctx {
   std::vector<std::vector<int>> groups;
   std::vector<Samp> order;
   std::vector<char> kinv_valid;
+  bool toeplitz = false;
   std::vector<void*> allocs;
   size_t smem_kinv = 0, smem_fn = 0;
   std::vector<size_t> smem_prior;
@@ -122,7 +124,8 @@ int dev_alloc(gpf_ctx* c, T** p, size_t count) {
 
 int launch_kinv(gpf_ctx* c, int g) {
   Timer t(c, 1);
-  k_group_kinv<<<c->grid, NTHR, c->smem_kinv, c->stream>>>(c->dev, g);
+  if (c->toeplitz) k_group_kinv<true><<<c->grid, NTHR, c->smem_kinv, c->stream>>>(c->dev, g);
+  else k_group_kinv<false><<<c->grid, NTHR, c->smem_kinv, c->stream>>>(c->dev, g);
   ++c->launches;
   CK(c, cudaGetLastError());
   c->kinv_valid[g] = 1;
@@ -142,6 +145,20 @@ int launch_function(gpf_ctx* c, int fn, unsigned sampler_id, unsigned sweep, con
   return GPF_OK;
 }
 
+// mode: 0/1 evaluate sigma / lengthscale candidates, 2/3 slice step on sigma / lengthscale, 4 fused sigma + lengthscale
+int launch_prior(gpf_ctx* c, int g, int mode, const double* cand, double* outv, unsigned sampler_id, unsigned sweep,
+                 const double* u, int nu, int* nev) {
+  Timer t(c, 3);
+  PriorArgs a{g, mode, cand, outv, c->slice_w[1 + 2 * g], c->slice_w[2 + 2 * g], c->slice_m[1 + 2 * g], c->slice_m[2 + 2 * g],
+              sampler_id, sweep, u, nu, nev};
+  if (c->toeplitz) k_prior<true><<<c->grid, NTHR, c->smem_prior[g], c->stream>>>(c->dev, a);
+  else k_prior<false><<<c->grid, NTHR, c->smem_prior[g], c->stream>>>(c->dev, a);
+  ++c->launches;
+  CK(c, cudaGetLastError());
+  if (mode >= 2) c->kinv_valid[g] = 0;
+  return GPF_OK;
+}
+
 int launch_slice(gpf_ctx* c, int h, int mode, const double* cand, double* outv, unsigned sampler_id, unsigned sweep,
                  const double* u, int nu, int* nev) {
   if (h == 0) {
@@ -153,13 +170,7 @@ int launch_slice(gpf_ctx* c, int h, int mode, const double* cand, double* outv, 
     return GPF_OK;
   }
   const int g = (h - 1) / 2, which = (h - 1) % 2;
-  Timer t(c, 3);
-  k_prior<<<c->grid, NTHR, c->smem_prior[g], c->stream>>>(c->dev, g, which, mode, cand, outv, c->slice_w[h], c->slice_m[h],
-                                                         sampler_id, sweep, u, nu, nev);
-  ++c->launches;
-  CK(c, cudaGetLastError());
-  if (mode == 1) c->kinv_valid[g] = 0;
-  return GPF_OK;
+  return launch_prior(c, g, mode ? 2 + which : which, cand, outv, sampler_id, sweep, u, nu, nev);
 }
 
 }  // namespace
@@ -297,16 +308,20 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
     return fail(GPF_ERR_UNSUPPORTED);
   }
   {
-    cudaError_t e = allow_smem(k_group_kinv, c->smem_kinv);
+    const size_t sp = *std::max_element(c->smem_prior.begin(), c->smem_prior.end());
+    cudaError_t e = allow_smem(k_group_kinv<true>, c->smem_kinv);
+    if (e == cudaSuccess) e = allow_smem(k_group_kinv<false>, c->smem_kinv);
     if (e == cudaSuccess) e = allow_smem(k_function, c->smem_fn);
-    if (e == cudaSuccess) e = allow_smem(k_prior, *std::max_element(c->smem_prior.begin(), c->smem_prior.end()));
+    if (e == cudaSuccess) e = allow_smem(k_prior<true>, sp);
+    if (e == cudaSuccess) e = allow_smem(k_prior<false>, sp);
     if (e != cudaSuccess) { c->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return fail(GPF_ERR_CUDA); }
   }
   c->grid = std::min(v.C, 2 * c->sms);
   // device buffers
   const size_t tstride = (size_t)plt_tiles(v.NT) * TILE;
   v.ws_stride = tstride + (size_t)v.NEmax * v.NT * TILE;
-  double *dx, *dyT, *dX, *dF, *dh, *dK, *dws;
+  double *dx, *dyT, *dX, *dF, *dh, *dK, *dws, *dd2, *dG, *dZ;
+  unsigned char* dfull;
   int *dgof, *dgf, *dgo, *dst;
   unsigned long long* dcn;
   int rc;
@@ -315,8 +330,38 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
       (rc = dev_alloc(c, &dh, (size_t)v.C * v.H)) || (rc = dev_alloc(c, &dK, (size_t)d->P * v.C * tstride)) ||
       (rc = dev_alloc(c, &dws, (size_t)c->grid * v.ws_stride)) || (rc = dev_alloc(c, &dgof, (size_t)d->f)) ||
       (rc = dev_alloc(c, &dgf, (size_t)d->f)) || (rc = dev_alloc(c, &dgo, (size_t)d->P + 1)) ||
-      (rc = dev_alloc(c, &dst, (size_t)v.C)) || (rc = dev_alloc(c, &dcn, (size_t)CNT_N)))
+      (rc = dev_alloc(c, &dst, (size_t)v.C)) || (rc = dev_alloc(c, &dcn, (size_t)CNT_N)) ||
+      (rc = dev_alloc(c, &dd2, (size_t)d->n)) || (rc = dev_alloc(c, &dG, (size_t)d->f * d->f)) ||
+      (rc = dev_alloc(c, &dZ, (size_t)d->f * d->n)) || (rc = dev_alloc(c, &dfull, (size_t)d->n)))
     return fail(rc);
+  // uniform grid?  then every RBF matrix is Toeplitz: K[i][j] = k(|i-j| h) and needs one exp per lag
+  std::vector<double> d2(d->n, 0.0);
+  c->toeplitz = false;
+  if (d->p == 1) {
+    const long double x0 = d->h_x[0], h = d->n > 1 ? ((long double)d->h_x[d->n - 1] - x0) / (d->n - 1) : 0.0L;
+    const double tol = 1e-14 * (std::fabs(d->h_x[0]) + std::fabs(d->h_x[d->n - 1]));
+    bool uni = true;
+    for (int i = 0; i < d->n && uni; ++i) uni = std::fabs((double)(x0 + i * h - (long double)d->h_x[i])) <= tol;
+    if (uni) {
+      c->toeplitz = true;
+      for (int k = 0; k < d->n; ++k) d2[k] = (double)((k * h) * (k * h));
+    }
+  }
+  // X^T X, X^T y (observed entries) and the per-time-point "nothing missing" flag for the residual projection
+  std::vector<double> G((size_t)d->f * d->f, 0.0), Z((size_t)d->f * d->n, 0.0);
+  std::vector<unsigned char> full(d->n, 1);
+  for (int a = 0; a < d->f; ++a)
+    for (int b = 0; b < d->f; ++b) {
+      double s = 0.0;
+      for (int o = 0; o < d->m; ++o) s += d->h_X[(size_t)o * d->f + a] * d->h_X[(size_t)o * d->f + b];
+      G[(size_t)a * d->f + b] = s;
+    }
+  for (int t = 0; t < d->n; ++t)
+    for (int o = 0; o < d->m; ++o) {
+      const double yv = d->h_y[(size_t)t * d->m + o];
+      if (yv != yv) { full[t] = 0; continue; }
+      for (int a = 0; a < d->f; ++a) Z[(size_t)a * d->n + t] += d->h_X[(size_t)o * d->f + a] * yv;
+    }
   std::vector<double> yT((size_t)d->n * d->m);
   for (int t = 0; t < d->n; ++t)
     for (int o = 0; o < d->m; ++o) yT[(size_t)o * d->n + t] = d->h_y[(size_t)t * d->m + o];
@@ -331,12 +376,17 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
   if (e == cudaSuccess) e = cudaMemcpy(dgof, c->group_of_fn.data(), sizeof(int) * d->f, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(dgf, gf.data(), sizeof(int) * gf.size(), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(dgo, go.data(), sizeof(int) * go.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dd2, d2.data(), sizeof(double) * d->n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dG, G.data(), sizeof(double) * G.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dZ, Z.data(), sizeof(double) * Z.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dfull, full.data(), full.size(), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemset(dF, 0, sizeof(double) * v.C * d->f * d->n);
   if (e == cudaSuccess) e = cudaMemset(dh, 0, sizeof(double) * v.C * v.H);
   if (e == cudaSuccess) e = cudaMemset(dst, 0, sizeof(int) * v.C);
   if (e == cudaSuccess) e = cudaMemset(dcn, 0, sizeof(unsigned long long) * CNT_N);
   if (e != cudaSuccess) { c->err = std::string("gpf_create: upload: ") + cudaGetErrorString(e); return fail(GPF_ERR_CUDA); }
   v.x = dx; v.yT = dyT; v.X = dX; v.F = dF; v.hyper = dh; v.Kinv = dK; v.ws = dws;
+  v.d2 = dd2; v.G = dG; v.Z = dZ; v.full = dfull;
   v.group_of_fn = dgof; v.group_fns = dgf; v.group_off = dgo; v.status = dst; v.counters = dcn;
   *out = c;
   return GPF_OK;
@@ -485,7 +535,14 @@ int gpf_sweep(gpf_ctx* c, int n_sweeps, int thin, unsigned sweep0, const int* h_
       const Samp& sp = c->order[sid];
       int rc;
       if (sp.kind == 1) rc = launch_function(c, sp.arg, (unsigned)sid, sweep, nullptr, FnOut{nullptr, nullptr, nullptr, nullptr});
-      else rc = launch_slice(c, sp.arg, 1, nullptr, nullptr, (unsigned)sid, sweep, nullptr, 0, nullptr);
+      else {
+        // prior{g}_sigma immediately followed by prior{g}_lengthscale (the reference's fixed order): one fused launch
+        const int nxt = (k + 1 < ns) ? (h_order ? h_order[(size_t)s * ns + k + 1] : k + 1) : -1;
+        if (sp.arg >= 1 && (sp.arg - 1) % 2 == 0 && nxt == sid + 1 && c->order[nxt].kind == 0 && c->order[nxt].arg == sp.arg + 1) {
+          rc = launch_prior(c, (sp.arg - 1) / 2, 4, nullptr, nullptr, (unsigned)sid, sweep, nullptr, 0, nullptr);
+          ++k;
+        } else rc = launch_slice(c, sp.arg, 1, nullptr, nullptr, (unsigned)sid, sweep, nullptr, 0, nullptr);
+      }
       if (rc) return rc;
     }
     if (d_history && (thin <= 0 || (s + 1) % thin == 0)) {

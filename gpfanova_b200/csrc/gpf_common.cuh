@@ -33,6 +33,10 @@ struct CtxDev {
   size_t ws_stride;
   double offset, prior_jitter, prior_lb, prior_ub;
   unsigned k0, k1;            // Philox key
+  const double* d2;           // uniform grid (p = 1): squared distance at lag k, n entries (K is Toeplitz); else null
+  const double* G;            // f x f   X^T X
+  const double* Z;            // f x n   X^T y over the observed entries (NaN -> 0)
+  const unsigned char* full;  // n       1 if no observation is missing at time t
 };
 
 __device__ __forceinline__ void status_merge(int* st, int code) {
@@ -151,5 +155,82 @@ __device__ inline double slice_step(double x, double w, int m, LogP&& logp, Unif
   }
   return x1;
 }
+
+// first-touch source: RBF kernel evaluated element by element (general inputs)
+struct SrcRbf {
+  const double *xs, *xsq;
+  int n, p;
+  double sigma;
+  __device__ __forceinline__ void rows(double (&a)[32], int bi, int bj, int lane) const {
+#pragma unroll
+    for (int c = 0; c < 32; ++c) a[c] = rbf_elem(xs, xsq, n, p, sigma, bi * TB + lane, bj * TB + c);
+  }
+  __device__ __forceinline__ void cfrag(CFrag& f, int bi, int bj, int g, int tig) const {
+#pragma unroll
+    for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+      for (int tj = 0; tj < 4; ++tj) {
+        f.c[ti][tj][0] = rbf_elem(xs, xsq, n, p, sigma, bi * TB + 8 * ti + g, bj * TB + 8 * tj + 2 * tig);
+        f.c[ti][tj][1] = rbf_elem(xs, xsq, n, p, sigma, bi * TB + 8 * ti + g, bj * TB + 8 * tj + 2 * tig + 1);
+      }
+  }
+};
+
+// uniform grid: tab[k] = sigma * exp(-d2[k] / (2 l^2)), k < n (one exp per lag instead of one per matrix element).
+// Returns the sum of the full n x n matrix to every thread (base.py:222's cov.mean() * n^2).
+__device__ inline double toeplitz_table(const double* __restrict__ d2, int n, double sigma, double ls, double* tab, double* red) {
+  const double s = -0.5 / (ls * ls);
+  double part = 0.0;
+  for (int k = threadIdx.x; k < n; k += NTHR) {
+    const double v = sigma * exp(d2[k] * s);
+    tab[k] = v;
+    part += (k == 0 ? (double)n : 2.0 * (double)(n - k)) * v;
+  }
+  return block_sum(part, red);   // contains the __syncthreads that publish tab
+}
+
+// Slice._sample (sample/slice.pyx:24-62) as a resumable state machine: the caller evaluates the log density at `cand`
+// (one call site, so the factorisation code is instantiated once) and feeds the value back until `done`.
+struct SliceSM {
+  double x, w, z, l, r, cand;
+  int m, j, k, phase, nev, d;
+  bool done;
+  __device__ void init(double x0, double w0, int m0) {
+    x = x0; w = w0; m = m0; cand = x0; phase = 0; nev = 1; d = 3; done = false;
+    z = 0.0; l = r = x0; j = k = 0;
+  }
+  template <class Unif>
+  __device__ void feed(double lp, Unif&& unif) {
+    if (phase == 0) {
+      z = lp - (1.0 - log(unif(0)));               // slice.pyx:30: expon.rvs(1) has loc = 1
+      const double u = unif(1);
+      l = x - w * u;
+      r = l + w;
+      const double v = unif(2);
+      j = (int)(m * v);
+      k = m - 1 - j;
+      phase = 1;
+    } else if (phase == 1) {
+      if (z < lp) { --j; l -= w; } else phase = 2;
+    } else if (phase == 2) {
+      if (z < lp) { --k; r += w; } else phase = 3;
+    } else {
+      if (!(z > lp)) { done = true; return; }
+      if (cand < x) l = cand; else r = cand;
+      if (d > 4096) { done = true; return; }       // unreachable in exact arithmetic
+    }
+    if (phase == 1) {
+      if (j > 0) { cand = l; ++nev; return; }
+      phase = 2;
+    }
+    if (phase == 2) {
+      if (k > 0) { cand = r; ++nev; return; }
+      phase = 3;
+    }
+    const double u = unif(d++);
+    cand = l + u * (r - l);
+    ++nev;
+  }
+};
 
 }  // namespace gpf

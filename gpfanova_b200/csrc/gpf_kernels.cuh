@@ -62,8 +62,8 @@ __global__ void __launch_bounds__(NTHR, 2) k_jitchol_dense(const double* __restr
       dense_to_tiles(Ab, n, NT, W);
       for (int t = threadIdx.x; t < NT * TB; t += NTHR) sm.dvec[t] = (t < n) ? add_diag + jitter : 0.0;
       __syncthreads();
-      EngineIO io{W, W, nullptr, RowSrc{nullptr, nullptr, 0, 0, 0}, nullptr, 0};
-      if (chol_engine<AUG_NONE, true>(io, NT, 0, 0, sm)) { code = tries; break; }
+      EngineIO io{W, nullptr, RowSrc{nullptr, nullptr, 0, 0, 0}, nullptr, 0};
+      if (chol_engine<AUG_NONE, true>(SrcTiles{W}, io, NT, 0, 0, sm)) { code = tries; break; }
       if (tries == 0) {
         bool nonpos;
         const double dm = dense_diag_mean(Ab, n, sm.red(), nonpos) + add_diag;
@@ -97,8 +97,8 @@ __global__ void __launch_bounds__(NTHR, 2) k_kinv_dense(const double* __restrict
       dense_to_tiles(Ab, n, NT, W);
       for (int t = threadIdx.x; t < NT * TB; t += NTHR) sm.dvec[t] = (t < n) ? offset + jitter : 0.0;
       __syncthreads();
-      EngineIO io{W, W, nullptr, RowSrc{nullptr, nullptr, 0, 0, 0}, nullptr, 0};
-      if (chol_engine<AUG_IDENT, false>(io, NT, 0, 0, sm)) { code = tries; break; }
+      EngineIO io{W, nullptr, RowSrc{nullptr, nullptr, 0, 0, 0}, nullptr, 0};
+      if (chol_engine<AUG_IDENT, false>(SrcTiles{W}, io, NT, 0, 0, sm)) { code = tries; break; }
       if (tries == 0) {
         bool nonpos;
         const double dm = dense_diag_mean(Ab, n, sm.red(), nonpos) + offset;
@@ -123,12 +123,14 @@ __global__ void __launch_bounds__(NTHR) k_tiles_to_dense(const double* tiles, si
 
 // ---------------------------------------------------------------------------------------------------------
 // Kernel.K_inv of prior group g for every chain at the current hyper-parameters
-//   kernel/kernel.pyx:51-64 (K + 1e-9 I, jitchol, L^-T L^-1) with rbf.pyx:16-19 generated on chip.
+//   kernel/kernel.pyx:51-64 (K + 1e-9 I, jitchol, L^-T L^-1) with rbf.pyx:16-19 generated on chip at first touch
+//   (TOEP: uniform grid, one exp per lag; else one exp per element).
 // The inverse is built in place in its destination (c.Kinv), never as a separate L / L^-1.
 // ---------------------------------------------------------------------------------------------------------
+template <bool TOEP>
 __global__ void __launch_bounds__(NTHR, 2) k_group_kinv(CtxDev c, int g) {
   EngineSmem sm(smem_base(), c.NT, 0);
-  double* xs = smem_base() + engine_smem_doubles(c.NT, 0);
+  double* xs = smem_base() + engine_smem_doubles(c.NT, 0);   // TOEP: lag table (n); else scaled inputs (n*p) + xsq (n)
   double* xsq = xs + (size_t)c.n * c.p;
   const size_t tstride = (size_t)plt_tiles(c.NT) * TILE;
   for (int ch = blockIdx.x; ch < c.C; ch += gridDim.x) {
@@ -136,16 +138,19 @@ __global__ void __launch_bounds__(NTHR, 2) k_group_kinv(CtxDev c, int g) {
     const double ls = exp10(c.hyper[(size_t)ch * c.H + 2 + 2 * g]);
     double* W = c.Kinv + ((size_t)g * c.C + ch) * tstride;
     __syncthreads();
-    rbf_scale_inputs(c.x, c.n, c.p, ls, xs, xsq);
+    if constexpr (TOEP) toeplitz_table(c.d2, c.n, sigma, ls, xs, sm.red());
+    else rbf_scale_inputs(c.x, c.n, c.p, ls, xs, xsq);
     int tries = 0, code = 0;
     double jitter = 0.0;
     for (;;) {
       __syncthreads();
-      rbf_fill_tiles(W, c.NT, c.n, c.p, xs, xsq, sigma, sm.red());
       for (int t = threadIdx.x; t < c.NT * TB; t += NTHR) sm.dvec[t] = (t < c.n) ? c.offset + jitter : 0.0;
       __syncthreads();
-      EngineIO io{W, W, nullptr, RowSrc{nullptr, nullptr, 0, 0, 0}, nullptr, 0};
-      if (chol_engine<AUG_IDENT, false>(io, c.NT, 0, 0, sm)) { code = tries; break; }
+      EngineIO io{W, nullptr, RowSrc{nullptr, nullptr, 0, 0, 0}, nullptr, 0};
+      bool ok;
+      if constexpr (TOEP) ok = chol_engine<AUG_IDENT, false>(SrcToeplitz{xs, c.n}, io, c.NT, 0, 0, sm);
+      else ok = chol_engine<AUG_IDENT, false>(SrcRbf{xs, xsq, c.n, c.p, sigma}, io, c.NT, 0, 0, sm);
+      if (ok) { code = tries; break; }
       // jitchol ladder (linalg.py:41-54): diag(K + offset I) = sigma + offset everywhere
       const double dm = sigma + c.offset;
       if (tries == 0) {
@@ -168,6 +173,8 @@ __global__ void __launch_bounds__(NTHR, 2) k_group_kinv(CtxDev c, int g) {
 // Function._sample (sample/function.py:14-40) + base.functionResidual (base.py:180-190), fused:
 //   m_t, n_t  ->  A = K_inv + diag(n_t)/(sigma_y + offset), b = m_t/(sigma_y + offset)  ->  L_A = jitchol(A) with
 //   w = L_A^-1 b riding along  ->  mu = L_A^-T w, beta = L_A^-T (w + z)  (draw contract: beta = mu + L_A^-T z).
+// Residual projection: at time points where nothing is missing, m_t = (X^T y)[f,t] - sum_{q != f} (X^T X)[f,q] F_q(t)
+// and n_t = (X^T X)[f,f] (precomputed Z, G); time points with missing observations take the per-observation loop.
 // ---------------------------------------------------------------------------------------------------------
 struct FnOut { double *mu, *LA, *mt, *nt; };
 
@@ -183,25 +190,34 @@ __global__ void __launch_bounds__(NTHR, 2) k_function(CtxDev c, int fn, unsigned
   double* W = c.ws + (size_t)blockIdx.x * c.ws_stride;
   double* Wx = W + tstride;
   const Stream rng{c.k0, c.k1};
+  const double* Grow = c.G + (size_t)fn * c.f;
   for (int ch = blockIdx.x; ch < c.C; ch += gridDim.x) {
     const double* Fc = c.F + (size_t)ch * c.f * n;
     const double* A0 = c.Kinv + ((size_t)g * c.C + ch) * tstride;
     const double yinv = 1.0 / (exp10(c.hyper[(size_t)ch * c.H]) + c.offset);   // white.py:7-9 through kernel.pyx:51-64
     __syncthreads();
-    // ---- residual projection (base.py:180-190, function.py:16-25) ----
     for (int t = threadIdx.x; t < npad; t += NTHR) {
       double mt = 0.0, nt = 0.0;
       if (t < n) {
-        for (int o = 0; o < c.m; ++o) {
-          const double xf = c.X[o * c.f + fn];
-          if (xf == 0.0) continue;
-          const double yv = c.yT[(size_t)o * n + t];
-          if (isnan(yv)) continue;
-          double pred = 0.0;
-          for (int q = 0; q < c.f; ++q)
-            if (q != fn) pred = fma(c.X[o * c.f + q], Fc[(size_t)q * n + t], pred);
-          mt = fma(xf, yv - pred, mt);
-          nt = fma(xf, xf, nt);
+        if (c.full[t]) {
+          mt = c.Z[(size_t)fn * n + t];
+          for (int q = 0; q < c.f; ++q) {
+            const double gq = Grow[q];
+            if (q != fn && gq != 0.0) mt = fma(-gq, Fc[(size_t)q * n + t], mt);
+          }
+          nt = Grow[fn];
+        } else {
+          for (int o = 0; o < c.m; ++o) {
+            const double xf = c.X[o * c.f + fn];
+            if (xf == 0.0) continue;
+            const double yv = c.yT[(size_t)o * n + t];
+            if (isnan(yv)) continue;
+            double pred = 0.0;
+            for (int q = 0; q < c.f; ++q)
+              if (q != fn) pred = fma(c.X[o * c.f + q], Fc[(size_t)q * n + t], pred);
+            mt = fma(xf, yv - pred, mt);
+            nt = fma(xf, xf, nt);
+          }
         }
         if (out.mt) out.mt[(size_t)ch * n + t] = mt;
         if (out.nt) out.nt[(size_t)ch * n + t] = nt;
@@ -215,8 +231,8 @@ __global__ void __launch_bounds__(NTHR, 2) k_function(CtxDev c, int fn, unsigned
     double jitter = 0.0;
     for (;;) {
       __syncthreads();
-      EngineIO io{A0, W, Wx, RowSrc{brow, nullptr, npad, 1, n}, xs, npad};
-      if (chol_engine<AUG_RHS, true>(io, NT, 1, 1, sm)) { code = tries; break; }
+      EngineIO io{W, Wx, RowSrc{brow, nullptr, npad, 1, n}, xs, npad};
+      if (chol_engine<AUG_RHS, true>(SrcTiles{A0}, io, NT, 1, 1, sm)) { code = tries; break; }
       // jitchol ladder on A (linalg.py:41-54)
       if (tries == 0) {
         double s = 0.0, bad = 0.0;
@@ -327,113 +343,138 @@ __global__ void __launch_bounds__(NTHR) k_obs(CtxDev c, int mode, const double* 
 //   cov = K(sigma, ls) + mean(K) 1e-6 I;  ll = 1 + sum_{f in g} log N(beta_f; 0, cov) + log U(lb,ub)(cand)
 // Every evaluation that changes the lengthscale is one factorisation with the group's functions riding along as
 // right-hand sides (quadratic forms) and the log-determinant from the pivots.  Candidates that only change sigma
-// rescale cov exactly, cov(s') = (s'/s) cov(s), so they cost O(1) after one factorisation.
-// mode 0: evaluate cand[ch] -> out[ch].  mode 1: slice step on hyper-parameter 1+2g+which.
+// rescale cov exactly, cov(s') = (s'/s) cov(s), so they cost O(1) after one factorisation -- and in the reference's
+// sampler order (sigma slice, then lengthscale slice of the same group) the lengthscale slice's first density value
+// is such a rescaling too, so the fused mode needs no factorisation for it.
+// The slice loops are state machines (SliceSM) around ONE factorisation call site.
+//   mode 0: evaluate sigma candidate cand[ch] -> out[ch]      mode 1: evaluate lengthscale candidate
+//   mode 2: slice step on prior{g}_sigma                      mode 3: slice step on prior{g}_lengthscale
+//   mode 4: sigma slice followed by lengthscale slice (sampler ids sampler_id, sampler_id + 1)
 // ---------------------------------------------------------------------------------------------------------
-struct PriorEval {
-  const CtxDev& c;
-  const EngineSmem& sm;
-  double *xs, *xsq, *W, *Wx;
-  int g, ch, ng, NE, nti_last;
-  const int* fns;
-  int nfact;     // factorisations executed
-  int failed;    // a factorisation met a non-positive pivot
-
-  // log N terms at (lsig, lls): returns logdet and total quadratic form through references; false if not PD
-  __device__ __noinline__ bool factor(double lsig, double lls, double& logdet, double& quad) {
-    const int n = c.n, NT = c.NT;
-    __syncthreads();
-    rbf_scale_inputs(c.x, n, c.p, exp10(lls), xs, xsq);
-    __syncthreads();
-    const double tot = rbf_fill_tiles(W, NT, n, c.p, xs, xsq, exp10(lsig), sm.red());
-    const double jit = tot / ((double)n * (double)n) * c.prior_jitter;   // base.py:222
-    for (int t = threadIdx.x; t < NT * TB; t += NTHR) sm.dvec[t] = (t < n) ? jit : 0.0;
-    __syncthreads();
-    EngineIO io{W, W, Wx, RowSrc{c.F + (size_t)ch * c.f * n, fns, n, ng, n}, nullptr, 0};
-    ++nfact;
-    const bool ok = chol_engine<AUG_RHS, false>(io, NT, NE, nti_last, sm);
-    if (!ok) { failed = 1; return false; }
-    logdet = sm.scal[0];
-    quad = engine_quad_total(sm, NT, NE);
-    return true;
-  }
-  __device__ double prior_ll(double cand) const {
-    if (cand < c.prior_lb || cand > c.prior_ub) return -(double)INFINITY;
-    return -log(c.prior_ub - c.prior_lb);
-  }
-  __device__ double assemble(double logdet, double quad, double cand) const {
-    // base.py:235-243:  1 + sum_f [-(n log 2pi + logdet + quad_f)/2] + priorll
-    return 1.0 - 0.5 * ((double)ng * ((double)c.n * LOG2PI + logdet) + quad) + prior_ll(cand);
-  }
+struct PriorArgs {
+  int g, mode;
+  const double* cand;
+  double* outv;
+  double w_s, w_l;
+  int m_s, m_l;
+  unsigned sampler_id, sweep;
+  const double* u_inject;
+  int n_inject;
+  int* nevals;       // mode 2/3: evaluations of that step; mode 4: sigma step, nevals[C + ch]: lengthscale step
 };
 
-__global__ void __launch_bounds__(NTHR, 2) k_prior(CtxDev c, int g, int which, int mode, const double* __restrict__ cand,
-                                                   double* __restrict__ outv, double w, int mstep, unsigned sampler_id,
-                                                   unsigned sweep, const double* __restrict__ u_inject, int n_inject,
-                                                   int* __restrict__ nevals) {
-  const int NT = c.NT, n = c.n;
+template <bool TOEP>
+__global__ void __launch_bounds__(NTHR, 2) k_prior(CtxDev c, PriorArgs a) {
+  const int NT = c.NT, n = c.n, g = a.g, mode = a.mode;
   const int ng = c.group_off[g + 1] - c.group_off[g];
   const int NE = (ng + TB - 1) / TB;
-  const int rem = ng - (NE - 1) * TB;
+  const int nti_last = (ng - (NE - 1) * TB + 7) / 8;
   EngineSmem sm(smem_base(), NT, NE);
-  double* xs = smem_base() + engine_smem_doubles(NT, NE);
+  double* xs = smem_base() + engine_smem_doubles(NT, NE);   // TOEP: lag table (n); else scaled inputs (n*p) + xsq (n)
   double* xsq = xs + (size_t)n * c.p;
   double* W = c.ws + (size_t)blockIdx.x * c.ws_stride;
+  double* Wx = W + (size_t)plt_tiles(NT) * TILE;
+  const int* fns = c.group_fns + c.group_off[g];
   const Stream rng{c.k0, c.k1};
+  const double lb = c.prior_lb, ub = c.prior_ub;
+  const double lprior = -log(ub - lb);
+  const double nlog2pi = (double)n * LOG2PI;
   for (int ch = blockIdx.x; ch < c.C; ch += gridDim.x) {
-    PriorEval pe{c, sm, xs, xsq, W, W + (size_t)plt_tiles(NT) * TILE, g, ch, ng, NE, (rem + 7) / 8,
-                 c.group_fns + c.group_off[g], 0, 0};
+    const unsigned gch = (unsigned)(ch + c.chain_offset);
     const double cur_s = c.hyper[(size_t)ch * c.H + 1 + 2 * g];
     const double cur_l = c.hyper[(size_t)ch * c.H + 2 + 2 * g];
-    int nev = 0;
-    if (which == 0) {
-      // sigma: factor once at the chain's current sigma, rescale for every candidate
-      double ld0 = 0.0, q0 = 0.0;
-      const bool ok = pe.factor(cur_s, cur_l, ld0, q0);
-      auto lp = [&](double v) -> double {
-        if (!ok) return -(double)INFINITY;
-        if (v < c.prior_lb || v > c.prior_ub) return -(double)INFINITY;
-        const double dl = v - cur_s;                       // log10(s'/s)
-        return pe.assemble(ld0 + (double)n * LN10 * dl, q0 * exp10(-dl), v);
-      };
-      if (mode == 0) {
-        if (threadIdx.x == 0) outv[ch] = lp(cand[ch]);
-      } else {
-        const unsigned gch = (unsigned)(ch + c.chain_offset);
-        const double x1 = slice_step(
-            cur_s, w, mstep, lp,
-            [&](int k) { return (u_inject && k < n_inject) ? u_inject[(size_t)ch * n_inject + k] : rng.uniform(gch, sweep, sampler_id, (unsigned)k); },
-            nev);
+    auto unif_s = [&](int k) {
+      return (a.u_inject && mode == 2 && k < a.n_inject) ? a.u_inject[(size_t)ch * a.n_inject + k]
+                                                          : rng.uniform(gch, a.sweep, a.sampler_id, (unsigned)k);
+    };
+    const unsigned sid_l = a.sampler_id + (mode == 4 ? 1u : 0u);
+    auto unif_l = [&](int k) {
+      return (a.u_inject && mode == 3 && k < a.n_inject) ? a.u_inject[(size_t)ch * a.n_inject + k]
+                                                          : rng.uniform(gch, a.sweep, sid_l, (unsigned)k);
+    };
+    bool base = (mode == 0 || mode == 2 || mode == 4);   // next factorisation is the one at the current (sigma, ls)
+    double s_fact = cur_s, l_eval = cur_l, result = 0.0;
+    SliceSM sl;
+    sl.init(cur_l, a.w_l, a.m_l);
+    if (mode == 1) l_eval = a.cand[ch];
+    int nfact = 0, failed = 0, nev_s = 0;
+    bool running = true;
+    while (running) {
+      const bool inb = base || (l_eval >= lb && l_eval <= ub);   // base.py:224-231: outside the prior -> -inf
+      double ld = 0.0, q = 0.0;
+      bool ok = true;
+      if (inb) {
+        // ---- the factorisation: cov = K(10^s_fact, 10^l_eval) + mean(K) 1e-6 I, group functions as right-hand sides ----
         __syncthreads();
-        if (threadIdx.x == 0) c.hyper[(size_t)ch * c.H + 1 + 2 * g] = x1;
+        double tot;
+        if constexpr (TOEP) tot = toeplitz_table(c.d2, n, exp10(s_fact), exp10(l_eval), xs, sm.red());
+        else {
+          rbf_scale_inputs(c.x, n, c.p, exp10(l_eval), xs, xsq);
+          __syncthreads();
+          tot = rbf_fill_tiles(W, NT, n, c.p, xs, xsq, exp10(s_fact), sm.red());
+        }
+        const double jit = tot / ((double)n * (double)n) * c.prior_jitter;   // base.py:222
+        for (int t = threadIdx.x; t < NT * TB; t += NTHR) sm.dvec[t] = (t < n) ? jit : 0.0;
+        __syncthreads();
+        EngineIO io{W, Wx, RowSrc{c.F + (size_t)ch * c.f * n, fns, n, ng, n}, nullptr, 0};
+        if constexpr (TOEP) ok = chol_engine<AUG_RHS, false>(SrcToeplitz{xs, n}, io, NT, NE, nti_last, sm);
+        else ok = chol_engine<AUG_RHS, false>(SrcTiles{W}, io, NT, NE, nti_last, sm);
+        ++nfact;
+        if (ok) { ld = sm.scal[0]; q = engine_quad_total(sm, NT, NE); }
+        else failed = 1;
       }
-    } else {
-      auto lp = [&](double v) -> double {
-        if (v < c.prior_lb || v > c.prior_ub) return -(double)INFINITY;   // base.py:224-231 (no factorisation needed)
-        double ld, q;
-        if (!pe.factor(cur_s, v, ld, q)) return -(double)INFINITY;
-        return pe.assemble(ld, q, v);
-      };
-      if (mode == 0) {
-        const double v = lp(cand[ch]);
-        if (threadIdx.x == 0) outv[ch] = v;
+      if (base) {
+        base = false;
+        // density of a sigma candidate v by exact rescaling of the factorisation at cur_s (base.py:235-243)
+        auto lp_s = [&](double v, double pr) -> double {
+          if (!ok) return -(double)INFINITY;
+          const double dl = v - cur_s;
+          return 1.0 - 0.5 * ((double)ng * (nlog2pi + ld + (double)n * LN10 * dl) + q * exp10(-dl)) + pr;
+        };
+        auto prior_of = [&](double v) -> double { return (v < lb || v > ub) ? -(double)INFINITY : lprior; };
+        if (mode == 0) {
+          result = lp_s(a.cand[ch], prior_of(a.cand[ch]));
+          running = false;
+        } else {
+          SliceSM ss;
+          ss.init(cur_s, a.w_s, a.m_s);
+          while (!ss.done) ss.feed(lp_s(ss.cand, prior_of(ss.cand)), unif_s);
+          nev_s = ss.nev;
+          const double new_s = ss.cand;
+          __syncthreads();
+          if (threadIdx.x == 0) c.hyper[(size_t)ch * c.H + 1 + 2 * g] = new_s;
+          if (mode == 2) running = false;
+          else {
+            s_fact = new_s;
+            sl.feed(lp_s(new_s, prior_of(cur_l)), unif_l);   // log density of the current lengthscale under the new sigma
+            l_eval = sl.cand;
+          }
+        }
       } else {
-        const unsigned gch = (unsigned)(ch + c.chain_offset);
-        const double x1 = slice_step(
-            cur_l, w, mstep, lp,
-            [&](int k) { return (u_inject && k < n_inject) ? u_inject[(size_t)ch * n_inject + k] : rng.uniform(gch, sweep, sampler_id, (unsigned)k); },
-            nev);
-        __syncthreads();
-        if (threadIdx.x == 0) c.hyper[(size_t)ch * c.H + 2 + 2 * g] = x1;
+        const double lp = (inb && ok) ? 1.0 - 0.5 * ((double)ng * (nlog2pi + ld) + q) + lprior : -(double)INFINITY;
+        if (mode == 1) { result = lp; running = false; }
+        else {
+          sl.feed(lp, unif_l);
+          if (sl.done) {
+            running = false;
+            __syncthreads();
+            if (threadIdx.x == 0) c.hyper[(size_t)ch * c.H + 2 + 2 * g] = sl.cand;
+          } else l_eval = sl.cand;
+        }
       }
     }
     if (threadIdx.x == 0) {
-      if (pe.failed) status_merge(c.status + ch, GPF_STATUS_NOT_PD);
-      atomicAdd(c.counters + CNT_CHOL, (unsigned long long)pe.nfact);
-      if (mode == 1) {
-        if (nevals) nevals[ch] = nev;
-        atomicAdd(c.counters + CNT_LOGP, (unsigned long long)nev);
-        atomicAdd(c.counters + CNT_SLICE, 1ull);
+      if (mode <= 1) a.outv[ch] = result;
+      if (failed) status_merge(c.status + ch, GPF_STATUS_NOT_PD);
+      atomicAdd(c.counters + CNT_CHOL, (unsigned long long)nfact);
+      if (mode >= 2) {
+        const int nev_total = (mode == 2 ? nev_s : (mode == 3 ? sl.nev : nev_s + sl.nev));
+        if (a.nevals) {
+          a.nevals[ch] = (mode == 3) ? sl.nev : nev_s;
+          if (mode == 4) a.nevals[c.C + ch] = sl.nev;
+        }
+        atomicAdd(c.counters + CNT_LOGP, (unsigned long long)nev_total);
+        atomicAdd(c.counters + CNT_SLICE, mode == 4 ? 2ull : 1ull);
       }
     }
     __syncthreads();

@@ -12,7 +12,7 @@
 // global workspace that stays L2-resident (one slot per persistent CTA); the current panel lives in
 // shared memory.  Trailing updates are mma.sync m8n8k4 f64 (DMMA.8x8x4 on sm_100a: measured
 // 37.1 TFLOP/s on B200, profiles/fp64_peak_r01.json); the 32x32 diagonal factorisation and the panel
-// solves are warp-level (registers + shuffles / broadcast shared-memory reads).
+// solves are warp-level (registers + broadcast shared-memory reads of the column-major diagonal factor).
 // Replaces linalg.jitchol's dpotrf (linalg.py:35-37).
 #pragma once
 #include <cuda_runtime.h>
@@ -23,7 +23,6 @@ namespace gpf {
 constexpr int TB = 32;            // tile edge
 constexpr int TILE = TB * TB;     // doubles per tile
 constexpr int PS = 36;            // row stride of a panel slot in shared memory (conflict-free DMMA fragment loads)
-constexpr int DS = 33;            // row stride of the diagonal tile in shared memory
 constexpr int NW = 8;             // warps per CTA
 constexpr int NTHR = NW * 32;
 constexpr unsigned FULLMASK = 0xffffffffu;
@@ -138,37 +137,74 @@ __device__ __forceinline__ void rows_store(const double (&a)[32], double* tile, 
   for (int c = 0; c < 16; ++c) p[c] = make_double2(a[2 * c], a[2 * c + 1]);
 }
 
-// In-register Cholesky of a 32x32 tile, lane = row.  dpotf2's failure rule: pivot <= 0 or NaN.
-// Returns false on failure.  On success a[c] (c <= lane) = L[lane][c]; rinv = 1/L[lane][lane];
-// piv = pivot value before the square root (for the log-determinant).
-__device__ __forceinline__ bool potrf_warp(double (&a)[32], int lane, double& rinv_out, double& piv_out) {
-  bool ok = true;
-  rinv_out = 1.0; piv_out = 1.0;
-#pragma unroll
-  for (int c = 0; c < 32; ++c) {
-    double dcc = __shfl_sync(FULLMASK, a[c], c);
-    if (!(dcc > 0.0) || !(dcc < 1.0e300)) ok = false;
-    double rinv = rsqrt(dcc);
-    double l = a[c] * rinv;
-    a[c] = l;
-    if (lane == c) { rinv_out = rinv; piv_out = dcc; }
-#pragma unroll
-    for (int c2 = c + 1; c2 < 32; ++c2) {
-      double l2 = __shfl_sync(FULLMASK, l, c2);
-      a[c2] = fma(-l, l2, a[c2]);
-    }
-  }
-  return ok;
+// 1/sqrt(x) from the MUFU seed (rel. error ~2^-22) and two Newton steps; no special-case slow path (callers reject
+// non-positive / non-finite pivots through the running minimum instead).
+__device__ __forceinline__ double rsqrt_nr(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x * y, y, 1.0);
+  y = fma(0.5 * y, e, y);
+  e = fma(-x * y, y, 1.0);
+  y = fma(0.5 * y, e, y);
+  return y;
 }
 
-// X <- X L^-T for one 32-row block, lane = row of X.  sD: L (row-major, stride DS), sRinv[c] = 1/L[c][c]
-__device__ __forceinline__ void trsm_warp(double (&a)[32], const double* __restrict__ sD, const double* __restrict__ sRinv) {
+// Cholesky of a 32x32 tile by one warp, lane = row, a[c] = A[lane][c] in registers.
+// Column c of L is published column-major in shared memory (DT[c*32 + r] = L[r][c]) and read back with broadcast
+// LDS.128 -- no 64-bit shuffles in the update -- and the next pivot is formed early by its own lane
+// (a[c+1][c+1] - L[c+1][c]^2 only needs that lane's values), so the dependent chain per column is
+// mul -> fma -> shfl -> rsqrt.  dpotf2's failure rule (pivot <= 0 or NaN) is evaluated once from the running
+// minimum pivot.  rinv[c] = 1/L[c][c] and piv[c] = pivot before the square root go to shared memory.
+// Returns false on failure.  On exit a[c] = L[lane][c] for c <= lane (entries above the diagonal are garbage).
+__device__ __forceinline__ bool potrf_warp(double (&a)[32], int lane, double* __restrict__ DT, double* __restrict__ rinv_out,
+                                           double* __restrict__ piv_out) {
+  double piv = __shfl_sync(FULLMASK, a[0], 0);
+  double dmin = piv, dmax = piv;
+  double rinv = rsqrt_nr(piv);
 #pragma unroll
   for (int c = 0; c < 32; ++c) {
-    double x = a[c] * sRinv[c];
-    a[c] = x;
+    const double l = a[c] * rinv;
+    a[c] = l;
+    DT[c * TB + lane] = l;
+    if (lane == c) { rinv_out[c] = rinv; piv_out[c] = piv; }
+    if (c < 31) {
+      const double pn = fma(-l, l, a[c + 1]);
+      piv = __shfl_sync(FULLMASK, pn, c + 1);
+      dmin = fmin(dmin, piv);
+      dmax = fmax(dmax, piv);
+      rinv = rsqrt_nr(piv);
+    }
+    __syncwarp();
+    if (c < 31) {
+      // L[c2][c] for c2 > c: broadcast reads of the column just published
+      if ((c + 1) & 1) a[c + 1] = fma(-l, DT[c * TB + c + 1], a[c + 1]);
 #pragma unroll
-    for (int c2 = c + 1; c2 < 32; ++c2) a[c2] = fma(-x, sD[c2 * DS + c], a[c2]);
+      for (int c2 = (c + 2) & ~1; c2 < 32; c2 += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(DT + c * TB + c2);
+        a[c2] = fma(-l, v.x, a[c2]);
+        a[c2 + 1] = fma(-l, v.y, a[c2 + 1]);
+      }
+    }
+  }
+  // fmin/fmax drop NaNs: a NaN pivot makes every later entry NaN, caught by the self-comparison of the last one
+  return (dmin > 0.0) && (dmax < 1.0e300) && (piv == piv);
+}
+
+// X <- X L^-T for one 32-row block, lane = row of X.  DT: L column-major (DT[c*32 + r] = L[r][c]), sRinv[c] = 1/L[c][c]
+__device__ __forceinline__ void trsm_warp(double (&a)[32], const double* __restrict__ DT, const double* __restrict__ sRinv) {
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    const double x = a[c] * sRinv[c];
+    a[c] = x;
+    if (c < 31) {
+      if ((c + 1) & 1) a[c + 1] = fma(-x, DT[c * TB + c + 1], a[c + 1]);
+#pragma unroll
+      for (int c2 = (c + 2) & ~1; c2 < 32; c2 += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(DT + c * TB + c2);
+        a[c2] = fma(-x, v.x, a[c2]);
+        a[c2 + 1] = fma(-x, v.y, a[c2 + 1]);
+      }
+    }
   }
 }
 
@@ -192,33 +228,69 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 
 // shared-memory footprint (doubles) of the engine for NT matrix tile rows + NE extra panel slots
 __host__ __device__ inline size_t engine_smem_doubles(int NT, int NE) {
-  return (size_t)TB * DS + (size_t)(NT + NE) * TB * PS + (size_t)NT * TB /*rinv*/ + (size_t)NT * TB /*dvec*/ +
-         (size_t)(NE > 0 ? NE : 1) * NT /*quadpart*/ + 16;
+  return (size_t)TILE /*DT*/ + (size_t)(NT + NE) * TB * PS + (size_t)NT * TB /*rinv*/ + (size_t)NT * TB /*dvec*/ +
+         (size_t)TB /*piv*/ + (size_t)(NE > 0 ? NE : 1) * NT /*quadpart*/ + 16;
 }
 
 struct EngineSmem {
-  double* D;      // 32 x DS
+  double* DT;     // 32 x 32, current diagonal factor, column-major: DT[c*32 + r] = L_kk[r][c]
   double* P;      // (NT+NE) slots of 32 x PS
   double* rinv;   // NT*32 reciprocal diagonal of L
   double* dvec;   // NT*32 additive diagonal applied at first touch (jitter, offset, n_t/sigma_y; 0 on padding)
+  double* piv;    // 32 pivots of the current diagonal tile
   double* quad;   // NE*NT partial sums of squares of finished augmented rows (deterministic reduction)
   double* scal;   // [0] logdet, [1] fail flag (as double), [2..9] block_sum scratch, spare
   __device__ EngineSmem(double* base, int NT, int NE) {
-    D = base;
-    P = D + TB * DS;
+    DT = base;
+    P = DT + TILE;
     rinv = P + (size_t)(NT + NE) * TB * PS;
     dvec = rinv + NT * TB;
-    quad = dvec + NT * TB;
+    piv = dvec + NT * TB;
+    quad = piv + TB;
     scal = quad + (size_t)(NE > 0 ? NE : 1) * NT;
   }
   __device__ double* red() const { return scal + 2; }
 };
 
+// ---- first-touch sources of the matrix (step k = 0 reads the matrix from here, later steps from the workspace) ----
+// tiles in memory, packed lower-triangular by tile
+struct SrcTiles {
+  const double* A0;
+  __device__ __forceinline__ void rows(double (&a)[32], int bi, int bj, int lane) const {
+    rows_load(a, A0 + (size_t)plt(bi, bj) * TILE, lane);
+  }
+  __device__ __forceinline__ void cfrag(CFrag& f, int bi, int bj, int g, int tig) const {
+    cfrag_load(f, A0 + (size_t)plt(bi, bj) * TILE, g, tig, 4);
+  }
+};
+// stationary kernel on a uniform grid: K[i][j] = tab[|i-j|] (tab in shared memory, sigma folded in); identity padding
+struct SrcToeplitz {
+  const double* tab;
+  int n;
+  __device__ __forceinline__ double at(int R, int Cc) const {
+    if (R >= n || Cc >= n) return (R == Cc) ? 1.0 : 0.0;
+    const int d = R - Cc;
+    return tab[d < 0 ? -d : d];
+  }
+  __device__ __forceinline__ void rows(double (&a)[32], int bi, int bj, int lane) const {
+#pragma unroll
+    for (int c = 0; c < 32; ++c) a[c] = at(bi * TB + lane, bj * TB + c);
+  }
+  __device__ __forceinline__ void cfrag(CFrag& f, int bi, int bj, int g, int tig) const {
+#pragma unroll
+    for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+      for (int tj = 0; tj < 4; ++tj) {
+        f.c[ti][tj][0] = at(bi * TB + 8 * ti + g, bj * TB + 8 * tj + 2 * tig);
+        f.c[ti][tj][1] = at(bi * TB + 8 * ti + g, bj * TB + 8 * tj + 2 * tig + 1);
+      }
+  }
+};
+
 struct EngineIO {
-  const double* A0;   // first-touch source of the matrix tiles (plt layout, padded rows = identity); may alias W
-  double* W;          // plt_tiles(NT) tiles of workspace; with KEEPL the final L tiles are left there
-  double* Wx;         // AUG_RHS: NE*NT tiles of in-flight right-hand-side rows.  AUG_IDENT: unused; the inverse
-                      // (lower tiles, full diagonal tiles) is left in W
+  double* W;          // plt_tiles(NT) tiles of workspace; with KEEPL the final L tiles are left there.
+                      // AUG_IDENT: the inverse (lower tiles, full diagonal tiles) is left in W
+  double* Wx;         // AUG_RHS: NE*NT tiles of in-flight right-hand-side rows
   RowSrc rows;        // AUG_RHS: first-touch source of the extra rows
   double* vout;       // AUG_RHS: finished rows r < rows.nrows are written to vout[r*ldv + col] (may be nullptr)
   int ldv;
@@ -228,36 +300,32 @@ struct EngineIO {
  *   AUG_RHS  : NE extra tile rows; the last extra tile row uses only nti_last 8-row strips.
  * Returns false if a pivot failed (matrix not PD); logdet (= 2 sum log L_ii) is in sm.scal[0] on success,
  * sm.quad[e*NT+k] hold the sums of squares of the finished augmented rows. */
-template <int AUG, bool KEEPL>
-__device__ bool chol_engine(const EngineIO& io, int NT, int NE, int nti_last, const EngineSmem& sm) {
+template <int AUG, bool KEEPL, class Src>
+__device__ __forceinline__ bool chol_engine(const Src& src, const EngineIO& io, int NT, int NE, int nti_last,
+                                            const EngineSmem& sm) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
-  const double* A0 = io.A0;
   double* W = io.W;
   double* Wx = io.Wx;
   if (tid == 0) { sm.scal[0] = 0.0; sm.scal[1] = 0.0; }
   __syncthreads();
   for (int k = 0; k < NT; ++k) {
-    const double* S = (k == 0) ? A0 : W;
     // ---------------- phase 1: factor the diagonal tile (warp 0) ----------------
     if (warp == 0) {
       double a[32];
-      rows_load(a, S + (size_t)plt(k, k) * TILE, lane);
       if (k == 0) {
+        src.rows(a, 0, 0, lane);
         const double dv = sm.dvec[lane];
 #pragma unroll
         for (int c = 0; c < 32; ++c) if (c == lane) a[c] += dv;
-      }
-      double rinv, piv;
-      bool ok = potrf_warp(a, lane, rinv, piv);
+      } else rows_load(a, W + (size_t)plt(k, k) * TILE, lane);
+      const bool ok = potrf_warp(a, lane, sm.DT, sm.rinv + k * TB, sm.piv);
+      __syncwarp();
+      const double lg = warp_sum(log(sm.piv[lane]));
+      if (KEEPL) {
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        double v = (c <= lane) ? a[c] : 0.0;
-        a[c] = v;
-        sm.D[lane * DS + c] = v;
+        for (int c = 0; c < 32; ++c) a[c] = (c <= lane) ? a[c] : 0.0;
+        rows_store(a, W + (size_t)plt(k, k) * TILE, lane);
       }
-      sm.rinv[k * TB + lane] = rinv;
-      double lg = warp_sum(log(piv));
-      if (KEEPL) rows_store(a, W + (size_t)plt(k, k) * TILE, lane);
       if (lane == 0) { sm.scal[0] += lg; if (!ok) sm.scal[1] = 1.0; }
     }
     __syncthreads();
@@ -271,7 +339,8 @@ __device__ bool chol_engine(const EngineIO& io, int NT, int NE, int nti_last, co
       if (t < nreg) {
         const int i = k + 1 + t;
         slot = i;
-        rows_load(a, S + (size_t)plt(i, k) * TILE, lane);
+        if (k == 0) src.rows(a, i, 0, lane);
+        else rows_load(a, W + (size_t)plt(i, k) * TILE, lane);
       } else {
         const int e = t - nreg;
         if (AUG == AUG_RHS) {
@@ -292,10 +361,10 @@ __device__ bool chol_engine(const EngineIO& io, int NT, int NE, int nti_last, co
           } else rows_load(a, W + (size_t)plt(k, e) * TILE, lane);
         }
       }
-      trsm_warp(a, sm.D, sm.rinv + k * TB);
+      trsm_warp(a, sm.DT, sm.rinv + k * TB);
       double* ps = sm.P + (size_t)slot * TB * PS + lane * PS;
 #pragma unroll
-      for (int c = 0; c < 32; ++c) ps[c] = a[c];
+      for (int c = 0; c < 32; c += 2) *reinterpret_cast<double2*>(ps + c) = make_double2(a[c], a[c + 1]);
       if (t < nreg) {
         if (KEEPL) rows_store(a, W + (size_t)plt(k + 1 + t, k) * TILE, lane);
       } else if (AUG == AUG_RHS) {
@@ -323,8 +392,10 @@ __device__ bool chol_engine(const EngineIO& io, int NT, int NE, int nti_last, co
         int ii = 0, tt = t;
         while (tt > ii) { tt -= ii + 1; ++ii; }
         const int i = k + 1 + ii, j = k + 1 + tt;
-        cfrag_load(f, S + (size_t)plt(i, j) * TILE, g, tig, 4);
-        if (k == 0 && i == j) cfrag_add_diag(f, sm.dvec + i * TB, g, tig);
+        if (k == 0) {
+          src.cfrag(f, i, j, g, tig);
+          if (i == j) cfrag_add_diag(f, sm.dvec + i * TB, g, tig);
+        } else cfrag_load(f, W + (size_t)plt(i, j) * TILE, g, tig, 4);
         tile_mma<true>(f, sm.P + (size_t)i * TB * PS, sm.P + (size_t)j * TB * PS, g, tig, 4);
         cfrag_store(f, W + (size_t)plt(i, j) * TILE, g, tig, 4);
       } else if (t < T1 + T2) {
