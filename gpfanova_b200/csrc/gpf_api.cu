@@ -12,6 +12,7 @@
 
 #include "../../include/gpfanova_b200.h"
 #include "gpf_kernels.cuh"
+#include "gpf_schur.cuh"
 
 using namespace gpf;
 
@@ -44,6 +45,8 @@ struct gpf_ctx {
   std::vector<Samp> order;
   std::vector<char> kinv_valid;
   bool toeplitz = false;
+  std::vector<int> schur_warps;       // per group: warps per CTA of the Schur slice kernel (0: dense engine)
+  int use_schur = 1;
   std::vector<void*> allocs;
   size_t smem_kinv = 0, smem_fn = 0;
   std::vector<size_t> smem_prior;
@@ -124,6 +127,7 @@ int dev_alloc(gpf_ctx* c, T** p, size_t count) {
 
 int launch_kinv(gpf_ctx* c, int g) {
   Timer t(c, 1);
+  CK(c, cudaMemsetAsync(c->dev.sched, 0, sizeof(int), c->stream));
   if (c->toeplitz) k_group_kinv<true><<<c->grid, NTHR, c->smem_kinv, c->stream>>>(c->dev, g);
   else k_group_kinv<false><<<c->grid, NTHR, c->smem_kinv, c->stream>>>(c->dev, g);
   ++c->launches;
@@ -139,6 +143,7 @@ int launch_function(gpf_ctx* c, int fn, unsigned sampler_id, unsigned sweep, con
     if (rc) return rc;
   }
   Timer t(c, 2);
+  CK(c, cudaMemsetAsync(c->dev.sched, 0, sizeof(int), c->stream));
   k_function<<<c->grid, NTHR, c->smem_fn, c->stream>>>(c->dev, fn, sampler_id, sweep, z, out);
   ++c->launches;
   CK(c, cudaGetLastError());
@@ -151,7 +156,13 @@ int launch_prior(gpf_ctx* c, int g, int mode, const double* cand, double* outv, 
   Timer t(c, 3);
   PriorArgs a{g, mode, cand, outv, c->slice_w[1 + 2 * g], c->slice_w[2 + 2 * g], c->slice_m[1 + 2 * g], c->slice_m[2 + 2 * g],
               sampler_id, sweep, u, nu, nev};
-  if (c->toeplitz) k_prior<true><<<c->grid, NTHR, c->smem_prior[g], c->stream>>>(c->dev, a);
+  CK(c, cudaMemsetAsync(c->dev.sched, 0, sizeof(int), c->stream));
+  if (c->toeplitz && c->use_schur && c->schur_warps[g] > 0) {
+    const int wpc = c->schur_warps[g], ng = (int)c->groups[g].size();
+    const size_t smem = (size_t)wpc * schur_warp_doubles(c->dev.n, ng) * sizeof(double);
+    const int grid = std::min((c->dev.C + wpc - 1) / wpc, 2 * c->sms);
+    k_prior_schur<<<grid, wpc * 32, smem, c->stream>>>(c->dev, a);
+  } else if (c->toeplitz) k_prior<true><<<c->grid, NTHR, c->smem_prior[g], c->stream>>>(c->dev, a);
   else k_prior<false><<<c->grid, NTHR, c->smem_prior[g], c->stream>>>(c->dev, a);
   ++c->launches;
   CK(c, cudaGetLastError());
@@ -303,6 +314,12 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
     c->smem_prior[g] = (engine_smem_doubles(v.NT, NE) + xsd) * sizeof(double);
     smax = std::max(smax, c->smem_prior[g]);
   }
+  c->schur_warps.assign(d->P, 0);
+  for (int g = 0; g < d->P; ++g) {
+    const size_t per_warp = schur_warp_doubles(d->n, (int)c->groups[g].size()) * sizeof(double);
+    const int w = (int)std::min<size_t>(NW, (110 * 1024) / per_warp);   // two CTAs per SM
+    c->schur_warps[g] = w;                                            // 0: vectors do not fit -> dense engine
+  }
   if (smax > smem_limit()) {
     c->err = "gpf_create: n / prior-group size exceed the shared-memory budget of the tile engine";
     return fail(GPF_ERR_UNSUPPORTED);
@@ -314,6 +331,7 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
     if (e == cudaSuccess) e = allow_smem(k_function, c->smem_fn);
     if (e == cudaSuccess) e = allow_smem(k_prior<true>, sp);
     if (e == cudaSuccess) e = allow_smem(k_prior<false>, sp);
+    if (e == cudaSuccess) e = allow_smem(k_prior_schur, 112 * 1024);
     if (e != cudaSuccess) { c->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return fail(GPF_ERR_CUDA); }
   }
   c->grid = std::min(v.C, 2 * c->sms);
@@ -322,7 +340,7 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
   v.ws_stride = tstride + (size_t)v.NEmax * v.NT * TILE;
   double *dx, *dyT, *dX, *dF, *dh, *dK, *dws, *dd2, *dG, *dZ;
   unsigned char* dfull;
-  int *dgof, *dgf, *dgo, *dst;
+  int *dgof, *dgf, *dgo, *dst, *dsched;
   unsigned long long* dcn;
   int rc;
   if ((rc = dev_alloc(c, &dx, (size_t)d->n * d->p)) || (rc = dev_alloc(c, &dyT, (size_t)d->n * d->m)) ||
@@ -331,7 +349,7 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
       (rc = dev_alloc(c, &dws, (size_t)c->grid * v.ws_stride)) || (rc = dev_alloc(c, &dgof, (size_t)d->f)) ||
       (rc = dev_alloc(c, &dgf, (size_t)d->f)) || (rc = dev_alloc(c, &dgo, (size_t)d->P + 1)) ||
       (rc = dev_alloc(c, &dst, (size_t)v.C)) || (rc = dev_alloc(c, &dcn, (size_t)CNT_N)) ||
-      (rc = dev_alloc(c, &dd2, (size_t)d->n)) || (rc = dev_alloc(c, &dG, (size_t)d->f * d->f)) ||
+      (rc = dev_alloc(c, &dsched, (size_t)4)) || (rc = dev_alloc(c, &dd2, (size_t)d->n)) || (rc = dev_alloc(c, &dG, (size_t)d->f * d->f)) ||
       (rc = dev_alloc(c, &dZ, (size_t)d->f * d->n)) || (rc = dev_alloc(c, &dfull, (size_t)d->n)))
     return fail(rc);
   // uniform grid?  then every RBF matrix is Toeplitz: K[i][j] = k(|i-j| h) and needs one exp per lag
@@ -386,6 +404,7 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
   if (e == cudaSuccess) e = cudaMemset(dcn, 0, sizeof(unsigned long long) * CNT_N);
   if (e != cudaSuccess) { c->err = std::string("gpf_create: upload: ") + cudaGetErrorString(e); return fail(GPF_ERR_CUDA); }
   v.x = dx; v.yT = dyT; v.X = dX; v.F = dF; v.hyper = dh; v.Kinv = dK; v.ws = dws;
+  v.sched = dsched;
   v.d2 = dd2; v.G = dG; v.Z = dZ; v.full = dfull;
   v.group_of_fn = dgof; v.group_fns = dgf; v.group_off = dgo; v.status = dst; v.counters = dcn;
   *out = c;
@@ -567,6 +586,12 @@ int gpf_sweep(gpf_ctx* c, int n_sweeps, int thin, unsigned sweep0, const int* h_
     cudaEventDestroy(t0); cudaEventDestroy(t1);
   }
   return GPF_OK;
+}
+
+int gpf_set_option(gpf_ctx* c, int option, int value) {
+  if (option == 0) { c->use_schur = value; return GPF_OK; }
+  c->err = "gpf_set_option: unknown option";
+  return GPF_ERR_ARG;
 }
 
 int gpf_set_profile(gpf_ctx* c, int on) { c->profile = on != 0; return GPF_OK; }

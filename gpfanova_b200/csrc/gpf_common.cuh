@@ -37,7 +37,17 @@ struct CtxDev {
   const double* G;            // f x f   X^T X
   const double* Z;            // f x n   X^T y over the observed entries (NaN -> 0)
   const unsigned char* full;  // n       1 if no observation is missing at time t
+  int* sched;                 // chain hand-out counter of the running launch (reset to 0 by the host before it)
 };
+
+// dynamic hand-out of chains to CTAs (chains differ in the number of slice evaluations they need): returns the next
+// chain index to every thread; >= C when the launch is exhausted.  slot: one int of shared memory.
+__device__ __forceinline__ int next_chain(int* sched, int* slot) {
+  __syncthreads();
+  if (threadIdx.x == 0) *slot = atomicAdd(sched, 1);
+  __syncthreads();
+  return *slot;
+}
 
 __device__ __forceinline__ void status_merge(int* st, int code) {
   const int old = *st;

@@ -133,7 +133,8 @@ __global__ void __launch_bounds__(NTHR, 2) k_group_kinv(CtxDev c, int g) {
   double* xs = smem_base() + engine_smem_doubles(c.NT, 0);   // TOEP: lag table (n); else scaled inputs (n*p) + xsq (n)
   double* xsq = xs + (size_t)c.n * c.p;
   const size_t tstride = (size_t)plt_tiles(c.NT) * TILE;
-  for (int ch = blockIdx.x; ch < c.C; ch += gridDim.x) {
+  __shared__ int s_chain;
+  for (int ch = next_chain(c.sched, &s_chain); ch < c.C; ch = next_chain(c.sched, &s_chain)) {
     const double sigma = exp10(c.hyper[(size_t)ch * c.H + 1 + 2 * g]);
     const double ls = exp10(c.hyper[(size_t)ch * c.H + 2 + 2 * g]);
     double* W = c.Kinv + ((size_t)g * c.C + ch) * tstride;
@@ -191,7 +192,8 @@ __global__ void __launch_bounds__(NTHR, 2) k_function(CtxDev c, int fn, unsigned
   double* Wx = W + tstride;
   const Stream rng{c.k0, c.k1};
   const double* Grow = c.G + (size_t)fn * c.f;
-  for (int ch = blockIdx.x; ch < c.C; ch += gridDim.x) {
+  __shared__ int s_chain;
+  for (int ch = next_chain(c.sched, &s_chain); ch < c.C; ch = next_chain(c.sched, &s_chain)) {
     const double* Fc = c.F + (size_t)ch * c.f * n;
     const double* A0 = c.Kinv + ((size_t)g * c.C + ch) * tstride;
     const double yinv = 1.0 / (exp10(c.hyper[(size_t)ch * c.H]) + c.offset);   // white.py:7-9 through kernel.pyx:51-64
@@ -363,6 +365,14 @@ struct PriorArgs {
   int* nevals;       // mode 2/3: evaluations of that step; mode 4: sigma step, nevals[C + ch]: lengthscale step
 };
 
+// slice-step state of one chain, kept in shared memory and advanced by thread 0 only (keeps the registers of the
+// other 255 threads for the factorisation)
+struct PriorState {
+  SliceSM sl, ss;
+  double s_fact, l_eval, result;
+  int base, running, inb, nfact, failed, nev_s;
+};
+
 template <bool TOEP>
 __global__ void __launch_bounds__(NTHR, 2) k_prior(CtxDev c, PriorArgs a) {
   const int NT = c.NT, n = c.n, g = a.g, mode = a.mode;
@@ -375,43 +385,35 @@ __global__ void __launch_bounds__(NTHR, 2) k_prior(CtxDev c, PriorArgs a) {
   double* W = c.ws + (size_t)blockIdx.x * c.ws_stride;
   double* Wx = W + (size_t)plt_tiles(NT) * TILE;
   const int* fns = c.group_fns + c.group_off[g];
-  const Stream rng{c.k0, c.k1};
-  const double lb = c.prior_lb, ub = c.prior_ub;
-  const double lprior = -log(ub - lb);
-  const double nlog2pi = (double)n * LOG2PI;
-  for (int ch = blockIdx.x; ch < c.C; ch += gridDim.x) {
-    const unsigned gch = (unsigned)(ch + c.chain_offset);
+  __shared__ PriorState st;
+  __shared__ int s_chain;
+  for (int ch = next_chain(c.sched, &s_chain); ch < c.C; ch = next_chain(c.sched, &s_chain)) {
     const double cur_s = c.hyper[(size_t)ch * c.H + 1 + 2 * g];
     const double cur_l = c.hyper[(size_t)ch * c.H + 2 + 2 * g];
-    auto unif_s = [&](int k) {
-      return (a.u_inject && mode == 2 && k < a.n_inject) ? a.u_inject[(size_t)ch * a.n_inject + k]
-                                                          : rng.uniform(gch, a.sweep, a.sampler_id, (unsigned)k);
-    };
-    const unsigned sid_l = a.sampler_id + (mode == 4 ? 1u : 0u);
-    auto unif_l = [&](int k) {
-      return (a.u_inject && mode == 3 && k < a.n_inject) ? a.u_inject[(size_t)ch * a.n_inject + k]
-                                                          : rng.uniform(gch, a.sweep, sid_l, (unsigned)k);
-    };
-    bool base = (mode == 0 || mode == 2 || mode == 4);   // next factorisation is the one at the current (sigma, ls)
-    double s_fact = cur_s, l_eval = cur_l, result = 0.0;
-    SliceSM sl;
-    sl.init(cur_l, a.w_l, a.m_l);
-    if (mode == 1) l_eval = a.cand[ch];
-    int nfact = 0, failed = 0, nev_s = 0;
-    bool running = true;
-    while (running) {
-      const bool inb = base || (l_eval >= lb && l_eval <= ub);   // base.py:224-231: outside the prior -> -inf
-      double ld = 0.0, q = 0.0;
+    if (threadIdx.x == 0) {
+      st.base = (mode == 0 || mode == 2 || mode == 4);   // next factorisation is the one at the current (sigma, ls)
+      st.s_fact = cur_s;
+      st.l_eval = (mode == 1) ? a.cand[ch] : cur_l;
+      st.result = 0.0;
+      st.sl.init(cur_l, a.w_l, a.m_l);
+      st.nfact = st.failed = st.nev_s = 0;
+      st.running = 1;
+      st.inb = st.base || (st.l_eval >= c.prior_lb && st.l_eval <= c.prior_ub);   // base.py:224-231: outside -> -inf
+    }
+    for (;;) {
+      __syncthreads();
+      if (!st.running) break;
+      const bool inb = st.inb != 0;
       bool ok = true;
       if (inb) {
         // ---- the factorisation: cov = K(10^s_fact, 10^l_eval) + mean(K) 1e-6 I, group functions as right-hand sides ----
-        __syncthreads();
+        const double sig = exp10(st.s_fact), ls = exp10(st.l_eval);
         double tot;
-        if constexpr (TOEP) tot = toeplitz_table(c.d2, n, exp10(s_fact), exp10(l_eval), xs, sm.red());
+        if constexpr (TOEP) tot = toeplitz_table(c.d2, n, sig, ls, xs, sm.red());
         else {
-          rbf_scale_inputs(c.x, n, c.p, exp10(l_eval), xs, xsq);
+          rbf_scale_inputs(c.x, n, c.p, ls, xs, xsq);
           __syncthreads();
-          tot = rbf_fill_tiles(W, NT, n, c.p, xs, xsq, exp10(s_fact), sm.red());
+          tot = rbf_fill_tiles(W, NT, n, c.p, xs, xsq, sig, sm.red());
         }
         const double jit = tot / ((double)n * (double)n) * c.prior_jitter;   // base.py:222
         for (int t = threadIdx.x; t < NT * TB; t += NTHR) sm.dvec[t] = (t < n) ? jit : 0.0;
@@ -419,65 +421,80 @@ __global__ void __launch_bounds__(NTHR, 2) k_prior(CtxDev c, PriorArgs a) {
         EngineIO io{W, Wx, RowSrc{c.F + (size_t)ch * c.f * n, fns, n, ng, n}, nullptr, 0};
         if constexpr (TOEP) ok = chol_engine<AUG_RHS, false>(SrcToeplitz{xs, n}, io, NT, NE, nti_last, sm);
         else ok = chol_engine<AUG_RHS, false>(SrcTiles{W}, io, NT, NE, nti_last, sm);
-        ++nfact;
-        if (ok) { ld = sm.scal[0]; q = engine_quad_total(sm, NT, NE); }
-        else failed = 1;
       }
-      if (base) {
-        base = false;
-        // density of a sigma candidate v by exact rescaling of the factorisation at cur_s (base.py:235-243)
-        auto lp_s = [&](double v, double pr) -> double {
-          if (!ok) return -(double)INFINITY;
-          const double dl = v - cur_s;
-          return 1.0 - 0.5 * ((double)ng * (nlog2pi + ld + (double)n * LN10 * dl) + q * exp10(-dl)) + pr;
+      if (threadIdx.x == 0) {
+        // ---- thread 0 advances the slice state machine(s) with this evaluation ----
+        const Stream rng{c.k0, c.k1};
+        const unsigned gch = (unsigned)(ch + c.chain_offset);
+        const double lb = c.prior_lb, ub = c.prior_ub, lprior = -log(ub - lb), nlog2pi = (double)n * LOG2PI;
+        double ld = 0.0, q = 0.0;
+        if (inb) {
+          ++st.nfact;
+          if (ok) { ld = sm.scal[0]; q = engine_quad_total(sm, NT, NE); }
+          else st.failed = 1;
+        }
+        const unsigned sid_l = a.sampler_id + (mode == 4 ? 1u : 0u);
+        auto unif_s = [&](int k) {
+          return (a.u_inject && mode == 2 && k < a.n_inject) ? a.u_inject[(size_t)ch * a.n_inject + k]
+                                                              : rng.uniform(gch, a.sweep, a.sampler_id, (unsigned)k);
         };
-        auto prior_of = [&](double v) -> double { return (v < lb || v > ub) ? -(double)INFINITY : lprior; };
-        if (mode == 0) {
-          result = lp_s(a.cand[ch], prior_of(a.cand[ch]));
-          running = false;
+        auto unif_l = [&](int k) {
+          return (a.u_inject && mode == 3 && k < a.n_inject) ? a.u_inject[(size_t)ch * a.n_inject + k]
+                                                              : rng.uniform(gch, a.sweep, sid_l, (unsigned)k);
+        };
+        if (st.base) {
+          st.base = 0;
+          // density of a sigma candidate v by exact rescaling of the factorisation at cur_s (base.py:235-243)
+          auto lp_s = [&](double v, double pr) -> double {
+            if (!ok) return -(double)INFINITY;
+            const double dl = v - cur_s;
+            return 1.0 - 0.5 * ((double)ng * (nlog2pi + ld + (double)n * LN10 * dl) + q * exp10(-dl)) + pr;
+          };
+          auto prior_of = [&](double v) -> double { return (v < lb || v > ub) ? -(double)INFINITY : lprior; };
+          if (mode == 0) {
+            st.result = lp_s(a.cand[ch], prior_of(a.cand[ch]));
+            st.running = 0;
+          } else {
+            st.ss.init(cur_s, a.w_s, a.m_s);
+            while (!st.ss.done) st.ss.feed(lp_s(st.ss.cand, prior_of(st.ss.cand)), unif_s);
+            st.nev_s = st.ss.nev;
+            const double new_s = st.ss.cand;
+            c.hyper[(size_t)ch * c.H + 1 + 2 * g] = new_s;
+            if (mode == 2) st.running = 0;
+            else {
+              st.s_fact = new_s;
+              st.sl.feed(lp_s(new_s, prior_of(cur_l)), unif_l);   // density of the current lengthscale under the new sigma
+              st.l_eval = st.sl.cand;
+            }
+          }
         } else {
-          SliceSM ss;
-          ss.init(cur_s, a.w_s, a.m_s);
-          while (!ss.done) ss.feed(lp_s(ss.cand, prior_of(ss.cand)), unif_s);
-          nev_s = ss.nev;
-          const double new_s = ss.cand;
-          __syncthreads();
-          if (threadIdx.x == 0) c.hyper[(size_t)ch * c.H + 1 + 2 * g] = new_s;
-          if (mode == 2) running = false;
+          const double lp = (inb && ok) ? 1.0 - 0.5 * ((double)ng * (nlog2pi + ld) + q) + lprior : -(double)INFINITY;
+          if (mode == 1) { st.result = lp; st.running = 0; }
           else {
-            s_fact = new_s;
-            sl.feed(lp_s(new_s, prior_of(cur_l)), unif_l);   // log density of the current lengthscale under the new sigma
-            l_eval = sl.cand;
+            st.sl.feed(lp, unif_l);
+            if (st.sl.done) {
+              st.running = 0;
+              c.hyper[(size_t)ch * c.H + 2 + 2 * g] = st.sl.cand;
+            } else st.l_eval = st.sl.cand;
           }
         }
-      } else {
-        const double lp = (inb && ok) ? 1.0 - 0.5 * ((double)ng * (nlog2pi + ld) + q) + lprior : -(double)INFINITY;
-        if (mode == 1) { result = lp; running = false; }
-        else {
-          sl.feed(lp, unif_l);
-          if (sl.done) {
-            running = false;
-            __syncthreads();
-            if (threadIdx.x == 0) c.hyper[(size_t)ch * c.H + 2 + 2 * g] = sl.cand;
-          } else l_eval = sl.cand;
+        st.inb = (st.l_eval >= lb && st.l_eval <= ub);
+        if (!st.running) {
+          if (mode <= 1) a.outv[ch] = st.result;
+          if (st.failed) status_merge(c.status + ch, GPF_STATUS_NOT_PD);
+          atomicAdd(c.counters + CNT_CHOL, (unsigned long long)st.nfact);
+          if (mode >= 2) {
+            const int nev_total = (mode == 2 ? st.nev_s : (mode == 3 ? st.sl.nev : st.nev_s + st.sl.nev));
+            if (a.nevals) {
+              a.nevals[ch] = (mode == 3) ? st.sl.nev : st.nev_s;
+              if (mode == 4) a.nevals[c.C + ch] = st.sl.nev;
+            }
+            atomicAdd(c.counters + CNT_LOGP, (unsigned long long)nev_total);
+            atomicAdd(c.counters + CNT_SLICE, mode == 4 ? 2ull : 1ull);
+          }
         }
       }
     }
-    if (threadIdx.x == 0) {
-      if (mode <= 1) a.outv[ch] = result;
-      if (failed) status_merge(c.status + ch, GPF_STATUS_NOT_PD);
-      atomicAdd(c.counters + CNT_CHOL, (unsigned long long)nfact);
-      if (mode >= 2) {
-        const int nev_total = (mode == 2 ? nev_s : (mode == 3 ? sl.nev : nev_s + sl.nev));
-        if (a.nevals) {
-          a.nevals[ch] = (mode == 3) ? sl.nev : nev_s;
-          if (mode == 4) a.nevals[c.C + ch] = sl.nev;
-        }
-        atomicAdd(c.counters + CNT_LOGP, (unsigned long long)nev_total);
-        atomicAdd(c.counters + CNT_SLICE, mode == 4 ? 2ull : 1ull);
-      }
-    }
-    __syncthreads();
   }
 }
 

@@ -1,0 +1,196 @@
+// Slice-sampler GP log-likelihood on a uniform time grid through the Schur algorithm.
+//
+// On a uniform grid the slice covariance  cov = K(sigma, ls) + mean(K) 1e-6 I  (base.py:221-222) is a symmetric
+// positive definite TOEPLITZ matrix  T[i][j] = t[|i-j|].  Its displacement  T - Z T Z^T = u^T u - v^T v  has rank 2
+// (u = t / sqrt(t0), v = u with v0 = 0), and the Schur algorithm turns the generator (u, v) into the columns of the
+// lower Cholesky factor, one column per step, with one hyperbolic rotation and O(n) work per step:
+//     column k of L  = u^(k)                      (stored from the diagonal down: us[j] = L[k+j][k])
+//     rho = v[k+1] / us[0],  c = sqrt(1 - rho^2)  (|rho| < 1  <=>  T positive definite)
+//     us'[j] = (us[j] - rho v[k+1+j]) / c,   v'[k+1+j] = c v[k+1+j] - rho us'[j]        (mixed, stable form)
+// so a whole evaluation is ~n^2 multiply-adds instead of n^3/3, needs no n x n storage, and L[k+1][k+1] = L[k][k] c.
+// The log-determinant comes from the rotation cosines, and the quadratic forms beta^T cov^-1 beta = |L^-1 beta|^2 of
+// the group's functions from a column-oriented forward substitution that consumes each column as it appears.
+// One WARP works on one chain (vectors in shared memory, lanes over the vector index); the Neal slice state machine
+// (SliceSM) runs redundantly in the warp's registers.  General (non-uniform) inputs use the dense engine (k_prior).
+// Stability: Bojanczyk, Brent, de Hoog & Sweet, "On the stability of the Bareiss and related Toeplitz factorization
+// algorithms" (1995) -- for positive definite T the computed factor satisfies a Cholesky-like backward error bound.
+#pragma once
+#include "gpf_common.cuh"
+
+namespace gpf {
+
+// shared memory per warp, in doubles: us, v, e (rotation 1 - rho^2 per step), tab, r[ng][n]
+__host__ __device__ inline size_t schur_warp_doubles(int n, int ng) { return (size_t)(4 + ng) * n; }
+
+struct SchurOut { double logdet, quad; bool ok; };
+
+// all lanes of the warp call this with identical arguments; smem regions are the warp's own
+__device__ __forceinline__ SchurOut schur_eval(const CtxDev& c, int n, int ng, const int* __restrict__ fns,
+                                               const double* __restrict__ Fc, double sigma, double ls, double* us, double* v,
+                                               double* ev, double* r, int lane) {
+  // lag table and its full-matrix sum (base.py:222's cov.mean())
+  const double s = -0.5 / (ls * ls);
+  double part = 0.0;
+  for (int k = lane; k < n; k += 32) {
+    const double t = sigma * exp(c.d2[k] * s);
+    us[k] = t;
+    part += (k == 0 ? (double)n : 2.0 * (double)(n - k)) * t;
+  }
+  part = warp_sum(part);
+  const double jit = part / ((double)n * (double)n) * c.prior_jitter;
+  __syncwarp();
+  const double t0 = us[0] + jit;
+  SchurOut out{0.0, 0.0, true};
+  if (!(t0 > 0.0) || !(t0 < 1.0e300)) { out.ok = false; return out; }
+  double uinv = rsqrt_nr(t0);                 // 1 / L[0][0]
+  __syncwarp();
+  for (int k = lane; k < n; k += 32) {
+    const double u = (k == 0 ? t0 : us[k]) * uinv;
+    us[k] = u;
+    v[k] = (k == 0) ? 0.0 : u;
+  }
+  for (int q = 0; q < ng; ++q)
+    for (int k = lane; k < n; k += 32) r[q * n + k] = Fc[(size_t)fns[q] * n + k];
+  __syncwarp();
+  double quad = 0.0;
+  bool ok = true;
+  for (int k = 0; k < n; ++k) {
+    const int m = n - 1 - k;                  // entries below the diagonal in column k
+    // ---- forward substitution with column k:  w = r[k] / L[k][k];  r[i] -= L[i][k] w  (i > k) ----
+    for (int q = 0; q < ng; ++q) {
+      double* rq = r + q * n + k;
+      const double w = rq[0] * uinv;
+      quad = fma(w, w, quad);
+      for (int j = 1 + lane; j <= m; j += 32) rq[j] = fma(-us[j], w, rq[j]);
+    }
+    if (m == 0) break;
+    // ---- hyperbolic rotation that produces column k+1 ----
+    const double rho = v[k + 1] * uinv;
+    const double e = fma(-rho, rho, 1.0);
+    if (!(e > 0.0)) { ok = false; break; }
+    const double cinv = rsqrt_nr(e);
+    const double cc = e * cinv;
+    if (lane == 0) ev[k] = e;
+    uinv *= cinv;                             // L[k+1][k+1] = L[k][k] c
+    __syncwarp();
+    for (int j = lane; j < m; j += 32) {
+      const double un = (us[j] - rho * v[k + 1 + j]) * cinv;
+      const double vn = fma(cc, v[k + 1 + j], -rho * un);
+      us[j] = un;
+      v[k + 1 + j] = vn;
+    }
+    __syncwarp();
+  }
+  if (!ok) { out.ok = false; return out; }
+  // logdet = 2 sum_k log L[k][k],  L[k][k] = sqrt(t0) prod_{j<k} sqrt(e_j)
+  __syncwarp();
+  double ld = 0.0;
+  for (int j = lane; j < n - 1; j += 32) ld += (double)(n - 1 - j) * log(ev[j]);
+  ld = warp_sum(ld);
+  out.logdet = (double)n * log(t0) + ld;
+  out.quad = quad;
+  return out;
+}
+
+// warp-level chain hand-out
+__device__ __forceinline__ int next_chain_warp(int* sched, int lane) {
+  int t = 0;
+  if (lane == 0) t = atomicAdd(sched, 1);
+  return __shfl_sync(FULLMASK, t, 0);
+}
+
+// same modes as k_prior (PriorArgs): 0/1 evaluate sigma / lengthscale candidate, 2/3 slice step, 4 fused sigma + ls
+__global__ void __launch_bounds__(NTHR) k_prior_schur(CtxDev c, PriorArgs a) {
+  extern __shared__ __align__(16) double gpf_smem_schur[];
+  const int n = c.n, g = a.g, mode = a.mode;
+  const int ng = c.group_off[g + 1] - c.group_off[g];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* base = gpf_smem_schur + (size_t)warp * schur_warp_doubles(n, ng);
+  double *us = base, *v = base + n, *ev = base + 2 * n, *r = base + 4 * n;   // base + 3n: spare (alignment of r)
+  const int* fns = c.group_fns + c.group_off[g];
+  const Stream rng{c.k0, c.k1};
+  const double lb = c.prior_lb, ub = c.prior_ub, lprior = -log(ub - lb), nlog2pi = (double)n * LOG2PI;
+  for (int ch = next_chain_warp(c.sched, lane); ch < c.C; ch = next_chain_warp(c.sched, lane)) {
+    const unsigned gch = (unsigned)(ch + c.chain_offset);
+    const double* Fc = c.F + (size_t)ch * c.f * n;
+    const double cur_s = c.hyper[(size_t)ch * c.H + 1 + 2 * g];
+    const double cur_l = c.hyper[(size_t)ch * c.H + 2 + 2 * g];
+    const unsigned sid_l = a.sampler_id + (mode == 4 ? 1u : 0u);
+    auto unif_s = [&](int k) {
+      return (a.u_inject && mode == 2 && k < a.n_inject) ? a.u_inject[(size_t)ch * a.n_inject + k]
+                                                          : rng.uniform(gch, a.sweep, a.sampler_id, (unsigned)k);
+    };
+    auto unif_l = [&](int k) {
+      return (a.u_inject && mode == 3 && k < a.n_inject) ? a.u_inject[(size_t)ch * a.n_inject + k]
+                                                          : rng.uniform(gch, a.sweep, sid_l, (unsigned)k);
+    };
+    bool basef = (mode == 0 || mode == 2 || mode == 4);
+    double s_fact = cur_s, l_eval = (mode == 1) ? a.cand[ch] : cur_l, result = 0.0;
+    SliceSM sl;
+    sl.init(cur_l, a.w_l, a.m_l);
+    int nfact = 0, failed = 0, nev_s = 0;
+    bool running = true;
+    while (running) {
+      const bool inb = basef || (l_eval >= lb && l_eval <= ub);   // base.py:224-231: outside the prior -> -inf
+      SchurOut o{0.0, 0.0, true};
+      if (inb) {
+        o = schur_eval(c, n, ng, fns, Fc, exp10(s_fact), exp10(l_eval), us, v, ev, r, lane);
+        ++nfact;
+        if (!o.ok) failed = 1;
+      }
+      if (basef) {
+        basef = false;
+        auto lp_s = [&](double x, double pr) -> double {   // exact rescaling cov(s') = (s'/s) cov(s), base.py:235-243
+          if (!o.ok) return -(double)INFINITY;
+          const double dl = x - cur_s;
+          return 1.0 - 0.5 * ((double)ng * (nlog2pi + o.logdet + (double)n * LN10 * dl) + o.quad * exp10(-dl)) + pr;
+        };
+        auto prior_of = [&](double x) -> double { return (x < lb || x > ub) ? -(double)INFINITY : lprior; };
+        if (mode == 0) {
+          result = lp_s(a.cand[ch], prior_of(a.cand[ch]));
+          running = false;
+        } else {
+          SliceSM ss;
+          ss.init(cur_s, a.w_s, a.m_s);
+          while (!ss.done) ss.feed(lp_s(ss.cand, prior_of(ss.cand)), unif_s);
+          nev_s = ss.nev;
+          const double new_s = ss.cand;
+          if (lane == 0) c.hyper[(size_t)ch * c.H + 1 + 2 * g] = new_s;
+          if (mode == 2) running = false;
+          else {
+            s_fact = new_s;
+            sl.feed(lp_s(new_s, prior_of(cur_l)), unif_l);
+            l_eval = sl.cand;
+          }
+        }
+      } else {
+        const double lp = (inb && o.ok) ? 1.0 - 0.5 * ((double)ng * (nlog2pi + o.logdet) + o.quad) + lprior : -(double)INFINITY;
+        if (mode == 1) { result = lp; running = false; }
+        else {
+          sl.feed(lp, unif_l);
+          if (sl.done) {
+            running = false;
+            if (lane == 0) c.hyper[(size_t)ch * c.H + 2 + 2 * g] = sl.cand;
+          } else l_eval = sl.cand;
+        }
+      }
+    }
+    if (lane == 0) {
+      if (mode <= 1) a.outv[ch] = result;
+      if (failed) status_merge(c.status + ch, GPF_STATUS_NOT_PD);
+      atomicAdd(c.counters + CNT_CHOL, (unsigned long long)nfact);
+      if (mode >= 2) {
+        const int nev_total = (mode == 2 ? nev_s : (mode == 3 ? sl.nev : nev_s + sl.nev));
+        if (a.nevals) {
+          a.nevals[ch] = (mode == 3) ? sl.nev : nev_s;
+          if (mode == 4) a.nevals[c.C + ch] = sl.nev;
+        }
+        atomicAdd(c.counters + CNT_LOGP, (unsigned long long)nev_total);
+        atomicAdd(c.counters + CNT_SLICE, mode == 4 ? 2ull : 1ull);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace gpf

@@ -287,6 +287,10 @@ class ChainEngine(object):
         self.sweeps_done = sweep0 + n_sweeps
         return int(rows.value)
 
+    def set_option(self, option, value):
+        """option 0: Toeplitz/Schur slice log-likelihood on uniform grids (1, default) or dense tile engine (0)"""
+        self._ck(self._lib.gpf_set_option(self._h, int(option), int(value)))
+
     def set_profile(self, on=True):
         self._ck(self._lib.gpf_set_profile(self._h, int(on)))
 

@@ -150,6 +150,9 @@ int gpf_sweep(gpf_ctx* ctx, int n_sweeps, int thin, unsigned sweep0, const int* 
 /* timing/accounting of the last gpf_sweep call, measured with CUDA events on the ctx stream:
  * h_ms[0] total, [1] kinv kernels, [2] function kernels, [3] slice kernels, [4] y_sigma kernel, [5] store.
  * Only filled when profiling was enabled with gpf_set_profile(ctx, 1) (adds event overhead). */
+/* options: 0 = use the O(n^2) Toeplitz (Schur algorithm) slice log-likelihood when the time grid is uniform
+ * (default 1; 0 forces the dense tile engine, which is always used for non-uniform inputs). */
+int gpf_set_option(gpf_ctx* ctx, int option, int value);
 int gpf_set_profile(gpf_ctx* ctx, int on);
 int gpf_get_profile(gpf_ctx* ctx, double* h_ms6, unsigned long long* h_launches);
 

@@ -209,8 +209,11 @@ def test_logliks_match_reference(eng, name):
                 # cov = K + mean(K) 1e-6 I has cond ~ 1e6 n: two FP64 evaluations of the quadratic form differ by
                 # ~ eps * cond (measured <= 5e-10, like the reference's eigh-vs-Cholesky spread of 2e-9);
                 # well-conditioned cases (n = 5) agree to 1e-10.  The arbiter test below bounds the error itself.
-                tol = 1e-10 if m.n <= 5 else 2e-9
-                assert abs(got[i] - o) <= tol * max(1.0, abs(o)), (name, g, which, cand, got[i], o)
+                ls_, ll_ = (cand, m.hyper[2 + 2 * g]) if which == "sigma" else (m.hyper[1 + 2 * g], cand)
+                Kc = orc.rbf_K(m.x, 10.0 ** ls_, 10.0 ** ll_)
+                condc = np.linalg.cond(Kc + Kc.mean() * 1e-6 * np.eye(m.n))
+                tol = max(1e-10, min(2e-9, 4 * EPS * condc))
+                assert abs(got[i] - o) <= tol * max(1.0, abs(o)), (name, g, which, cand, got[i], o, condc)
                 assert abs(got[i] - ref) <= 5e-9 * max(1.0, abs(ref))
     e.status()
     e.close()
@@ -239,11 +242,14 @@ def test_conditioning_limited_stages_against_arbiter(eng):
             cov = np.linalg.inv(LA @ LA.T)
             Ko = orc.K_inv(orc.rbf_K(m.x, 10.0 ** m.hyper[1 + 2 * g], 10.0 ** m.hyper[2 + 2 * g]))[0]
             so = orc.function_conditional(*orc.function_moments(m.y, m.X, m.F, f), m.hyper[0], Ko)
+            condA = np.linalg.cond(so["A"])
             for dev, tru, refs in ((Kd, T["%s/Kinv_%d" % (name, g)], (Ko, c["Kinv_%d" % g])),
                                    (mu, T["%s/mu_%d" % (name, f)], (so["mu"], c["mu_%d" % f])),
                                    (cov, T["%s/cov_%d" % (name, f)], (so["cov"], c["cov_%d" % f]))):
                 floor = max(relerr(r, tru) for r in refs)
-                assert relerr(dev, tru) <= max(1e-10, 3 * floor), (name, f, relerr(dev, tru), floor)
+                # allowance: the reference's own distance from the truth (x3 for the scatter of rounding), and never
+                # tighter than one rounding error amplified by the conditioning of A
+                assert relerr(dev, tru) <= max(1e-10, 3 * floor, EPS * condA), (name, f, relerr(dev, tru), floor)
             seen += 1
             e.close()
     assert seen >= 10

@@ -1,0 +1,61 @@
+// micro-benchmarks of the tile engine (cycles, per-phase trace of CTA 0)
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -DGPF_TRACE -I../gpfanova_b200/csrc -o engine_micro engine_micro.cu
+#include <cstdio>
+#include <vector>
+#include "gpf_tile.cuh"
+using namespace gpf;
+
+extern __shared__ __align__(16) double smem[];
+
+template <int AUG, bool KEEPL>
+__global__ void __launch_bounds__(NTHR, 2) k_engine(int n, int NT, int NE, int reps, double* ws, size_t stride, const double* F,
+                                                    long long* cyc, double* out) {
+  EngineSmem sm(smem, NT, NE);
+  double* tab = smem + engine_smem_doubles(NT, NE);
+  double* W = ws + (size_t)blockIdx.x * stride;
+  for (int k = threadIdx.x; k < n; k += NTHR) tab[k] = exp(-0.5 * (k * 2.0 / 255) * (k * 2.0 / 255) / 0.25);
+  for (int t = threadIdx.x; t < NT * TB; t += NTHR) sm.dvec[t] = (t < n) ? 1e-6 : 0.0;
+  __syncthreads();
+  long long t0 = clock64();
+  bool ok = true;
+  for (int r = 0; r < reps; ++r) {
+    EngineIO io{W, W + (size_t)plt_tiles(NT) * TILE, RowSrc{F, nullptr, n, 4, n}, nullptr, 0};
+    ok = chol_engine<AUG, KEEPL>(SrcToeplitz{tab, n}, io, NT, NE, 1, sm) && ok;
+  }
+  long long t1 = clock64();
+  if (threadIdx.x == 0) { cyc[blockIdx.x] = (t1 - t0) / reps; out[blockIdx.x] = sm.scal[0] + (ok ? 0 : 1e9); }
+}
+
+template <int AUG, bool KEEPL>
+void run(const char* name, int ctas, int NE) {
+  const int n = 256, NT = 8, reps = 10;
+  size_t stride = (size_t)(plt_tiles(NT) + NE * NT) * TILE;
+  double *ws, *F, *out; long long* cyc;
+  cudaMalloc(&ws, ctas * stride * 8); cudaMalloc(&F, 4 * n * 8); cudaMalloc(&out, ctas * 8); cudaMalloc(&cyc, ctas * 8);
+  std::vector<double> hF(4 * n, 0.5);
+  cudaMemcpy(F, hF.data(), 4 * n * 8, cudaMemcpyHostToDevice);
+  size_t smemb = (engine_smem_doubles(NT, NE) + n) * 8;
+  cudaFuncSetAttribute(k_engine<AUG, KEEPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemb);
+  long long z[64] = {0};
+  cudaMemcpyToSymbol(gpf_trace, z, sizeof z);
+  k_engine<AUG, KEEPL><<<ctas, NTHR, smemb>>>(n, NT, NE, reps, ws, stride, F, cyc, out);
+  std::vector<long long> hc(ctas); std::vector<double> ho(ctas);
+  cudaMemcpy(hc.data(), cyc, ctas * 8, cudaMemcpyDeviceToHost); cudaMemcpy(ho.data(), out, ctas * 8, cudaMemcpyDeviceToHost);
+  long long tr[64]; cudaMemcpyFromSymbol(tr, gpf_trace, sizeof tr);
+  printf("%-22s ctas %3d: %7lld cycles/factorisation (logdet %.6f) %s\n", name, ctas, hc[0], ho[0], cudaGetErrorString(cudaGetLastError()));
+  const char* nm[6] = {"prologue", "wait-top", "phase2", "wait-p2", "lookahead", "phase3"};
+  for (int w = 0; w < 8; w += 1) {
+    printf("   warp %d:", w);
+    for (int s = 0; s < 6; ++s) printf(" %s %6lld", nm[s], tr[w * 8 + s] / reps);
+    printf("\n");
+  }
+  cudaFree(ws); cudaFree(F); cudaFree(out); cudaFree(cyc);
+}
+
+int main() {
+  run<AUG_RHS, false>("chol+rhs (prior)", 148, 1);
+  run<AUG_RHS, false>("chol+rhs (prior)", 296, 1);
+  run<AUG_RHS, true>("chol+rhs keepL (fn)", 296, 1);
+  run<AUG_IDENT, false>("inverse (kinv)", 296, 0);
+  return 0;
+}
