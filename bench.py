@@ -167,17 +167,18 @@ def fp64_peak():
         return 37.0, "fallback 37 TFLOP/s (B200 FP64 datasheet order; profiles/fp64_peak_r01.json missing)"
 
 
-def flops_model(n, f, P, ng_list, counts, chains, sweeps):
-    """algorithmic FP64 flops: chol n^3/3, K_inv n^3 (chol + triangular inverse + L^-T L^-1),
-    function draw n^3/3 + 6 n^2, slice factorisation n^3/3 + |g| n^2"""
+def flops_model(n, f, P, ng_list, counts, schur):
+    """algorithmic FP64 flops of what was executed (counted by the kernels), SURVEY.md 8d / DESIGN.md 5:
+    K_inv n^3 (chol + triangular inverse + L^-T L^-1); function draw n^3/3 + 6 n^2 (chol, forward + 2 back solves);
+    slice factorisation: dense n^3/3 + |g| n^2, or -- uniform grid, Schur algorithm -- (3 + |g|) n^2."""
     n3 = float(n) ** 3
     inv = counts["inverses"] * n3
     draws = counts["draws"] * (n3 / 3 + 6.0 * n * n)
     prior_facts = counts["chol"] - counts["inverses"] - counts["draws"] - counts["jitter"]
     gbar = float(np.mean(ng_list))
-    prior = prior_facts * (n3 / 3 + gbar * n * n)
-    return {"kinv": inv, "function": draws, "prior_slice": prior, "prior_factorisations": prior_facts,
-            "total": inv + draws + prior}
+    per = (3.0 + gbar) * n * n if schur else (n3 / 3 + gbar * n * n)
+    return {"kinv": inv, "function": draws, "prior_slice": prior_facts * per, "prior_factorisations": prior_facts,
+            "total": inv + draws + prior_facts * per}
 
 
 def main():
@@ -273,20 +274,25 @@ def main():
     dev_ms_max = float(el.item())
     value = total_chains * f * args.steps / (dev_ms_max * 1e-3)
 
-    # ---------------- roofline of the dominant kernel (k_prior: slice-sampler GP log-likelihood) ----------------
+    # ---------------- roofline of the dominant kernel (largest share of the step) ----------------
     peak, peak_src = fp64_peak()
-    fm = flops_model(n, f, P, [len(g) for g in groups], counts, C, args.steps)
-    n_prior_launches = 2 * P * args.steps
-    prior_tf = fm["prior_slice"] / (prof["prior_slice"] * 1e-3) / 1e12 if prof["prior_slice"] > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "k_prior (sigma + lengthscale slice steps)", "achieved": prior_tf, "peak": peak,
-                "unit": "TFLOP/s", "frac": prior_tf / peak, "traffic": None, "peak_source": peak_src,
-                "flops_per_launch": fm["prior_slice"] / n_prior_launches,
-                "ms_per_launch": prof["prior_slice"] / n_prior_launches,
-                "share_of_step": prof["prior_slice"] / dev_ms if dev_ms else None,
-                "whole_step": {"achieved": fm["total"] / (dev_ms * 1e-3) / 1e12, "frac": fm["total"] / (dev_ms * 1e-3) / 1e12 / peak,
-                               "ms": {k: prof[k] / args.steps for k in prof},
-                               "tflops": {k: (fm[k] / (prof[k] * 1e-3) / 1e12 if prof[k] > 0 else None)
-                                          for k in ("kinv", "function", "prior_slice")}},
+    schur = bool(np.allclose(np.diff(x[:, 0]), np.diff(x[:, 0])[0], rtol=0, atol=1e-13)) and x.shape[1] == 1
+    fm = flops_model(n, f, P, [len(g) for g in groups], counts, schur)
+    kern = {"kinv": ("k_group_kinv (Kernel.K_inv per prior group: RBF build + jitchol + in-place inverse)", P * args.steps),
+            "function": ("k_function (Function._sample: residual projection, jitchol(A), solves, Philox draw)", f * args.steps),
+            "prior_slice": ("k_prior_schur (sigma+lengthscale slice steps: Toeplitz/Schur GP log-likelihood)" if schur else
+                            "k_prior (sigma+lengthscale slice steps: dense GP log-likelihood)", P * args.steps)}
+    dom = max(("kinv", "function", "prior_slice"), key=lambda k: prof[k])
+    tf = {k: (fm[k] / (prof[k] * 1e-3) / 1e12 if prof[k] > 0 else 0.0) for k in kern}
+    roofline = {"bound": "tensor", "kernel": kern[dom][0], "achieved": tf[dom], "peak": peak, "unit": "TFLOP/s",
+                "frac": tf[dom] / peak, "traffic": None, "peak_source": peak_src,
+                "flops_per_launch": fm[dom] / kern[dom][1], "ms_per_launch": prof[dom] / kern[dom][1],
+                "share_of_step": prof[dom] / dev_ms if dev_ms else None,
+                "per_kernel": {k: {"ms_per_step": prof[k] / args.steps, "tflops": tf[k], "frac": tf[k] / peak,
+                                   "launches_per_step": kern[k][1] / args.steps} for k in kern},
+                "whole_step": {"achieved": fm["total"] / (dev_ms * 1e-3) / 1e12,
+                               "frac": fm["total"] / (dev_ms * 1e-3) / 1e12 / peak,
+                               "note": "algorithmic flops of the executed algorithm (Schur slices are O(n^2))"},
                 "counted": {"factorisations_per_sweep_per_chain": counts["chol"] / (C * args.steps),
                             "logp_evals_per_slice_step": counts["logp"] / max(1, counts["slice_steps"]),
                             "jitter_retries": counts["jitter"]}}
