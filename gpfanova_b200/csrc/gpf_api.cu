@@ -157,11 +157,19 @@ int launch_prior(gpf_ctx* c, int g, int mode, const double* cand, double* outv, 
   PriorArgs a{g, mode, cand, outv, c->slice_w[1 + 2 * g], c->slice_w[2 + 2 * g], c->slice_m[1 + 2 * g], c->slice_m[2 + 2 * g],
               sampler_id, sweep, u, nu, nev};
   CK(c, cudaMemsetAsync(c->dev.sched, 0, sizeof(int), c->stream));
-  if (c->toeplitz && c->use_schur && c->schur_warps[g] > 0) {
-    const int wpc = c->schur_warps[g], ng = (int)c->groups[g].size();
-    const size_t smem = (size_t)wpc * schur_warp_doubles(c->dev.n, ng) * sizeof(double);
-    const int grid = std::min((c->dev.C + wpc - 1) / wpc, 2 * c->sms);
-    k_prior_schur<<<grid, wpc * 32, smem, c->stream>>>(c->dev, a);
+  if (c->toeplitz && c->use_schur && (c->schur_warps[g] > 0 || (c->dev.n <= 256 && c->groups[g].size() <= 4))) {
+    const int ng = (int)c->groups[g].size();
+    if (c->dev.n <= 256 && ng <= 4) {       // vectors in registers
+      const int grid = std::min((c->dev.C + 3) / 4, 3 * c->sms);   // 4 warps per CTA, 3 CTAs per SM (168 registers)
+      if (ng == 1) k_prior_schur<1><<<grid, 128, 0, c->stream>>>(c->dev, a);
+      else if (ng == 2) k_prior_schur<2><<<grid, 128, 0, c->stream>>>(c->dev, a);
+      else k_prior_schur<4><<<grid, 128, 0, c->stream>>>(c->dev, a);
+    } else {
+      const int wpc = c->schur_warps[g];
+      const size_t smem = (size_t)wpc * schur_warp_doubles(c->dev.n, ng) * sizeof(double);
+      const int grid = std::min((c->dev.C + wpc - 1) / wpc, 2 * c->sms);
+      k_prior_schur<0><<<grid, wpc * 32, smem, c->stream>>>(c->dev, a);
+    }
   } else if (c->toeplitz) k_prior<true><<<c->grid, NTHR, c->smem_prior[g], c->stream>>>(c->dev, a);
   else k_prior<false><<<c->grid, NTHR, c->smem_prior[g], c->stream>>>(c->dev, a);
   ++c->launches;
@@ -331,7 +339,7 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
     if (e == cudaSuccess) e = allow_smem(k_function, c->smem_fn);
     if (e == cudaSuccess) e = allow_smem(k_prior<true>, sp);
     if (e == cudaSuccess) e = allow_smem(k_prior<false>, sp);
-    if (e == cudaSuccess) e = allow_smem(k_prior_schur, 112 * 1024);
+    if (e == cudaSuccess) e = allow_smem(k_prior_schur<0>, 112 * 1024);
     if (e != cudaSuccess) { c->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return fail(GPF_ERR_CUDA); }
   }
   c->grid = std::min(v.C, 2 * c->sms);

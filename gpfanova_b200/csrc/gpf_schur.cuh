@@ -92,6 +92,93 @@ __device__ __forceinline__ SchurOut schur_eval(const CtxDev& c, int n, int ng, c
   return out;
 }
 
+// Register-resident version for n <= 256 and at most NG functions per group: lane l owns positions 8l .. 8l+7 of every
+// vector (column of L, v, right-hand sides).  v and the right-hand sides never move; the column shifts down by one
+// position per step, which with the step loop unrolled by 8 is a compile-time renaming of the lane's registers plus ONE
+// shuffle (the value crossing the lane boundary).  The shared-memory version above moves 32 bytes per multiply-add
+// through the LSU and is bound by it (measured 53k cycles per evaluation per SM); this one is bound by the FP64 pipe.
+// Positions above the diagonal of the current column hold dead values that are never read by live ones.
+// log det = -2 sum_k log(1/L[k][k]) is accumulated as a product with the exponent split off every 8 steps.
+template <int NG>
+__device__ __forceinline__ SchurOut schur_eval_reg(const CtxDev& c, int n, int ng, const int* __restrict__ fns,
+                                                   const double* __restrict__ Fc, double sigma, double ls, int lane) {
+  double col[8], v[8], r[NG][8];
+  const double sc = -0.5 / (ls * ls);
+  double part = 0.0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int i = lane * 8 + q;
+    const double t = (i < n) ? sigma * exp(c.d2[i] * sc) : 0.0;
+    col[q] = t;
+    if (i < n) part += (i == 0 ? (double)n : 2.0 * (double)(n - i)) * t;
+  }
+  part = warp_sum(part);
+  const double jit = part / ((double)n * (double)n) * c.prior_jitter;   // base.py:222
+  const double t0 = __shfl_sync(FULLMASK, col[0], 0) + jit;
+  SchurOut out{0.0, 0.0, true};
+  if (!(t0 > 0.0) || !(t0 < 1.0e300)) { out.ok = false; return out; }
+  double uinv = rsqrt_nr(t0);                 // 1 / L[0][0]
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int i = lane * 8 + q;
+    const double u = ((i == 0) ? t0 : col[q]) * uinv;
+    col[q] = u;
+    v[q] = (i == 0) ? 0.0 : u;
+  }
+#pragma unroll
+  for (int qq = 0; qq < NG; ++qq)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int i = lane * 8 + q;
+      r[qq][q] = (qq < ng && i < n) ? Fc[(size_t)fns[qq] * n + i] : 0.0;
+    }
+  double prod = 1.0, quad = 0.0;
+  int e2 = 0;
+  bool ok = true;
+  const int nblk = (n + 7) >> 3;
+  for (int K = 0; K < nblk; ++K) {
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      const int k = 8 * K + s;
+      // ---- forward substitution with column k (logical position q of this lane is col[(q - s) & 7]) ----
+#pragma unroll
+      for (int qq = 0; qq < NG; ++qq) {
+        // (positions >= n pick up shifted-out column entries: they are dead, and steps k >= n contribute nothing)
+        const double w = (k < n) ? __shfl_sync(FULLMASK, r[qq][s], K) * uinv : 0.0;
+        quad = fma(w, w, quad);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) r[qq][q] = fma(-col[(q - s) & 7], w, r[qq][q]);
+      }
+      if (k < n) prod *= uinv;
+      // ---- hyperbolic rotation that produces column k+1 ----
+      double vk1 = (s < 7) ? __shfl_sync(FULLMASK, v[(s + 1) & 7], K) : __shfl_sync(FULLMASK, v[0], (K + 1) & 31);
+      const double rho = (k + 1 < n) ? vk1 * uinv : 0.0;
+      const double e = fma(-rho, rho, 1.0);
+      if (!(e > 0.0)) ok = false;
+      const double cinv = rsqrt_nr(e);
+      const double cc = e * cinv;
+      uinv *= cinv;                             // L[k+1][k+1] = L[k][k] c
+      // shift the column down by one position: only the register holding logical position 7 crosses lanes
+      col[(7 - s) & 7] = __shfl_up_sync(FULLMASK, col[(7 - s) & 7], 1);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int pc = (q - s - 1) & 7;
+        const double un = (col[pc] - rho * v[q]) * cinv;
+        v[q] = fma(cc, v[q], -rho * un);
+        col[pc] = un;
+      }
+    }
+    int ex;
+    prod = frexp(prod, &ex);
+    e2 += ex;
+    if (!ok) break;
+  }
+  if (!ok) { out.ok = false; return out; }
+  out.logdet = -2.0 * (log(prod) + (double)e2 * 0.6931471805599453);
+  out.quad = quad;
+  return out;
+}
+
 // warp-level chain hand-out
 __device__ __forceinline__ int next_chain_warp(int* sched, int lane) {
   int t = 0;
@@ -100,7 +187,8 @@ __device__ __forceinline__ int next_chain_warp(int* sched, int lane) {
 }
 
 // same modes as k_prior (PriorArgs): 0/1 evaluate sigma / lengthscale candidate, 2/3 slice step, 4 fused sigma + ls
-__global__ void __launch_bounds__(NTHR) k_prior_schur(CtxDev c, PriorArgs a) {
+template <int NG>   // NG > 0: register-resident evaluation (n <= 256, group size <= NG); 0: shared-memory evaluation
+__global__ void __launch_bounds__(NG > 0 ? 128 : NTHR, NG > 0 ? 3 : 2) k_prior_schur(CtxDev c, PriorArgs a) {
   extern __shared__ __align__(16) double gpf_smem_schur[];
   const int n = c.n, g = a.g, mode = a.mode;
   const int ng = c.group_off[g + 1] - c.group_off[g];
@@ -134,7 +222,8 @@ __global__ void __launch_bounds__(NTHR) k_prior_schur(CtxDev c, PriorArgs a) {
       const bool inb = basef || (l_eval >= lb && l_eval <= ub);   // base.py:224-231: outside the prior -> -inf
       SchurOut o{0.0, 0.0, true};
       if (inb) {
-        o = schur_eval(c, n, ng, fns, Fc, exp10(s_fact), exp10(l_eval), us, v, ev, r, lane);
+        if constexpr (NG > 0) o = schur_eval_reg<NG>(c, n, ng, fns, Fc, exp10(s_fact), exp10(l_eval), lane);
+        else o = schur_eval(c, n, ng, fns, Fc, exp10(s_fact), exp10(l_eval), us, v, ev, r, lane);
         ++nfact;
         if (!o.ok) failed = 1;
       }

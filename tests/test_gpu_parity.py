@@ -442,3 +442,57 @@ def test_full_size_sweep_statistics(eng):
     fit = Fm.T @ d.X.T
     assert np.sqrt(np.mean((fit - F @ d.X.T) ** 2)) < 0.05
     e.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# every slice log-likelihood path: Schur in registers (n <= 256, |g| <= 4), Schur in shared memory (larger groups),
+# dense engine with the lag-table source (option 0 = 0) and dense engine with element-wise RBF (non-uniform inputs)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", ["schur_reg", "schur_smem", "dense_toeplitz", "dense_general"])
+def test_prior_loglik_paths(eng, path):
+    rng = np.random.default_rng(11)
+    n = 72
+    levels = 7 if path == "schur_smem" else 4         # group of 6 functions does not fit the register version
+    x = np.linspace(-1, 1, n)[:, None]
+    if path == "dense_general":
+        x = np.sort(rng.uniform(-1, 1, size=(n, 1)), axis=0)
+    effect = np.array(list(range(levels)) * 2)[:, None]
+    d = orc.Design(effect)
+    groups = d.prior_groups()
+    F = np.zeros((n, d.f))
+    L = np.linalg.cholesky(orc.rbf_K(x, 1.0, 0.5) + 1e-8 * np.eye(n))
+    for i in range(d.f):
+        F[:, i] = L @ rng.standard_normal(n)
+    y = F @ d.X.T + rng.normal(0, 0.1, size=(n, d.m))
+    C = 8
+    e = eng.ChainEngine(x, y, d.X, groups, chains=C, seed=5)
+    if path == "dense_toeplitz":
+        e.set_option(0, 0)
+    hyper = np.concatenate([np.full((C, 1), -2.0), rng.uniform(-0.8, 0.8, size=(C, e.H - 1))], axis=1)
+    e.set_state(F=F.T, hyper=hyper)
+    cand = rng.uniform(-1.2, 1.2, size=C)
+    cand[0] = 2.5                                      # outside the prior
+    for g in range(len(groups)):
+        for which in ("sigma", "lengthscale"):
+            got = e.prior_loglik(g, which, cand)
+            for ch in range(C):
+                o = orc.prior_loglik(x, F[:, groups[g]].T, hyper[ch, 1 + 2 * g], hyper[ch, 2 + 2 * g], cand[ch], which)
+                if np.isinf(o):
+                    assert got[ch] == o
+                else:
+                    assert abs(got[ch] - o) <= 5e-9 * max(1.0, abs(o)), (path, g, which, ch, got[ch], o)
+    # and a few sweeps through this path follow the oracle
+    S = 2
+    hist = torch.zeros((S, C, e.H + e.f * n), dtype=torch.float64, device="cuda")
+    e.sweep(S, history=hist)
+    e.sync()
+    e.status()
+    hist = hist.cpu().numpy()
+    st = orc.Stream(5)
+    for ch in range(2):
+        m = orc.Model(x, y, d.X, groups)
+        m.F, m.hyper = F.copy(), hyper[ch].copy()
+        for s in range(S):
+            m.sweep(st, ch, s)
+            assert np.allclose(hist[s, ch, :e.H], m.hyper, rtol=0, atol=1e-6), (path, ch, s)
+    e.close()
