@@ -337,6 +337,55 @@ __device__ __forceinline__ void trsm_dmma(double* S, const double* __restrict__ 
   }
 }
 
+// X <- X L^-T for one 32-row block in a panel slot, in place: blocked substitution whose off-diagonal block updates
+// run on the tensor pipe (DMMA.8x8x4) while each 8x8 diagonal block is solved by plain substitution, one row per lane
+// (no explicit inverses: same accuracy as trsm_slot, a third of its shared-memory operand traffic, 144 instead of 496
+// dependent multiply-adds per lane).  DT: L column-major, rinv[c] = 1/L[c][c].
+__device__ __forceinline__ void trsm_hybrid(double* S, const double* __restrict__ DT, const double* __restrict__ rinv, int lane) {
+  const int g = lane >> 2, tig = lane & 3;
+#pragma unroll
+  for (int J = 0; J < 4; ++J) {
+    if (J > 0) {
+      double c[4][2];
+#pragma unroll
+      for (int ti = 0; ti < 4; ++ti) {
+        const double2 v = *reinterpret_cast<const double2*>(S + (8 * ti + g) * PS + 8 * J + 2 * tig);
+        c[ti][0] = v.x; c[ti][1] = v.y;
+      }
+#pragma unroll
+      for (int I = 0; I < J; ++I)
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          const double b = DT[(8 * I + 4 * kk + tig) * TB + 8 * J + g];          // L[8J+g][8I+4kk+tig]
+#pragma unroll
+          for (int ti = 0; ti < 4; ++ti) dmma884(c[ti][0], c[ti][1], -S[(8 * ti + g) * PS + 8 * I + 4 * kk + tig], b);
+        }
+#pragma unroll
+      for (int ti = 0; ti < 4; ++ti)
+        *reinterpret_cast<double2*>(S + (8 * ti + g) * PS + 8 * J + 2 * tig) = make_double2(c[ti][0], c[ti][1]);
+      __syncwarp();
+    }
+    // diagonal block: row `lane`, 8 columns, substitution against L_JJ
+    double x[8];
+    double* row = S + lane * PS + 8 * J;
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      const double2 v = *reinterpret_cast<const double2*>(row + j);
+      x[j] = v.x; x[j + 1] = v.y;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      x[j] *= rinv[8 * J + j];
+      const double* Lc = DT + (8 * J + j) * TB + 8 * J;      // column 8J+j of L, rows 8J..8J+7
+#pragma unroll
+      for (int j2 = j + 1; j2 < 8; ++j2) x[j2] = fma(-x[j], Lc[j2], x[j2]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2*>(row + j) = make_double2(x[j], x[j + 1]);
+    __syncwarp();
+  }
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
@@ -526,12 +575,12 @@ __device__ __forceinline__ bool chol_engine(const Src& src, const EngineIO& io, 
       __syncwarp();
       double* slotp = sm.P + (size_t)slot * TB * PS;
 #ifndef GPF_DBG_NOTRSM
-      // Plain substitution wherever the factor itself is a result (K_inv: cond ~ 1e11; L_A of the function step, held
-      // to 1e-10): the explicit 8x8 block inverses of the tensor version cost digits there (measured: K_inv residual
-      // 0.9 instead of 1e-2; conditional mean 2.3e-10 instead of 7e-11 from the truth).  The dense slice likelihood
-      // (general inputs) only needs log-det and quadratic forms and takes the tensor version.
+      // Substitution-accurate solves wherever the factor itself is a result (K_inv: cond ~ 1e11; L_A of the function
+      // step, held to 1e-10): the explicit 8x8 block inverses of the all-tensor version cost digits there (measured:
+      // K_inv residual 0.9 instead of 1e-2; conditional mean 2.3e-10 instead of 7e-11 from the truth).  The dense
+      // slice likelihood (general inputs) only needs log-det and quadratic forms and takes the all-tensor version.
       if (FAST_TRSM) trsm_dmma(slotp, sm.DT, sm.Linv, g, tig);
-      else trsm_slot(slotp, sm.DT, sm.rinv + k * TB, false);
+      else trsm_hybrid(slotp, sm.DT, sm.rinv + k * TB, lane);
 #endif
       if (t < nreg) {
         if (KEEPL) {
