@@ -317,8 +317,9 @@ def main():
         e2e_s = float(el.item())
         cols = model.H + f * n
         e2e = {"value": total_chains * f * ksteps / e2e_s, "unit": UNIT,
-               "h2d_bytes_per_step": int((y.nbytes + x.nbytes + C * cols * 8) / ksteps),
+               "h2d_bytes_per_step": int((y.nbytes + x.nbytes + model.design_matrix.nbytes + C * cols * 8) / ksteps),
                "d2h_bytes_per_step": int(C * cols * 8 + C * cols * 8 / ksteps),
+               "kernel_ms_per_step": dev_ms_max / args.steps,
                "seconds": e2e_s, "api": "FANOVA(...).sample(%d, thin=1): construction of the device context, upload of y / x / "
                                         "design / chain states, %d sweeps, every sweep's state of every chain read back to host "
                                         "and chain 0 appended to parameter_history" % (ksteps, ksteps)}

@@ -39,6 +39,7 @@ SIGNATURES = {
     "gpf_sync": (C.c_int, [C.c_void_p]),
     "gpf_set_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "gpf_get_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gpf_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "gpf_device_F": (C.c_void_p, [C.c_void_p]),
     "gpf_device_hyper": (C.c_void_p, [C.c_void_p]),
     "gpf_invalidate": (C.c_int, [C.c_void_p]),

@@ -103,6 +103,10 @@ class Base(SamplerContainer):
         self._F[:] = self.parameter_cache[self._flabels].values.astype(float).reshape(self.f, self.n)[None]
         self._hyper[:] = self.parameter_cache[self._hyper_names].values.astype(float)[None]
         self._transform_labels = [lab for s in self.samplers[self._n_core_samplers:] for lab in s.parameters]
+        pos = {lab: i for i, lab in enumerate(self.parameter_cache.index)}
+        self._pos_h = np.array([pos[l] for l in self._hyper_names], dtype=np.int64)
+        self._pos_F = np.array([pos[l] for l in self._flabels], dtype=np.int64)
+        self._pos_T = np.array([pos[l] for l in self._transform_labels], dtype=np.int64)
 
     # ------------------------------------------------------------------ reference protocol (base.py:88-149)
     def _additionalSamplers(self):
@@ -200,8 +204,9 @@ class Base(SamplerContainer):
         """parameter_cache (chain 0) -> host mirror -> device.  Entries of parameter_cache the caller changed since
         the last sync are applied to every chain."""
         eng = self.engine()
-        ch = self.parameter_cache[self._hyper_names].values.astype(float)
-        cF = self.parameter_cache[self._flabels].values.astype(float).reshape(self.f, self.n)
+        vals = self.parameter_cache.to_numpy(dtype=float)
+        ch = vals[self._pos_h]
+        cF = vals[self._pos_F].reshape(self.f, self.n)
         dh = ch != self._hyper[0]
         if dh.any():
             self._hyper[:, dh] = ch[dh][None]
@@ -214,23 +219,27 @@ class Base(SamplerContainer):
     def _pull_state(self):
         eng = self.engine()
         self._F, self._hyper = eng.get_state()
-        self.parameter_cache[self._hyper_names] = self._hyper[0]
-        self.parameter_cache[self._flabels] = self._F[0].ravel()
-        if self._transform_labels:
-            self.parameter_cache[self._transform_labels] = self._transform_block(self._F[0][None])[0]
+        vals = self.parameter_cache.to_numpy(dtype=float, copy=True)
+        vals[self._pos_h] = self._hyper[0]
+        vals[self._pos_F] = self._F[0].ravel()
+        if len(self._pos_T):
+            vals[self._pos_T] = self._transform_block(self._F[0][None])[0]
+        self.parameter_cache.iloc[:] = vals
 
     def set_chain_state(self, hyper=None, F=None):
         """per-chain state: hyper (chains, H) in the order of self.hyperNames(); F (chains, f, n)"""
+        vals = self.parameter_cache.to_numpy(dtype=float, copy=True)
         if hyper is not None:
             self._hyper = np.array(np.broadcast_to(np.asarray(hyper, dtype=float), (self.chains, self.H)))
-            self.parameter_cache[self._hyper_names] = self._hyper[0]
+            vals[self._pos_h] = self._hyper[0]
         if F is not None:
             self._F = np.array(np.broadcast_to(np.asarray(F, dtype=float), (self.chains, self.f, self.n)))
-            self.parameter_cache[self._flabels] = self._F[0].ravel()
+            vals[self._pos_F] = self._F[0].ravel()
+        self.parameter_cache.iloc[:] = vals
 
     def chain_state(self):
         """(hyper (chains, H), F (chains, f, n)) of every chain after the last sample() call"""
-        return self._hyper.copy(), self._F.copy()
+        return np.array(self._hyper), np.array(self._F)
 
     def hyperNames(self):
         return list(self._hyper_names)
@@ -272,11 +281,13 @@ class Base(SamplerContainer):
         self._check_prior_bounds(eng, prior_lb, prior_ub)
         if lengthscale is not None and sigma is not None:
             # both given: evaluate with sigma installed as the current value (the prior term is on the lengthscale)
-            hyper = self._hyper.copy()
+            orig = np.array(self._hyper)          # (self._hyper may alias the engine's staging buffer)
+            hyper = orig.copy()
             hyper[:, 1 + 2 * p] = sigma
             eng.set_state(hyper=hyper)
             val = eng.prior_loglik(p, "lengthscale", float(lengthscale))[0]
-            eng.set_state(hyper=self._hyper)
+            eng.set_state(hyper=orig)
+            self._hyper = orig
         elif lengthscale is not None:
             val = eng.prior_loglik(p, "lengthscale", float(lengthscale))[0]
         else:
@@ -325,37 +336,23 @@ class Base(SamplerContainer):
         logger = logging.getLogger(__name__)
         eng = self._push_state()
         start_time = time.time()
-        cols = self.H + self.f * self.n
         step = 1 if thin == 0 else int(thin)
-        rows_total = n // step
-        max_rows = max(1, int(2 ** 31 // (self.chains * cols * 8)))       # <= 2 GiB of device history per chunk
-        chunk_sweeps = max_rows * step if rows_total else n
-        blocks = []
-        done = 0
+        order = self._core_order(n) if random else None
         err = None
-        while done < n:
-            k = min(chunk_sweeps, n - done)
-            rows = k // step
-            hist = torch.empty((max(rows, 1), self.chains, cols), dtype=torch.float64, device=eng.dev)
-            order = self._core_order(k) if random else None
-            got = eng.sweep(k, thin=step, history=hist if rows else None, order=order)
-            eng.sync()
-            try:
-                eng.status()
-            except np.linalg.LinAlgError as e:    # keep what was sampled, then propagate like the reference
-                err = e
-            if got:
-                blocks.append(hist[:got].cpu().numpy())
-            done += k
-            if verbose:
-                j = sum(b.shape[0] for b in blocks)
+        progress = None
+        if verbose:
+            def progress(done):
                 logger.info("%d/%d iterations (%.2lf%s) finished in %.2lf minutes" % (
                     done, n, 100. * done / n, '%', (time.time() - start_time) / 60))
-            if err is not None:
-                break
+        blocks = eng.sweep_host(n, thin=step, order=order, on_chunk=progress,
+                                max_chunk_sweeps=max(step, n // 10) if verbose else None)
+        try:
+            eng.status()
+        except np.linalg.LinAlgError as e:        # keep what was sampled, then propagate like the reference
+            err = e
         self._pull_state()
-        if blocks:
-            self._store_blocks(np.concatenate(blocks, axis=0))
+        for blk in blocks:
+            self._store_blocks(blk)
         if verbose:
             logger.info("%d samples finished in %.2lf minutes" % (n, (time.time() - start_time) / 60))
         if err is not None:
@@ -377,16 +374,12 @@ class Base(SamplerContainer):
         S = raw.shape[0]
         hyper = raw[:, :self.H]
         F = raw[:, self.H:].reshape(S, self.f, self.n)
-        cols = list(self.parameter_cache.index)
+        cols = self.parameter_cache.index
         out = np.empty((S, len(cols)))
-        pos = {lab: i for i, lab in enumerate(cols)}
-        for h, nm in enumerate(self._hyper_names):
-            out[:, pos[nm]] = hyper[:, h]
-        fl = np.array([pos[lab] for lab in self._flabels])
-        out[:, fl] = F.reshape(S, self.f * self.n)
-        if self._transform_labels:
-            tl = np.array([pos[lab] for lab in self._transform_labels])
-            out[:, tl] = self._transform_block(F)
+        out[:, self._pos_h] = hyper
+        out[:, self._pos_F] = F.reshape(S, self.f * self.n)
+        if len(self._pos_T):
+            out[:, self._pos_T] = self._transform_block(F)
         return pd.DataFrame(out, columns=cols)
 
     def store(self):

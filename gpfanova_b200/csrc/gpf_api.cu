@@ -460,6 +460,12 @@ int gpf_get_state(gpf_ctx* c, double* h_F, double* h_hyper) {
   return GPF_OK;
 }
 
+int gpf_memcpy_d2h(gpf_ctx* c, void* h_dst, const void* d_src, size_t bytes) {
+  CK(c, cudaSetDevice(c->device));
+  CK(c, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  return GPF_OK;
+}
+
 double* gpf_device_F(gpf_ctx* c) { return c->dev.F; }
 double* gpf_device_hyper(gpf_ctx* c) { return c->dev.hyper; }
 

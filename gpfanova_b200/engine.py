@@ -149,6 +149,7 @@ class ChainEngine(object):
         _capi.check(self._lib.gpf_create(C.byref(h), C.byref(d)))
         self._h = h
         self.sweeps_done = 0
+        self._dev_hist = None
 
     # -- lifetime ------------------------------------------------------------------------------
     def close(self):
@@ -180,24 +181,33 @@ class ChainEngine(object):
         return t
 
     # -- state ---------------------------------------------------------------------------------
+    def _pinned_state(self):
+        if getattr(self, "_F_pin", None) is None:
+            self._F_pin = torch.empty((self.C, self.f, self.n), dtype=torch.float64, pin_memory=True)
+            self._h_pin = torch.empty((self.C, self.H), dtype=torch.float64, pin_memory=True)
+        return self._F_pin.numpy(), self._h_pin.numpy()
+
     def set_state(self, F=None, hyper=None):
-        """F: (C, f, n) or (f, n) broadcast to all chains; hyper: (C, H) or (H,)"""
+        """F: (C, f, n) or (f, n) broadcast to all chains; hyper: (C, H) or (H,).  Staged through pinned memory."""
+        Fpin, hpin = self._pinned_state()
         Fp = hp = None
         if F is not None:
-            F = np.broadcast_to(np.asarray(F, dtype=np.float64), (self.C, self.f, self.n))
-            F = np.ascontiguousarray(F)
-            Fp = F.ctypes.data_as(C.c_void_p)
+            F = np.asarray(F, dtype=np.float64)
+            if not np.shares_memory(F, Fpin):
+                np.copyto(Fpin, np.broadcast_to(F, Fpin.shape))
+            Fp = C.c_void_p(self._F_pin.data_ptr())
         if hyper is not None:
-            hyper = np.broadcast_to(np.asarray(hyper, dtype=np.float64), (self.C, self.H))
-            hyper = np.ascontiguousarray(hyper)
-            hp = hyper.ctypes.data_as(C.c_void_p)
+            hyper = np.asarray(hyper, dtype=np.float64)
+            if not np.shares_memory(hyper, hpin):
+                np.copyto(hpin, np.broadcast_to(hyper, hpin.shape))
+            hp = C.c_void_p(self._h_pin.data_ptr())
         self._ck(self._lib.gpf_set_state(self._h, Fp, hp))
 
     def get_state(self):
-        F = np.empty((self.C, self.f, self.n))
-        hyper = np.empty((self.C, self.H))
-        self._ck(self._lib.gpf_get_state(self._h, F.ctypes.data_as(C.c_void_p), hyper.ctypes.data_as(C.c_void_p)))
-        return F, hyper
+        """(F (C, f, n), hyper (C, H)) as numpy views of the engine's pinned staging buffers (refreshed by every call)"""
+        Fpin, hpin = self._pinned_state()
+        self._ck(self._lib.gpf_get_state(self._h, C.c_void_p(self._F_pin.data_ptr()), C.c_void_p(self._h_pin.data_ptr())))
+        return Fpin, hpin
 
     def status(self, clear=True, raise_on_error=True):
         st = np.zeros(self.C, dtype=np.int32)
@@ -290,6 +300,43 @@ class ChainEngine(object):
     def set_option(self, option, value):
         """option 0: Toeplitz/Schur slice log-likelihood on uniform grids (1, default) or dense tile engine (0)"""
         self._ck(self._lib.gpf_set_option(self._h, int(option), int(value)))
+
+    def sweep_host(self, n_sweeps=1, thin=0, order=None, max_chunk_bytes=1 << 30, max_chunk_sweeps=None, on_chunk=None):
+        """sweep() with the stored states delivered to the host: returns a list of numpy blocks
+        (rows_i, C, H + f*n) backed by PINNED memory (D2H at DMA speed, no pageable staging copy).  The copy of a
+        chunk is queued on the context's stream right behind its sweeps; the next chunk's kernels queue behind it."""
+        step = 1 if thin <= 0 else int(thin)
+        cols = self.H + self.f * self.n
+        rows_total = n_sweeps // step
+        if rows_total == 0:
+            self.sweep(n_sweeps, thin=step, order=order)
+            self.sync()
+            return []
+        max_rows = max(1, int(max_chunk_bytes // (self.C * cols * 8)))
+        if max_chunk_sweeps:
+            max_rows = max(1, min(max_rows, int(max_chunk_sweeps) // step))
+        blocks, done = [], 0
+        order = None if order is None else np.asarray(order, dtype=np.int32).reshape(n_sweeps, len(self.order))
+        while done < n_sweeps:
+            k = min(max_rows * step, n_sweeps - done)
+            rows = k // step
+            if rows == 0:
+                self.sweep(k, thin=step, order=None if order is None else order[done:done + k])
+                done += k
+                continue
+            if self._dev_hist is None or self._dev_hist.shape[0] < rows:
+                self._dev_hist = torch.empty((rows, self.C, cols), dtype=torch.float64, device=self.dev)
+            dev = self._dev_hist[:rows]
+            got = self.sweep(k, thin=step, history=dev, order=None if order is None else order[done:done + k])
+            host = torch.empty((got, self.C, cols), dtype=torch.float64, pin_memory=True)
+            self._ck(self._lib.gpf_memcpy_d2h(self._h, C.c_void_p(host.data_ptr()), _ptr(dev), got * self.C * cols * 8))
+            blocks.append(host)
+            done += k
+            if on_chunk is not None:
+                self.sync()
+                on_chunk(done)
+        self.sync()
+        return [b.numpy() for b in blocks]
 
     def set_profile(self, on=True):
         self._ck(self._lib.gpf_set_profile(self._h, int(on)))

@@ -97,6 +97,9 @@ int gpf_sync(gpf_ctx* ctx);
  * prior0_lengthscale, prior1_sigma, ...] (H = 1+2P per chain);  F: chains x f x n. */
 int gpf_set_state(gpf_ctx* ctx, const double* h_F, const double* h_hyper);
 int gpf_get_state(gpf_ctx* ctx, double* h_F, double* h_hyper);
+/* asynchronous device -> host copy queued on the ctx stream behind the kernels already launched (history rows to
+ * pinned host memory); complete after gpf_sync. */
+int gpf_memcpy_d2h(gpf_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
 double* gpf_device_F(gpf_ctx* ctx);       /* device pointers to the live state (chains x f x n) */
 double* gpf_device_hyper(gpf_ctx* ctx);   /* chains x H */
 int gpf_invalidate(gpf_ctx* ctx);         /* call after writing through gpf_device_hyper(): cached K_inv are stale */
