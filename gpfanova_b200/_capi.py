@@ -66,8 +66,8 @@ def lib():
     """load (building first if needed) libgpfanova_b200.so"""
     global _lib
     if _lib is None:
-        path = _build.LIB
-        if _build.stale():
+        path = os.environ.get("GPFANOVA_B200_LIB") or _build.LIB      # (override: A/B builds of the same ABI)
+        if path == _build.LIB and _build.stale():
             try:
                 path = _build.build()
             except Exception:

@@ -184,6 +184,9 @@ struct SrcRbf {
         f.c[ti][tj][1] = rbf_elem(xs, xsq, n, p, sigma, bi * TB + 8 * ti + g, bj * TB + 8 * tj + 2 * tig + 1);
       }
   }
+  __device__ __forceinline__ void fill_slot(double* slot, int bi, int bj, int lane) const {
+    for (int r = 0; r < 32; ++r) slot[r * PS + lane] = rbf_elem(xs, xsq, n, p, sigma, bi * TB + r, bj * TB + lane);
+  }
 };
 
 // uniform grid: tab[k] = sigma * exp(-d2[k] / (2 l^2)), k < n (one exp per lag instead of one per matrix element).

@@ -70,6 +70,8 @@ struct RowSrc {
   }
 };
 
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
 // ---- C fragment (32x32 tile in DMMA accumulator layout): c[ti][tj][e] = C[8ti+g][8tj+2tig+e] ----
 struct CFrag { double c[4][4][2]; };
 
@@ -120,6 +122,7 @@ __device__ __forceinline__ void cfrag_from_rows(CFrag& f, const RowSrc& s, int r
       }
     }
 }
+
 
 // C (+/-)= Pa * Pb^T, Pa/Pb panel slots in shared memory (32 x PS), 128 DMMA.8x8x4 for a full tile
 template <bool NEG>
@@ -179,7 +182,6 @@ __device__ __forceinline__ double rsqrt_nr(double x) {
 
 // ---- explicit shared-memory accesses (the warp-level routines below are separate functions: their pointer
 // arguments would otherwise be generic) ----
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ double lds1(unsigned a) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
@@ -418,7 +420,7 @@ struct EngineSmem {
   double* dvec;   // NT*32 additive diagonal applied at first touch (jitter, offset, n_t/sigma_y; 0 on padding)
   double* piv;    // 32 pivots of the current diagonal tile
   double* quad;   // NE*NT partial sums of squares of finished augmented rows (deterministic reduction)
-  double* scal;   // [0] logdet, [1] fail flag (as double), [2..9] block_sum scratch, spare
+  double* scal;   // [0] logdet, [1] fail flag (as double), [2..9] block_sum scratch, [10] tile counter
   __device__ EngineSmem(double* base, int NT, int NE) {
     DT = base;
     Linv = DT + TILE;
@@ -432,6 +434,25 @@ struct EngineSmem {
   __device__ double* red() const { return scal + 2; }
 };
 
+// 8 KB tile in global memory (row-major, stride 32) <-> panel slot in shared memory (row stride PS), one warp,
+// fully coalesced: every instruction moves 512 contiguous bytes (a row per lane would touch 32 cache lines per
+// instruction: measured 16.7k cycles per panel tile with 8 warps against 4.6k for one).
+__device__ __forceinline__ void tile_to_slot(const double* __restrict__ tile, double* slot, int lane) {
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const int idx = q * 32 + lane;                       // 16-byte chunk index: row = idx / 16, chunk in row = idx % 16
+    const double2 v = *reinterpret_cast<const double2*>(tile + 2 * idx);
+    *reinterpret_cast<double2*>(slot + (idx >> 4) * PS + 2 * (idx & 15)) = v;
+  }
+}
+__device__ __forceinline__ void slot_to_tile(const double* slot, double* __restrict__ tile, int lane) {
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const int idx = q * 32 + lane;
+    *reinterpret_cast<double2*>(tile + 2 * idx) = *reinterpret_cast<const double2*>(slot + (idx >> 4) * PS + 2 * (idx & 15));
+  }
+}
+
 // ---- first-touch sources of the matrix (step k = 0 reads the matrix from here, later steps from the workspace) ----
 // tiles in memory, packed lower-triangular by tile
 struct SrcTiles {
@@ -441,6 +462,9 @@ struct SrcTiles {
   }
   __device__ __forceinline__ void cfrag(CFrag& f, int bi, int bj, int g, int tig) const {
     cfrag_load(f, A0 + (size_t)plt(bi, bj) * TILE, g, tig, 4);
+  }
+  __device__ __forceinline__ void fill_slot(double* slot, int bi, int bj, int lane) const {
+    tile_to_slot(A0 + (size_t)plt(bi, bj) * TILE, slot, lane);
   }
 };
 // stationary kernel on a uniform grid: K[i][j] = tab[|i-j|] (tab in shared memory, sigma folded in); identity padding
@@ -465,6 +489,10 @@ struct SrcToeplitz {
         f.c[ti][tj][1] = at(bi * TB + 8 * ti + g, bj * TB + 8 * tj + 2 * tig + 1);
       }
   }
+  __device__ __forceinline__ void fill_slot(double* slot, int bi, int bj, int lane) const {
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) slot[r * PS + lane] = at(bi * TB + r, bj * TB + lane);
+  }
 };
 
 struct EngineIO {
@@ -476,10 +504,6 @@ struct EngineIO {
   int ldv;
 };
 
-/* The engine.  All NTHR threads of the CTA call it with identical arguments.
- *   AUG_RHS  : NE extra tile rows; the last extra tile row uses only nti_last 8-row strips.
- * Returns false if a pivot failed (matrix not PD); logdet (= 2 sum log L_ii) is in sm.scal[0] on success,
- * sm.quad[e*NT+k] hold the sums of squares of the finished augmented rows. */
 // factor the diagonal tile staged column-major in sm.DT (warp-level): potrf, log-determinant, optional store of L_kk
 template <bool FAST_TRSM, bool KEEPL>
 __device__ __forceinline__ void diag_factor(int k, int lane, double* W, const EngineSmem& sm) {
@@ -505,6 +529,21 @@ __device__ __forceinline__ void prefetch_tile(const double* tile, int lane) {
   asm volatile("prefetch.global.L1 [%0];" ::"l"(tile + 512 + lane * 16));
 }
 
+// stage an accumulator fragment column-major into the (idle) DT buffer: DT[c*32 + r] = C[r][c]
+__device__ __forceinline__ void cfrag_to_DT(const CFrag& f, double* DT, int g, int tig) {
+#pragma unroll
+  for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+    for (int tj = 0; tj < 4; ++tj) {
+      DT[(8 * tj + 2 * tig) * TB + 8 * ti + g] = f.c[ti][tj][0];
+      DT[(8 * tj + 2 * tig + 1) * TB + 8 * ti + g] = f.c[ti][tj][1];
+    }
+}
+/* The engine.  All NTHR threads of the CTA call it with identical arguments.
+ *   AUG_RHS  : NE extra tile rows; the last extra tile row uses only nti_last 8-row strips.
+ * Returns false if a pivot failed (matrix not PD); logdet (= 2 sum log L_ii) is in sm.scal[0] on success,
+ * sm.quad[e*NT+k] hold the sums of squares of the finished augmented rows.
+ */
 template <int AUG, bool KEEPL, class Src>
 __device__ __forceinline__ bool chol_engine(const Src& src, const EngineIO& io, int NT, int NE, int nti_last,
                                             const EngineSmem& sm) {
@@ -535,42 +574,40 @@ __device__ __forceinline__ bool chol_engine(const Src& src, const EngineIO& io, 
     // ---------------- phase 2: panel solves  X <- X L_kk^-T, in place in the panel slots ----------------
     const int nreg = NT - 1 - k;
     const int nx = (AUG == AUG_RHS) ? NE : ((AUG == AUG_IDENT) ? (k + 1) : 0);
-    if (tid == 0) *tilectr = (nreg > 0) ? 1 : 0;   // trailing tile 0 = next diagonal tile, taken by warp 0 (look-ahead)
+    if (tid == 0) *tilectr = (nreg > 0) ? 1 : 0;   // trailing tile 0 = next diagonal tile (look-ahead)
     for (int t = warp; t < nreg + nx; t += NW) {
+      const int iown = k + 1 + t;
       int slot;
-      bool zero_row = false;
-      {
-        double a[32];
-        if (t < nreg) {
-          const int i = k + 1 + t;
-          slot = i;
-#ifdef GPF_DBG_NOLOAD
-          for (int c = 0; c < 32; ++c) a[c] = 0.001 * c;
-#else
-          if (k == 0) src.rows(a, i, 0, lane);
-          else rows_load(a, W + (size_t)plt(i, k) * TILE, lane);
-#endif
-        } else {
-          const int e = t - nreg;
-          if (AUG == AUG_RHS) {
-            slot = NT + e;
-            if (k == 0) {
+      if (t < nreg) {
+        slot = iown;
+        if (k == 0) src.fill_slot(sm.P + (size_t)slot * TB * PS, iown, 0, lane);
+        else tile_to_slot(W + (size_t)plt(iown, k) * TILE, sm.P + (size_t)slot * TB * PS, lane);
+      } else {
+        const int e = t - nreg;
+        if (AUG == AUG_RHS) {
+          slot = NT + e;
+          double* sp = sm.P + (size_t)slot * TB * PS;
+          if (k == 0) {
+            double* ps = sp + lane * PS;
 #pragma unroll
-              for (int c = 0; c < 32; ++c) a[c] = io.rows.at(e * TB + lane, c);
-            } else rows_load(a, Wx + (size_t)(e * NT + k) * TILE, lane);
-            zero_row = e * TB + lane >= io.rows.nrows;   // unused rows of the last block: keep them exactly zero
+            for (int c = 0; c < 32; ++c) ps[c] = io.rows.at(e * TB + lane, c);
           } else {
-            slot = e;
-            if (e == k) {
+            tile_to_slot(Wx + (size_t)(e * NT + k) * TILE, sp, lane);
+            __syncwarp();
+            if (e * TB + lane >= io.rows.nrows) {   // unused rows of the last block: keep them exactly zero
+              double* ps = sp + lane * PS;
 #pragma unroll
-              for (int c = 0; c < 32; ++c) a[c] = (c == lane) ? 1.0 : 0.0;
-            } else rows_load(a, W + (size_t)plt(k, e) * TILE, lane);
+              for (int c = 0; c < 32; c += 2) *reinterpret_cast<double2*>(ps + c) = make_double2(0.0, 0.0);
+            }
           }
+        } else {
+          slot = e;
+          double* sp = sm.P + (size_t)slot * TB * PS;
+          if (e == k) {
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) sp[r * PS + lane] = (r == lane) ? 1.0 : 0.0;
+          } else tile_to_slot(W + (size_t)plt(k, e) * TILE, sp, lane);
         }
-        double* ps = sm.P + (size_t)slot * TB * PS + lane * PS;
-#pragma unroll
-        for (int c = 0; c < 32; c += 2)
-          *reinterpret_cast<double2*>(ps + c) = zero_row ? make_double2(0.0, 0.0) : make_double2(a[c], a[c + 1]);
       }
       __syncwarp();
       double* slotp = sm.P + (size_t)slot * TB * PS;
@@ -583,12 +620,8 @@ __device__ __forceinline__ bool chol_engine(const Src& src, const EngineIO& io, 
       else trsm_hybrid(slotp, sm.DT, sm.rinv + k * TB, lane);
 #endif
       if (t < nreg) {
-        if (KEEPL) {
-          const double* ps = slotp + lane * PS;
-          double* dst = W + (size_t)plt(k + 1 + t, k) * TILE + lane * TB;
-#pragma unroll
-          for (int c = 0; c < 32; c += 2) *reinterpret_cast<double2*>(dst + c) = *reinterpret_cast<const double2*>(ps + c);
-        }
+        if (KEEPL) slot_to_tile(slotp, W + (size_t)plt(k + 1 + t, k) * TILE, lane);
+
       } else if (AUG == AUG_RHS) {
         const int e = t - nreg;
         const double* ps = slotp + lane * PS;
@@ -612,47 +645,45 @@ __device__ __forceinline__ bool chol_engine(const Src& src, const EngineIO& io, 
     __syncthreads();
     GPF_STAMP(3);
     // ---------------- phase 3: trailing updates (DMMA), with look-ahead on the next diagonal tile ----------------
-    // Warp 0 first updates tile (k+1,k+1) and factors it at once (DT / rinv are idle during this phase), so the
-    // serial 32-column potrf of step k+1 runs under the other warps' tensor work.  The remaining tiles are handed
-    // out dynamically (shared-memory counter), warp 0 joins when it is done.
+    // Warp 0 first updates tile (k+1,k+1) and factors it at once (DT / rinv are idle during this phase), so the serial
+    // 32-column potrf of step k+1 runs under the other warps' tensor work.  The remaining tiles are handed out
+    // dynamically (shared-memory counter); warp 0 joins when it is done.
     const int T1 = nreg * (nreg + 1) / 2;
     const int T2 = nx * nreg;
     const int T3 = (AUG == AUG_IDENT) ? (k + 1) * (k + 2) / 2 : 0;
     if (warp == 0 && nreg > 0) {
-      CFrag f;
       const int i = k + 1;
+      CFrag f;
       if (k == 0) {
         src.cfrag(f, i, i, g, tig);
         cfrag_add_diag(f, sm.dvec + i * TB, g, tig);
       } else cfrag_load(f, W + (size_t)plt(i, i) * TILE, g, tig, 4);
       tile_mma<true>(f, sm.P + (size_t)i * TB * PS, sm.P + (size_t)i * TB * PS, g, tig, 4);
-      // accumulator layout -> column-major staging in the idle DT buffer: DT[c*32 + r] = C[r][c]
-#pragma unroll
-      for (int ti = 0; ti < 4; ++ti)
-#pragma unroll
-        for (int tj = 0; tj < 4; ++tj) {
-          sm.DT[(8 * tj + 2 * tig) * TB + 8 * ti + g] = f.c[ti][tj][0];
-          sm.DT[(8 * tj + 2 * tig + 1) * TB + 8 * ti + g] = f.c[ti][tj][1];
-        }
+      cfrag_to_DT(f, sm.DT, g, tig);
 #ifndef GPF_DBG_NOLOOK
       diag_factor<FAST_TRSM, KEEPL>(i, lane, W, sm);
 #endif
       GPF_STAMP(4);
     }
-    // dynamic hand-out; the ticket for the next tile is drawn before working on the current one so that its
-    // accumulator tile can be prefetched under the tensor work
+    // dynamic hand-out of the tiles; the ticket for the next tile is drawn before working on the current one so
+    // that its accumulator tile can be prefetched under the tensor work
     const int TT = T1 + T2 + T3;
     auto ticket = [&]() {
       int t = 0;
       if (lane == 0) t = atomicAdd(tilectr, 1);
       return __shfl_sync(FULLMASK, t, 0);
     };
+    auto t1_decode = [&](int t, int& i, int& j) {
+      int ii = 0, tt = t;
+      while (tt > ii) { tt -= ii + 1; ++ii; }
+      i = k + 1 + ii; j = k + 1 + tt;
+    };
     auto tile_ptr = [&](int t) -> const double* {   // accumulator tile of ticket t in the workspace (nullptr: no load)
       if (t >= TT || k == 0) return nullptr;
       if (t < T1) {
-        int ii = 0, tt = t;
-        while (tt > ii) { tt -= ii + 1; ++ii; }
-        return W + (size_t)plt(k + 1 + ii, k + 1 + tt) * TILE;
+        int i, j;
+        t1_decode(t, i, j);
+        return W + (size_t)plt(i, j) * TILE;
       }
       if (t < T1 + T2) {
         const int u = t - T1;
@@ -673,9 +704,8 @@ __device__ __forceinline__ bool chol_engine(const Src& src, const EngineIO& io, 
 #endif
       CFrag f;
       if (t < T1) {
-        int ii = 0, tt = t;
-        while (tt > ii) { tt -= ii + 1; ++ii; }
-        const int i = k + 1 + ii, j = k + 1 + tt;
+        int i, j;
+        t1_decode(t, i, j);
         if (k == 0) {
           src.cfrag(f, i, j, g, tig);
           if (i == j) cfrag_add_diag(f, sm.dvec + i * TB, g, tig);

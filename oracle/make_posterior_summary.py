@@ -1,0 +1,72 @@
+#!/usr/bin/env python
+"""Mint tests/golden/posterior_oneway_n16.npz: posterior summaries from LONG chains of the UNMODIFIED reference
+(oracle/_ref) on a small one-way FANOVA, for the statistical-parity test of the GPU sampler
+(BASELINE north_star: "posterior summaries over long chains must agree statistically").  TEST INFRASTRUCTURE ONLY.
+
+    python oracle/make_posterior_summary.py [--chains 8] [--sweeps 4000] [--burn 300]     (about 10 minutes on 8 cores)
+"""
+import argparse
+import multiprocessing as mp
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+
+
+def problem():
+    from gpfanova_b200 import synthetic
+    import gpfanova_oracle as orc
+    n = 16
+    x = np.linspace(-1, 1, n)[:, None]
+    eff = synthetic.effects((3,), 3)
+    d = orc.Design(eff)
+    y, F = synthetic.prior_draw(x, d.X, d.prior_groups(), y_sigma=-2.0, seed=321)
+    return x, eff, y, F, d
+
+
+def chain(args):
+    c, sweeps, burn = args
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    import logging
+    logging.disable(logging.CRITICAL)
+    import build_ref
+    gp = build_ref.import_ref()
+    x, eff, y, F, d = problem()
+    np.random.seed(5000 + c)
+    m = gp.fanova.FANOVA(x, y, eff)
+    m.parameter_cache['y_sigma'] = -2.0
+    m.sample(burn, thin=burn)                       # burn-in (one stored row, dropped)
+    m.parameter_history = m.parameter_history.iloc[0:0]
+    m.sample(sweeps, thin=1)
+    H = m.parameter_history
+    names = ['y_sigma', 'prior0_sigma', 'prior0_lengthscale', 'prior1_sigma', 'prior1_lengthscale']
+    hyper = H[names].values.astype(float)
+    Fs = np.stack([H[m.functionIndex(f)].values.astype(float) for f in range(m.f)], axis=1)   # (S, f, n)
+    return hyper.mean(0), hyper.var(0), Fs.mean(0), Fs.var(0), np.median(hyper, axis=0)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--chains", type=int, default=8)
+    ap.add_argument("--sweeps", type=int, default=4000)
+    ap.add_argument("--burn", type=int, default=300)
+    a = ap.parse_args()
+    import build_ref
+    if os.path.isdir("/root/reference/gpfanova"):
+        build_ref.build(quiet=True)
+    with mp.Pool(min(a.chains, os.cpu_count())) as pool:
+        res = pool.map(chain, [(c, a.sweeps, a.burn) for c in range(a.chains)])
+    hm = np.stack([r[0] for r in res]); hv = np.stack([r[1] for r in res])
+    fm = np.stack([r[2] for r in res]); fv = np.stack([r[3] for r in res])
+    hmed = np.stack([r[4] for r in res])
+    x, eff, y, F, d = problem()
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "posterior_oneway_n16.npz"),
+                        x=x, y=y, effect=eff, F_true=F, chains=a.chains, sweeps=a.sweeps, burn=a.burn,
+                        hyper_chain_means=hm, hyper_chain_vars=hv, hyper_chain_medians=hmed,
+                        F_chain_means=fm, F_chain_vars=fv)
+    print("hyper mean", hm.mean(0), "between-chain sd", hm.std(0, ddof=1))
