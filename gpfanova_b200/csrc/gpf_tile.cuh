@@ -38,6 +38,10 @@ __device__ long long gpf_trace[8 * 8];
 #define GPF_STAMP_FLUSH
 #endif
 
+#ifndef GPF_ENGINE_INLINE
+#define GPF_ENGINE_INLINE __forceinline__
+#endif
+
 namespace gpf {
 
 constexpr int TB = 32;            // tile edge
@@ -545,7 +549,7 @@ __device__ __forceinline__ void cfrag_to_DT(const CFrag& f, double* DT, int g, i
  * sm.quad[e*NT+k] hold the sums of squares of the finished augmented rows.
  */
 template <int AUG, bool KEEPL, class Src>
-__device__ __forceinline__ bool chol_engine(const Src& src, const EngineIO& io, int NT, int NE, int nti_last,
+__device__ GPF_ENGINE_INLINE bool chol_engine(const Src& src, const EngineIO& io, int NT, int NE, int nti_last,
                                             const EngineSmem& sm) {
   constexpr bool FAST_TRSM = (AUG == AUG_RHS) && !KEEPL;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
