@@ -115,12 +115,13 @@ class ClockSampler(object):
 
     def __init__(self, index):
         self.index = index
-        self.lines = []
+        self.lines = []          # (arrival time, csv line)
         self.p = None
+        self.t_start = self.t_end = None
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200",
+            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50",
                                        "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -129,7 +130,13 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.p.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def mark_start(self):
+        self.t_start = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
 
     def stop(self):
         if self.p is None:
@@ -140,7 +147,14 @@ class ClockSampler(object):
         except Exception:
             self.p.kill()
         sm, mx, reasons, pw = [], [], set(), []
-        for l in self.lines:
+        # samples that arrived during the timed region; short regions fall back to everything since the sampler was
+        # started (it is started before the warm-up sweeps, so the GPU is under the same load)
+        timed = [l for (t, l) in self.lines if self.t_start is not None and self.t_start <= t <= (self.t_end or t)]
+        window = "timed region"
+        if len(timed) < 2:
+            timed = [l for (_, l) in self.lines][1:] or [l for (_, l) in self.lines]
+            window = "warm-up + timed region"
+        for l in timed:
             parts = [q.strip() for q in l.split(",")]
             if len(parts) < 9:
                 continue
@@ -154,7 +168,7 @@ class ClockSampler(object):
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "power_w_max": max(pw), "samples": len(sm)}
+                "power_w_max": max(pw), "samples": len(sm), "window": window}
 
 
 def fp64_peak():
@@ -246,28 +260,37 @@ def main():
     eng = engine.ChainEngine(x, y, model.design_matrix, groups, chains=C, seed=20261019, device=local, chain_offset=first)
     eng.set_state(hyper=start)
     eng.sweep(args.burnin)
+    clocks = ClockSampler(local)
+    clocks.start()
     eng.sweep(args.warmup)
     eng.sync()
     eng.status()
     eng.counters(clear=True)
-    eng.set_profile(True)
+    eng.set_profile(2)                        # one CUDA-event pair on the context's stream around the K sweeps
     _, launches0 = eng.profile()
-    clocks = ClockSampler(local)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    clocks.start()
+    clocks.mark_start()
     t0 = time.perf_counter()
     eng.sweep(args.steps)
     eng.sync()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
+    clocks.mark_end()
     clk = clocks.stop()
-    prof, launches1 = eng.profile()
-    eng.set_profile(False)
+    prof_total, launches1 = eng.profile()
+    dev_ms = prof_total["total"]
     eng.status()
     counts = eng.counters()
-    dev_ms = prof["total"]
+    # per-kernel breakdown for the roofline: the same K sweeps again with per-launch event brackets
+    eng.counters(clear=True)
+    eng.set_profile(1)
+    eng.sweep(args.steps)
+    eng.sync()
+    prof, _ = eng.profile()
+    counts_prof = eng.counters()
+    eng.set_profile(0)
     el = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(el, op=dist.ReduceOp.MAX)
@@ -277,9 +300,10 @@ def main():
     # ---------------- roofline of the dominant kernel (largest share of the step) ----------------
     peak, peak_src = fp64_peak()
     schur = bool(np.allclose(np.diff(x[:, 0]), np.diff(x[:, 0])[0], rtol=0, atol=1e-13)) and x.shape[1] == 1
-    fm = flops_model(n, f, P, [len(g) for g in groups], counts, schur)
-    kern = {"kinv": ("k_group_kinv (Kernel.K_inv per prior group: RBF build + jitchol + in-place inverse)", P * args.steps),
-            "function": ("k_function (Function._sample: residual projection, jitchol(A), solves, Philox draw)", f * args.steps),
+    fm = flops_model(n, f, P, [len(g) for g in groups], counts_prof, schur)
+    fm_timed = flops_model(n, f, P, [len(g) for g in groups], counts, schur)
+    kern = {"kinv": ("k_group_kinv (Kernel.K_inv of every prior group: RBF build + jitchol + in-place inverse)", args.steps),
+            "function": ("k_function (Function._sample: residual projection, jitchol(A), solves, Philox draw; one launch per sweep for balanced designs)", args.steps),
             "prior_slice": ("k_prior_schur (sigma+lengthscale slice steps: Toeplitz/Schur GP log-likelihood)" if schur else
                             "k_prior (sigma+lengthscale slice steps: dense GP log-likelihood)", P * args.steps)}
     dom = max(("kinv", "function", "prior_slice"), key=lambda k: prof[k])
@@ -287,11 +311,11 @@ def main():
     roofline = {"bound": "tensor", "kernel": kern[dom][0], "achieved": tf[dom], "peak": peak, "unit": "TFLOP/s",
                 "frac": tf[dom] / peak, "traffic": None, "peak_source": peak_src,
                 "flops_per_launch": fm[dom] / kern[dom][1], "ms_per_launch": prof[dom] / kern[dom][1],
-                "share_of_step": prof[dom] / dev_ms if dev_ms else None,
+                "share_of_step": prof[dom] / prof["total"] if prof["total"] else None,
                 "per_kernel": {k: {"ms_per_step": prof[k] / args.steps, "tflops": tf[k], "frac": tf[k] / peak,
                                    "launches_per_step": kern[k][1] / args.steps} for k in kern},
-                "whole_step": {"achieved": fm["total"] / (dev_ms * 1e-3) / 1e12,
-                               "frac": fm["total"] / (dev_ms * 1e-3) / 1e12 / peak,
+                "whole_step": {"achieved": fm_timed["total"] / (dev_ms * 1e-3) / 1e12,
+                               "frac": fm_timed["total"] / (dev_ms * 1e-3) / 1e12 / peak,
                                "note": "algorithmic flops of the executed algorithm (Schur slices are O(n^2))"},
                 "counted": {"factorisations_per_sweep_per_chain": counts["chol"] / (C * args.steps),
                             "logp_evals_per_slice_step": counts["logp"] / max(1, counts["slice_steps"]),

@@ -45,13 +45,19 @@ struct gpf_ctx {
   std::vector<Samp> order;
   std::vector<char> kinv_valid;
   bool toeplitz = false;
+  bool indep = false;                 // X^T X diagonal and nothing missing: function draws of a sweep are independent
+  int* d_fn_all = nullptr;            // all functions in sampler order / their sampler ids (device)
+  unsigned* d_sid_all = nullptr;
   std::vector<int> schur_warps;       // per group: warps per CTA of the Schur slice kernel (0: dense engine)
   int use_schur = 1;
+  int batch = 1;                       // batch independent function draws / K_inv of all groups into one launch
+  cudaStream_t aux[4] = {nullptr, nullptr, nullptr, nullptr};   // the groups' slice kernels of a batched sweep run concurrently
+  cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<void*> allocs;
   size_t smem_kinv = 0, smem_fn = 0;
   std::vector<size_t> smem_prior;
   unsigned long long launches = 0;
-  bool profile = false;
+  int profile = 0;                     // 0 off, 1 per-kernel + total CUDA-event timing, 2 total only
   double ms[6] = {0, 0, 0, 0, 0, 0};
   struct Ev { cudaEvent_t a, b; int cat; };
   std::vector<Ev> evs;
@@ -87,7 +93,7 @@ struct Timer {   // optional per-launch CUDA-event bracket (gpf_set_profile)
   int cat;
   cudaEvent_t a = nullptr, b = nullptr;
   Timer(gpf_ctx* ctx, int category) : c(ctx), cat(category) {
-    if (!c->profile) return;
+    if (c->profile != 1) return;
     auto get = [&]() {
       cudaEvent_t e;
       if (!c->ev_pool.empty()) { e = c->ev_pool.back(); c->ev_pool.pop_back(); }
@@ -98,7 +104,7 @@ struct Timer {   // optional per-launch CUDA-event bracket (gpf_set_profile)
     cudaEventRecord(a, c->stream);
   }
   ~Timer() {
-    if (!c->profile) return;
+    if (c->profile != 1) return;
     cudaEventRecord(b, c->stream);
     c->evs.push_back({a, b, cat});
   }
@@ -125,14 +131,15 @@ int dev_alloc(gpf_ctx* c, T** p, size_t count) {
   return GPF_OK;
 }
 
-int launch_kinv(gpf_ctx* c, int g) {
+int launch_kinv(gpf_ctx* c, int g, int count = 1) {
   Timer t(c, 1);
   CK(c, cudaMemsetAsync(c->dev.sched, 0, sizeof(int), c->stream));
-  if (c->toeplitz) k_group_kinv<true><<<c->grid, NTHR, c->smem_kinv, c->stream>>>(c->dev, g);
-  else k_group_kinv<false><<<c->grid, NTHR, c->smem_kinv, c->stream>>>(c->dev, g);
+  const int grid = std::min(c->dev.C * count, 2 * c->sms);
+  if (c->toeplitz) k_group_kinv<true><<<grid, NTHR, c->smem_kinv, c->stream>>>(c->dev, g, count);
+  else k_group_kinv<false><<<grid, NTHR, c->smem_kinv, c->stream>>>(c->dev, g, count);
   ++c->launches;
   CK(c, cudaGetLastError());
-  c->kinv_valid[g] = 1;
+  for (int q = g; q < g + count; ++q) c->kinv_valid[q] = 1;
   return GPF_OK;
 }
 
@@ -144,7 +151,25 @@ int launch_function(gpf_ctx* c, int fn, unsigned sampler_id, unsigned sweep, con
   }
   Timer t(c, 2);
   CK(c, cudaMemsetAsync(c->dev.sched, 0, sizeof(int), c->stream));
-  k_function<<<c->grid, NTHR, c->smem_fn, c->stream>>>(c->dev, fn, sampler_id, sweep, z, out);
+  k_function<<<c->grid, NTHR, c->smem_fn, c->stream>>>(c->dev, fn, sampler_id, nullptr, nullptr, 1, sweep, z, out);
+  ++c->launches;
+  CK(c, cudaGetLastError());
+  return GPF_OK;
+}
+
+// every function of the model in one launch (only when the draws are independent of each other, c->indep)
+int launch_all_functions(gpf_ctx* c, unsigned sweep) {
+  bool all_valid = true;
+  for (char v : c->kinv_valid) all_valid = all_valid && v;
+  if (!all_valid) {
+    int rc = launch_kinv(c, 0, c->dev.P);
+    if (rc) return rc;
+  }
+  Timer t(c, 2);
+  CK(c, cudaMemsetAsync(c->dev.sched, 0, sizeof(int), c->stream));
+  const int grid = std::min(c->dev.C * c->dev.f, 2 * c->sms);
+  k_function<<<grid, NTHR, c->smem_fn, c->stream>>>(c->dev, 0, 0u, c->d_fn_all, c->d_sid_all, c->dev.f, sweep, nullptr,
+                                                    FnOut{nullptr, nullptr, nullptr, nullptr});
   ++c->launches;
   CK(c, cudaGetLastError());
   return GPF_OK;
@@ -152,26 +177,30 @@ int launch_function(gpf_ctx* c, int fn, unsigned sampler_id, unsigned sweep, con
 
 // mode: 0/1 evaluate sigma / lengthscale candidates, 2/3 slice step on sigma / lengthscale, 4 fused sigma + lengthscale
 int launch_prior(gpf_ctx* c, int g, int mode, const double* cand, double* outv, unsigned sampler_id, unsigned sweep,
-                 const double* u, int nu, int* nev) {
+                 const double* u, int nu, int* nev, int slot = -1) {
   Timer t(c, 3);
   PriorArgs a{g, mode, cand, outv, c->slice_w[1 + 2 * g], c->slice_w[2 + 2 * g], c->slice_m[1 + 2 * g], c->slice_m[2 + 2 * g],
               sampler_id, sweep, u, nu, nev};
-  CK(c, cudaMemsetAsync(c->dev.sched, 0, sizeof(int), c->stream));
+  // slot >= 0: run on auxiliary stream `slot` with its own hand-out counter (concurrent slice kernels of different groups)
+  cudaStream_t st = slot >= 0 ? c->aux[slot] : c->stream;
+  CtxDev dev = c->dev;
+  if (slot >= 0) dev.sched = c->dev.sched + 1 + slot;
+  CK(c, cudaMemsetAsync(dev.sched, 0, sizeof(int), st));
   if (c->toeplitz && c->use_schur && (c->schur_warps[g] > 0 || (c->dev.n <= 256 && c->groups[g].size() <= 4))) {
     const int ng = (int)c->groups[g].size();
     if (c->dev.n <= 256 && ng <= 4) {       // vectors in registers
       const int grid = std::min((c->dev.C + 3) / 4, 3 * c->sms);   // 4 warps per CTA, 3 CTAs per SM (168 registers)
-      if (ng == 1) k_prior_schur<1><<<grid, 128, 0, c->stream>>>(c->dev, a);
-      else if (ng == 2) k_prior_schur<2><<<grid, 128, 0, c->stream>>>(c->dev, a);
-      else k_prior_schur<4><<<grid, 128, 0, c->stream>>>(c->dev, a);
+      if (ng == 1) k_prior_schur<1><<<grid, 128, 0, st>>>(dev, a);
+      else if (ng == 2) k_prior_schur<2><<<grid, 128, 0, st>>>(dev, a);
+      else k_prior_schur<4><<<grid, 128, 0, st>>>(dev, a);
     } else {
       const int wpc = c->schur_warps[g];
       const size_t smem = (size_t)wpc * schur_warp_doubles(c->dev.n, ng) * sizeof(double);
       const int grid = std::min((c->dev.C + wpc - 1) / wpc, 2 * c->sms);
-      k_prior_schur<0><<<grid, wpc * 32, smem, c->stream>>>(c->dev, a);
+      k_prior_schur<0><<<grid, wpc * 32, smem, st>>>(dev, a);
     }
-  } else if (c->toeplitz) k_prior<true><<<c->grid, NTHR, c->smem_prior[g], c->stream>>>(c->dev, a);
-  else k_prior<false><<<c->grid, NTHR, c->smem_prior[g], c->stream>>>(c->dev, a);
+  } else if (c->toeplitz) k_prior<true><<<c->grid, NTHR, c->smem_prior[g], st>>>(dev, a);
+  else k_prior<false><<<c->grid, NTHR, c->smem_prior[g], st>>>(dev, a);
   ++c->launches;
   CK(c, cudaGetLastError());
   if (mode >= 2) c->kinv_valid[g] = 0;
@@ -281,6 +310,11 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
     e = cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, d->device);
     if (e != cudaSuccess) { c->err = cudaGetErrorString(e); return fail(GPF_ERR_CUDA); }
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i) {
+      e = cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
     if (e != cudaSuccess) { c->err = cudaGetErrorString(e); return fail(GPF_ERR_CUDA); }
   }
   CtxDev& v = c->dev;
@@ -343,6 +377,7 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
     if (e != cudaSuccess) { c->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return fail(GPF_ERR_CUDA); }
   }
   c->grid = std::min(v.C, 2 * c->sms);
+  const int ws_ctas = 2 * c->sms;     // batched launches (several functions / groups per launch) may fill the GPU even for small C
   // device buffers
   const size_t tstride = (size_t)plt_tiles(v.NT) * TILE;
   v.ws_stride = tstride + (size_t)v.NEmax * v.NT * TILE;
@@ -354,10 +389,10 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
   if ((rc = dev_alloc(c, &dx, (size_t)d->n * d->p)) || (rc = dev_alloc(c, &dyT, (size_t)d->n * d->m)) ||
       (rc = dev_alloc(c, &dX, (size_t)d->m * d->f)) || (rc = dev_alloc(c, &dF, (size_t)v.C * d->f * d->n)) ||
       (rc = dev_alloc(c, &dh, (size_t)v.C * v.H)) || (rc = dev_alloc(c, &dK, (size_t)d->P * v.C * tstride)) ||
-      (rc = dev_alloc(c, &dws, (size_t)c->grid * v.ws_stride)) || (rc = dev_alloc(c, &dgof, (size_t)d->f)) ||
+      (rc = dev_alloc(c, &dws, (size_t)ws_ctas * v.ws_stride)) || (rc = dev_alloc(c, &dgof, (size_t)d->f)) ||
       (rc = dev_alloc(c, &dgf, (size_t)d->f)) || (rc = dev_alloc(c, &dgo, (size_t)d->P + 1)) ||
       (rc = dev_alloc(c, &dst, (size_t)v.C)) || (rc = dev_alloc(c, &dcn, (size_t)CNT_N)) ||
-      (rc = dev_alloc(c, &dsched, (size_t)4)) || (rc = dev_alloc(c, &dd2, (size_t)d->n)) || (rc = dev_alloc(c, &dG, (size_t)d->f * d->f)) ||
+      (rc = dev_alloc(c, &dsched, (size_t)8)) || (rc = dev_alloc(c, &dd2, (size_t)d->n)) || (rc = dev_alloc(c, &dG, (size_t)d->f * d->f)) ||
       (rc = dev_alloc(c, &dZ, (size_t)d->f * d->n)) || (rc = dev_alloc(c, &dfull, (size_t)d->n)))
     return fail(rc);
   // uniform grid?  then every RBF matrix is Toeplitz: K[i][j] = k(|i-j| h) and needs one exp per lag
@@ -396,6 +431,21 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
     gf.insert(gf.end(), c->groups[g].begin(), c->groups[g].end());
     go.push_back((int)gf.size());
   }
+  {
+    bool diag = true, nomiss = true;
+    for (int a = 0; a < d->f; ++a)
+      for (int b = 0; b < d->f; ++b)
+        if (a != b && G[(size_t)a * d->f + b] != 0.0) diag = false;
+    for (unsigned char u : full) nomiss = nomiss && u;
+    c->indep = diag && nomiss;
+    std::vector<int> fl;
+    std::vector<unsigned> sl;
+    for (size_t i = 0; i < c->order.size(); ++i)
+      if (c->order[i].kind == 1) { fl.push_back(c->order[i].arg); sl.push_back((unsigned)i); }
+    if ((rc = dev_alloc(c, &c->d_fn_all, fl.size())) || (rc = dev_alloc(c, &c->d_sid_all, sl.size()))) return fail(rc);
+    cudaMemcpy(c->d_fn_all, fl.data(), sizeof(int) * fl.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(c->d_sid_all, sl.data(), sizeof(unsigned) * sl.size(), cudaMemcpyHostToDevice);
+  }
   cudaError_t e = cudaMemcpy(dx, d->h_x, sizeof(double) * d->n * d->p, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(dyT, yT.data(), sizeof(double) * yT.size(), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(dX, d->h_X, sizeof(double) * d->m * d->f, cudaMemcpyHostToDevice);
@@ -426,6 +476,11 @@ void gpf_destroy(gpf_ctx* c) {
   collect_profile(c);
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   for (void* p : c->allocs) cudaFree(p);
+  for (int i = 0; i < 4; ++i) {
+    if (c->aux[i]) { cudaStreamSynchronize(c->aux[i]); cudaStreamDestroy(c->aux[i]); }
+    if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+  }
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -563,6 +618,31 @@ int gpf_sweep(gpf_ctx* c, int n_sweeps, int thin, unsigned sweep0, const int* h_
   }
   for (int s = 0; s < n_sweeps; ++s) {
     const unsigned sweep = sweep0 + (unsigned)s;
+    if (!h_order && c->indep && c->batch) {
+      // Balanced design, nothing missing: given the hyper-parameters the function draws of a sweep do not depend on
+      // each other (X^T X diagonal), and a group's slice steps only read that group's functions, so the reference's
+      // order  y_sigma, [functions, sigma, lengthscale] per group  is reproduced exactly by
+      //   y_sigma | K_inv of all groups | all functions | slices per group   (same Philox counters, same inputs)
+      int rc = launch_slice(c, 0, 1, nullptr, nullptr, 0u, sweep, nullptr, 0, nullptr);
+      if (!rc) rc = launch_all_functions(c, sweep);
+      // the groups' slice kernels are independent of each other: run them concurrently on auxiliary streams when the
+      // chain count alone does not fill the GPU (and per-kernel timing is off -- the timers sit on the main stream)
+      const bool conc = c->profile != 1 && c->dev.C < 8 * c->sms;
+      if (conc && !rc) CK(c, cudaEventRecord(c->ev_fork, c->stream));
+      int used = 0;
+      for (int k = 0; k < ns && !rc; ++k)
+        if (c->order[k].kind == 0 && c->order[k].arg >= 1 && (c->order[k].arg - 1) % 2 == 0) {
+          const int g = (c->order[k].arg - 1) / 2, slot = conc ? g % 4 : -1;
+          if (conc && used < 4 && slot == used) { CK(c, cudaStreamWaitEvent(c->aux[slot], c->ev_fork, 0)); ++used; }
+          rc = launch_prior(c, g, 4, nullptr, nullptr, (unsigned)k, sweep, nullptr, 0, nullptr, slot);
+        }
+      if (conc && !rc)
+        for (int i = 0; i < used; ++i) {
+          CK(c, cudaEventRecord(c->ev_join[i], c->aux[i]));
+          CK(c, cudaStreamWaitEvent(c->stream, c->ev_join[i], 0));
+        }
+      if (rc) return rc;
+    } else
     for (int k = 0; k < ns; ++k) {
       const int sid = h_order ? h_order[(size_t)s * ns + k] : k;
       const Samp& sp = c->order[sid];
@@ -604,11 +684,12 @@ int gpf_sweep(gpf_ctx* c, int n_sweeps, int thin, unsigned sweep0, const int* h_
 
 int gpf_set_option(gpf_ctx* c, int option, int value) {
   if (option == 0) { c->use_schur = value; return GPF_OK; }
+  if (option == 1) { c->batch = value; return GPF_OK; }
   c->err = "gpf_set_option: unknown option";
   return GPF_ERR_ARG;
 }
 
-int gpf_set_profile(gpf_ctx* c, int on) { c->profile = on != 0; return GPF_OK; }
+int gpf_set_profile(gpf_ctx* c, int on) { c->profile = on; return GPF_OK; }
 
 int gpf_get_profile(gpf_ctx* c, double* h_ms6, unsigned long long* h_launches) {
   if (h_ms6) for (int i = 0; i < 6; ++i) h_ms6[i] = c->ms[i];

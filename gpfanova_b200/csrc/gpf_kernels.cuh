@@ -128,13 +128,15 @@ __global__ void __launch_bounds__(NTHR) k_tiles_to_dense(const double* tiles, si
 // The inverse is built in place in its destination (c.Kinv), never as a separate L / L^-1.
 // ---------------------------------------------------------------------------------------------------------
 template <bool TOEP>
-__global__ void __launch_bounds__(NTHR, 2) k_group_kinv(CtxDev c, int g) {
+__global__ void __launch_bounds__(NTHR, 2) k_group_kinv(CtxDev c, int g_first, int g_count) {
   EngineSmem sm(smem_base(), c.NT, 0);
   double* xs = smem_base() + engine_smem_doubles(c.NT, 0);   // TOEP: lag table (n); else scaled inputs (n*p) + xsq (n)
   double* xsq = xs + (size_t)c.n * c.p;
   const size_t tstride = (size_t)plt_tiles(c.NT) * TILE;
   __shared__ int s_chain;
-  for (int ch = next_chain(c.sched, &s_chain); ch < c.C; ch = next_chain(c.sched, &s_chain)) {
+  // items = (group, chain) pairs: g_count groups x C chains, handed out dynamically
+  for (int item = next_chain(c.sched, &s_chain); item < c.C * g_count; item = next_chain(c.sched, &s_chain)) {
+    const int ch = item % c.C, g = g_first + item / c.C;
     const double sigma = exp10(c.hyper[(size_t)ch * c.H + 1 + 2 * g]);
     const double ls = exp10(c.hyper[(size_t)ch * c.H + 2 + 2 * g]);
     double* W = c.Kinv + ((size_t)g * c.C + ch) * tstride;
@@ -179,21 +181,28 @@ __global__ void __launch_bounds__(NTHR, 2) k_group_kinv(CtxDev c, int g) {
 // ---------------------------------------------------------------------------------------------------------
 struct FnOut { double *mu, *LA, *mt, *nt; };
 
-__global__ void __launch_bounds__(NTHR, 2) k_function(CtxDev c, int fn, unsigned sampler_id, unsigned sweep,
+// fn_list / sid_list (nfn entries; nullptr: the single function fn_single): functions drawn by this launch.  Several
+// functions may share a launch only when their conditionals do not depend on each other (X^T X diagonal and nothing
+// missing -- decided by the host), items = (function, chain) pairs.
+__global__ void __launch_bounds__(NTHR, 2) k_function(CtxDev c, int fn_single, unsigned sid_single, const int* __restrict__ fn_list,
+                                                      const unsigned* __restrict__ sid_list, int nfn, unsigned sweep,
                                                       const double* __restrict__ z_inject, FnOut out) {
   const int NT = c.NT, n = c.n, npad = NT * TB;
   EngineSmem sm(smem_base(), NT, 1);
   double* xs = smem_base() + engine_smem_doubles(NT, 1);   // 2 x npad: w -> mu, w+z -> beta
   double* brow = xs + 2 * npad;                            // npad
   double* red = brow + npad;                               // NW*2*32
-  const int g = c.group_of_fn[fn];
   const size_t tstride = (size_t)plt_tiles(NT) * TILE;
   double* W = c.ws + (size_t)blockIdx.x * c.ws_stride;
   double* Wx = W + tstride;
   const Stream rng{c.k0, c.k1};
-  const double* Grow = c.G + (size_t)fn * c.f;
   __shared__ int s_chain;
-  for (int ch = next_chain(c.sched, &s_chain); ch < c.C; ch = next_chain(c.sched, &s_chain)) {
+  for (int item = next_chain(c.sched, &s_chain); item < c.C * nfn; item = next_chain(c.sched, &s_chain)) {
+    const int ch = item % c.C;
+    const int fn = fn_list ? fn_list[item / c.C] : fn_single;
+    const unsigned sampler_id = sid_list ? sid_list[item / c.C] : sid_single;
+    const int g = c.group_of_fn[fn];
+    const double* Grow = c.G + (size_t)fn * c.f;
     const double* Fc = c.F + (size_t)ch * c.f * n;
     const double* A0 = c.Kinv + ((size_t)g * c.C + ch) * tstride;
     const double yinv = 1.0 / (exp10(c.hyper[(size_t)ch * c.H]) + c.offset);   // white.py:7-9 through kernel.pyx:51-64

@@ -338,7 +338,8 @@ class ChainEngine(object):
         self.sync()
         return [b.numpy() for b in blocks]
 
-    def set_profile(self, on=True):
+    def set_profile(self, on=1):
+        """0 off; 1 per-kernel + total CUDA-event timing of the next sweep() calls; 2 total only"""
         self._ck(self._lib.gpf_set_profile(self._h, int(on)))
 
     def profile(self):

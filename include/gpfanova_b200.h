@@ -152,9 +152,12 @@ int gpf_sweep(gpf_ctx* ctx, int n_sweeps, int thin, unsigned sweep0, const int* 
 
 /* timing/accounting of the last gpf_sweep call, measured with CUDA events on the ctx stream:
  * h_ms[0] total, [1] kinv kernels, [2] function kernels, [3] slice kernels, [4] y_sigma kernel, [5] store.
- * Only filled when profiling was enabled with gpf_set_profile(ctx, 1) (adds event overhead). */
+ * gpf_set_profile(ctx, 1): total + per-kernel brackets (adds event overhead, serialises the groups' slice kernels);
+ * gpf_set_profile(ctx, 2): total only (one event pair around the whole call); 0: off. */
 /* options: 0 = use the O(n^2) Toeplitz (Schur algorithm) slice log-likelihood when the time grid is uniform
- * (default 1; 0 forces the dense tile engine, which is always used for non-uniform inputs). */
+ * (default 1; 0 forces the dense tile engine, which is always used for non-uniform inputs);
+ * 1 = batch the independent function draws (balanced design, nothing missing) and the K_inv of all groups of a sweep
+ * into single launches (default 1; results are identical either way). */
 int gpf_set_option(gpf_ctx* ctx, int option, int value);
 int gpf_set_profile(gpf_ctx* ctx, int on);
 int gpf_get_profile(gpf_ctx* ctx, double* h_ms6, unsigned long long* h_launches);

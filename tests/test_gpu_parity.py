@@ -496,3 +496,24 @@ def test_prior_loglik_paths(eng, path):
             m.sweep(st, ch, s)
             assert np.allclose(hist[s, ch, :e.H], m.hyper, rtol=0, atol=1e-6), (path, ch, s)
     e.close()
+
+
+def test_batched_launches_are_identical_to_sequential(eng):
+    """balanced design, nothing missing: batching all function draws / K_inv of a sweep into single launches must
+    reproduce the sequential sampler order bit for bit (gpf_set_option 1)"""
+    c = load_case("twoway_n24")
+    C, S = 5, 4
+    outs = []
+    for batch in (1, 0):
+        e = make_engine(eng, c, chains=C, seed=42)
+        e.set_option(1, batch)
+        hist = torch.zeros((S, C, e.H + e.f * e.n), dtype=torch.float64, device="cuda")
+        e.sweep(S, history=hist)
+        e.sync()
+        e.status()
+        outs.append(hist.cpu().numpy())
+        n_launch = e.profile()[1]
+        e.close()
+        outs.append(n_launch)
+    assert np.array_equal(outs[0], outs[2])
+    assert outs[1] < outs[3]          # fewer launches when batched
