@@ -175,6 +175,11 @@ int launch_all_functions(gpf_ctx* c, unsigned sweep) {
   return GPF_OK;
 }
 
+// the O(n^2) Toeplitz path needs a uniform grid and vectors that fit registers or shared memory
+bool uses_schur(const gpf_ctx* c, int g) {
+  return c->toeplitz && c->use_schur && (c->schur_warps[g] > 0 || (c->dev.n <= 256 && c->groups[g].size() <= 4));
+}
+
 // mode: 0/1 evaluate sigma / lengthscale candidates, 2/3 slice step on sigma / lengthscale, 4 fused sigma + lengthscale
 int launch_prior(gpf_ctx* c, int g, int mode, const double* cand, double* outv, unsigned sampler_id, unsigned sweep,
                  const double* u, int nu, int* nev, int slot = -1) {
@@ -186,7 +191,7 @@ int launch_prior(gpf_ctx* c, int g, int mode, const double* cand, double* outv, 
   CtxDev dev = c->dev;
   if (slot >= 0) dev.sched = c->dev.sched + 1 + slot;
   CK(c, cudaMemsetAsync(dev.sched, 0, sizeof(int), st));
-  if (c->toeplitz && c->use_schur && (c->schur_warps[g] > 0 || (c->dev.n <= 256 && c->groups[g].size() <= 4))) {
+  if (uses_schur(c, g)) {
     const int ng = (int)c->groups[g].size();
     if (c->dev.n <= 256 && ng <= 4) {       // vectors in registers
       const int grid = std::min((c->dev.C + 3) / 4, 3 * c->sms);   // 4 warps per CTA, 3 CTAs per SM (168 registers)
@@ -627,7 +632,8 @@ int gpf_sweep(gpf_ctx* c, int n_sweeps, int thin, unsigned sweep0, const int* h_
       if (!rc) rc = launch_all_functions(c, sweep);
       // the groups' slice kernels are independent of each other: run them concurrently on auxiliary streams when the
       // chain count alone does not fill the GPU (and per-kernel timing is off -- the timers sit on the main stream)
-      const bool conc = c->profile != 1 && c->dev.C < 8 * c->sms;
+      bool conc = c->profile != 1 && c->dev.C < 8 * c->sms;
+      for (int g = 0; g < c->dev.P; ++g) conc = conc && uses_schur(c, g);   // the dense slice kernel owns the per-CTA workspace
       if (conc && !rc) CK(c, cudaEventRecord(c->ev_fork, c->stream));
       int used = 0;
       for (int k = 0; k < ns && !rc; ++k)
