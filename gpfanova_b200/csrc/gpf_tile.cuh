@@ -38,6 +38,11 @@ __device__ long long gpf_trace[8 * 8];
 #define GPF_STAMP_FLUSH
 #endif
 
+// warps per CTA: measured 8 -> 49.1, 6 -> 47.7, 4 -> 47.2 ms per cfg5 sweep (the engine is bound by the serial
+// pivot / panel chain of each matrix, not by warp-level throughput); 6 leaves 168 registers per thread at 2 CTAs/SM
+#ifndef GPF_NW
+#define GPF_NW 6
+#endif
 #ifndef GPF_ENGINE_INLINE
 #define GPF_ENGINE_INLINE __forceinline__
 #endif
@@ -47,7 +52,7 @@ namespace gpf {
 constexpr int TB = 32;            // tile edge
 constexpr int TILE = TB * TB;     // doubles per tile
 constexpr int PS = 36;            // row stride of a panel slot in shared memory (conflict-free DMMA fragment loads)
-constexpr int NW = 8;             // warps per CTA
+constexpr int NW = GPF_NW;        // warps per CTA
 constexpr int NTHR = NW * 32;
 constexpr unsigned FULLMASK = 0xffffffffu;
 constexpr int MAX_NT = 16;
