@@ -351,8 +351,8 @@ class Base(SamplerContainer):
         except np.linalg.LinAlgError as e:        # keep what was sampled, then propagate like the reference
             err = e
         self._pull_state()
-        for blk in blocks:
-            self._store_blocks(blk)
+        if blocks.shape[0]:
+            self._store_blocks(blocks)
         if verbose:
             logger.info("%d samples finished in %.2lf minutes" % (n, (time.time() - start_time) / 60))
         if err is not None:

@@ -53,6 +53,7 @@ struct gpf_ctx {
   int batch = 1;                       // batch independent function draws / K_inv of all groups into one launch
   cudaStream_t aux[4] = {nullptr, nullptr, nullptr, nullptr};   // the groups' slice kernels of a batched sweep run concurrently
   cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_user[4] = {nullptr, nullptr, nullptr, nullptr};   // gpf_record_event / gpf_wait_event
   std::vector<void*> allocs;
   size_t smem_kinv = 0, smem_fn = 0;
   std::vector<size_t> smem_prior;
@@ -318,6 +319,7 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) {
       e = cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking);
       if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_user[i], cudaEventDisableTiming | cudaEventBlockingSync);
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
     if (e != cudaSuccess) { c->err = cudaGetErrorString(e); return fail(GPF_ERR_CUDA); }
@@ -484,6 +486,7 @@ void gpf_destroy(gpf_ctx* c) {
   for (int i = 0; i < 4; ++i) {
     if (c->aux[i]) { cudaStreamSynchronize(c->aux[i]); cudaStreamDestroy(c->aux[i]); }
     if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+    if (c->ev_user[i]) cudaEventDestroy(c->ev_user[i]);
   }
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -523,6 +526,20 @@ int gpf_get_state(gpf_ctx* c, double* h_F, double* h_hyper) {
 int gpf_memcpy_d2h(gpf_ctx* c, void* h_dst, const void* d_src, size_t bytes) {
   CK(c, cudaSetDevice(c->device));
   CK(c, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  return GPF_OK;
+}
+
+int gpf_record_event(gpf_ctx* c, int idx) {
+  if (idx < 0 || idx > 3) { c->err = "gpf_record_event: idx must be 0..3"; return GPF_ERR_ARG; }
+  CK(c, cudaSetDevice(c->device));
+  CK(c, cudaEventRecord(c->ev_user[idx], c->stream));
+  return GPF_OK;
+}
+
+int gpf_wait_event(gpf_ctx* c, int idx) {
+  if (idx < 0 || idx > 3) { c->err = "gpf_wait_event: idx must be 0..3"; return GPF_ERR_ARG; }
+  CK(c, cudaSetDevice(c->device));
+  CK(c, cudaEventSynchronize(c->ev_user[idx]));
   return GPF_OK;
 }
 

@@ -301,42 +301,61 @@ class ChainEngine(object):
         """option 0: Toeplitz/Schur slice log-likelihood on uniform grids (1, default) or dense tile engine (0)"""
         self._ck(self._lib.gpf_set_option(self._h, int(option), int(value)))
 
-    def sweep_host(self, n_sweeps=1, thin=0, order=None, max_chunk_bytes=1 << 30, max_chunk_sweeps=None, on_chunk=None):
-        """sweep() with the stored states delivered to the host: returns a list of numpy blocks
-        (rows_i, C, H + f*n) backed by PINNED memory (D2H at DMA speed, no pageable staging copy).  The copy of a
-        chunk is queued on the context's stream right behind its sweeps; the next chunk's kernels queue behind it."""
+    def sweep_host(self, n_sweeps=1, thin=0, order=None, stage_bytes=96 << 20, max_chunk_sweeps=None, on_chunk=None):
+        """sweep() with the stored states delivered to the host as ONE numpy array (rows, C, H + f*n).
+
+        Double-buffered pipeline: the stored rows of a chunk of sweeps are copied device -> PINNED staging buffer on the
+        context's stream right behind the chunk's kernels (DMA speed, no pageable staging), and drained into the result
+        array by the host while the GPU already runs the next chunk.  The staging buffers (2 x <= stage_bytes) and the
+        device history buffers are kept by the engine and reused by later calls."""
         step = 1 if thin <= 0 else int(thin)
         cols = self.H + self.f * self.n
         rows_total = n_sweeps // step
+        order = None if order is None else np.asarray(order, dtype=np.int32).reshape(n_sweeps, len(self.order))
         if rows_total == 0:
             self.sweep(n_sweeps, thin=step, order=order)
             self.sync()
-            return []
-        max_rows = max(1, int(max_chunk_bytes // (self.C * cols * 8)))
+            return np.zeros((0, self.C, cols))
+        rowbytes = self.C * cols * 8
+        crow = max(1, int(stage_bytes // rowbytes))            # rows per chunk
         if max_chunk_sweeps:
-            max_rows = max(1, min(max_rows, int(max_chunk_sweeps) // step))
-        blocks, done = [], 0
-        order = None if order is None else np.asarray(order, dtype=np.int32).reshape(n_sweeps, len(self.order))
+            crow = max(1, min(crow, int(max_chunk_sweeps) // step))
+        if getattr(self, "_stage", None) is None or self._stage[0].shape[0] < crow:
+            self._stage = [torch.empty((crow, self.C, cols), dtype=torch.float64, pin_memory=True) for _ in range(2)]
+            self._dev_hist = [torch.empty((crow, self.C, cols), dtype=torch.float64, device=self.dev) for _ in range(2)]
+        out = np.empty((rows_total, self.C, cols))
+        pending = []                                           # (buffer index, first row, rows)
+        done, row0, i = 0, 0, 0
+
+        def drain():
+            b, r0, nr = pending.pop(0)
+            self._ck(self._lib.gpf_wait_event(self._h, b))
+            np.copyto(out[r0:r0 + nr], self._stage[b].numpy()[:nr])
+
         while done < n_sweeps:
-            k = min(max_rows * step, n_sweeps - done)
+            k = min(crow * step, n_sweeps - done)
             rows = k // step
+            b = i % 2
+            if len(pending) == 2:
+                drain()                                        # frees buffer b (chunk i-2) while chunk i-1 runs on the GPU
+            sub = None if order is None else order[done:done + k]
             if rows == 0:
-                self.sweep(k, thin=step, order=None if order is None else order[done:done + k])
-                done += k
-                continue
-            if self._dev_hist is None or self._dev_hist.shape[0] < rows:
-                self._dev_hist = torch.empty((rows, self.C, cols), dtype=torch.float64, device=self.dev)
-            dev = self._dev_hist[:rows]
-            got = self.sweep(k, thin=step, history=dev, order=None if order is None else order[done:done + k])
-            host = torch.empty((got, self.C, cols), dtype=torch.float64, pin_memory=True)
-            self._ck(self._lib.gpf_memcpy_d2h(self._h, C.c_void_p(host.data_ptr()), _ptr(dev), got * self.C * cols * 8))
-            blocks.append(host)
+                self.sweep(k, thin=step, order=sub)
+            else:
+                got = self.sweep(k, thin=step, history=self._dev_hist[b][:rows], order=sub)
+                self._ck(self._lib.gpf_memcpy_d2h(self._h, C.c_void_p(self._stage[b].data_ptr()), _ptr(self._dev_hist[b]),
+                                                  got * rowbytes))
+                self._ck(self._lib.gpf_record_event(self._h, b))
+                pending.append((b, row0, got))
+                row0 += got
+                i += 1
             done += k
             if on_chunk is not None:
-                self.sync()
                 on_chunk(done)
+        while pending:
+            drain()
         self.sync()
-        return [b.numpy() for b in blocks]
+        return out[:row0]
 
     def set_profile(self, on=1):
         """0 off; 1 per-kernel + total CUDA-event timing of the next sweep() calls; 2 total only"""

@@ -100,6 +100,10 @@ int gpf_get_state(gpf_ctx* ctx, double* h_F, double* h_hyper);
 /* asynchronous device -> host copy queued on the ctx stream behind the kernels already launched (history rows to
  * pinned host memory); complete after gpf_sync. */
 int gpf_memcpy_d2h(gpf_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
+/* four user events on the ctx stream (idx 0..3): record after queued work, block the host until it has completed --
+ * lets the caller drain history chunks from pinned staging buffers while the next sweeps run. */
+int gpf_record_event(gpf_ctx* ctx, int idx);
+int gpf_wait_event(gpf_ctx* ctx, int idx);
 double* gpf_device_F(gpf_ctx* ctx);       /* device pointers to the live state (chains x f x n) */
 double* gpf_device_hyper(gpf_ctx* ctx);   /* chains x H */
 int gpf_invalidate(gpf_ctx* ctx);         /* call after writing through gpf_device_hyper(): cached K_inv are stale */
