@@ -517,3 +517,27 @@ def test_batched_launches_are_identical_to_sequential(eng):
         outs.append(n_launch)
     assert np.array_equal(outs[0], outs[2])
     assert outs[1] < outs[3]          # fewer launches when batched
+
+
+def test_history_pipeline_chunking(eng):
+    """sweep_host: the double-buffered pinned staging pipeline must deliver the same rows whatever the chunk size,
+    with thinning and a trailing partial chunk"""
+    c = load_case("oneway_n50")
+    C, S, thin = 3, 23, 2
+    ref = None
+    for stage_bytes in (1 << 30, 4 * C * (5 + 3 * 50) * 8, 1):      # one chunk / 4 rows per chunk / 1 row per chunk
+        e = make_engine(eng, c, chains=C, seed=9)
+        seen = []
+        out = e.sweep_host(S, thin=thin, stage_bytes=stage_bytes, on_chunk=seen.append)
+        e.status()
+        F1, h1 = e.get_state()
+        assert out.shape == (S // thin, C, e.H + e.f * e.n) and seen[-1] == S
+        if ref is None:
+            ref = (out.copy(), np.array(F1), np.array(h1))
+        else:
+            assert np.array_equal(out, ref[0]) and np.array_equal(F1, ref[1]) and np.array_equal(h1, ref[2])
+        e.close()
+    # no stored rows at all
+    e = make_engine(eng, c, chains=C, seed=9)
+    assert e.sweep_host(3, thin=5).shape[0] == 0
+    e.close()
