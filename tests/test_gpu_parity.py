@@ -448,11 +448,13 @@ def test_full_size_sweep_statistics(eng):
 # every slice log-likelihood path: Schur in registers (n <= 256, |g| <= 4), Schur in shared memory (larger groups),
 # dense engine with the lag-table source (option 0 = 0) and dense engine with element-wise RBF (non-uniform inputs)
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("path", ["schur_reg", "schur_smem", "dense_toeplitz", "dense_general"])
+@pytest.mark.parametrize("path", ["schur_reg", "schur_smem", "dense_toeplitz", "dense_general", "schur_smem_40", "dense_40"])
 def test_prior_loglik_paths(eng, path):
     rng = np.random.default_rng(11)
     n = 72
     levels = 7 if path == "schur_smem" else 4         # group of 6 functions does not fit the register version
+    if path.endswith("_40"):
+        levels, n = 40, 24                            # 39 functions in one group: two right-hand-side tile rows (NE = 2)
     x = np.linspace(-1, 1, n)[:, None]
     if path == "dense_general":
         x = np.sort(rng.uniform(-1, 1, size=(n, 1)), axis=0)
@@ -466,7 +468,7 @@ def test_prior_loglik_paths(eng, path):
     y = F @ d.X.T + rng.normal(0, 0.1, size=(n, d.m))
     C = 8
     e = eng.ChainEngine(x, y, d.X, groups, chains=C, seed=5)
-    if path == "dense_toeplitz":
+    if path in ("dense_toeplitz", "dense_40"):
         e.set_option(0, 0)
     hyper = np.concatenate([np.full((C, 1), -2.0), rng.uniform(-0.8, 0.8, size=(C, e.H - 1))], axis=1)
     e.set_state(F=F.T, hyper=hyper)
