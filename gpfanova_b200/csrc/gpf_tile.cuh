@@ -28,10 +28,10 @@ __device__ long long gpf_trace[8 * 8];
     gpf_tacc[(s)] += now_ - gpf_tprev;                        \
     gpf_tprev = now_;                                         \
   } while (0)
-#define GPF_STAMP_INIT long long gpf_tacc[6] = {0, 0, 0, 0, 0, 0}; long long gpf_tprev = clock64();
+#define GPF_STAMP_INIT long long gpf_tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long gpf_tprev = clock64();
 #define GPF_STAMP_FLUSH                                                                          \
   if (blockIdx.x == 0 && (threadIdx.x & 31) == 0)                                                \
-    for (int s_ = 0; s_ < 6; ++s_) gpf_trace[(threadIdx.x >> 5) * 8 + s_] += gpf_tacc[s_];
+    for (int s_ = 0; s_ < 8; ++s_) gpf_trace[(threadIdx.x >> 5) * 8 + s_] += gpf_tacc[s_];
 #else
 #define GPF_STAMP(s)
 #define GPF_STAMP_INIT
@@ -418,7 +418,7 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 // shared-memory footprint (doubles) of the engine for NT matrix tile rows + NE extra panel slots
 __host__ __device__ inline size_t engine_smem_doubles(int NT, int NE) {
   return (size_t)TILE /*DT*/ + 256 /*Linv*/ + (size_t)(NT + NE) * TB * PS + (size_t)NT * TB /*rinv*/ + (size_t)NT * TB /*dvec*/ +
-         (size_t)TB /*piv*/ + (size_t)(NE > 0 ? NE : 1) * NT /*quadpart*/ + 16;
+         (size_t)TB /*piv*/ + (size_t)NT * TB /*pivall*/ + (size_t)(NE > 0 ? NE : 1) * NT /*quadpart*/ + 16;
 }
 
 struct EngineSmem {
@@ -428,6 +428,7 @@ struct EngineSmem {
   double* rinv;   // NT*32 reciprocal diagonal of L
   double* dvec;   // NT*32 additive diagonal applied at first touch (jitter, offset, n_t/sigma_y; 0 on padding)
   double* piv;    // 32 pivots of the current diagonal tile
+  double* pivall; // NT*32: every pivot of the factorisation (log-determinant is summed once at the end)
   double* quad;   // NE*NT partial sums of squares of finished augmented rows (deterministic reduction)
   double* scal;   // [0] logdet, [1] fail flag (as double), [2..9] block_sum scratch, [10] tile counter
   __device__ EngineSmem(double* base, int NT, int NE) {
@@ -437,7 +438,8 @@ struct EngineSmem {
     rinv = P + (size_t)(NT + NE) * TB * PS;
     dvec = rinv + NT * TB;
     piv = dvec + NT * TB;
-    quad = piv + TB;
+    pivall = piv + TB;
+    quad = pivall + NT * TB;
     scal = quad + (size_t)(NE > 0 ? NE : 1) * NT;
   }
   __device__ double* red() const { return scal + 2; }
@@ -519,18 +521,27 @@ __device__ __forceinline__ void diag_factor(int k, int lane, double* W, const En
   __syncwarp();
   const bool ok = potrf_tile(sm.DT, sm.rinv + k * TB, sm.piv);
   if (FAST_TRSM) inv8_blocks(sm.DT, sm.rinv + k * TB, sm.Linv, lane);
-  const double lg = warp_sum(log(sm.piv[lane]));
-  if (KEEPL) {
-    double* dst = W + (size_t)plt(k, k) * TILE + lane * TB;   // row `lane` of L_kk, upper part zero
-#pragma unroll
-    for (int c = 0; c < 32; c += 2) {
-      const double v0 = (c <= lane) ? sm.DT[c * TB + lane] : 0.0;
-      const double v1 = (c + 1 <= lane) ? sm.DT[(c + 1) * TB + lane] : 0.0;
-      *reinterpret_cast<double2*>(dst + c) = make_double2(v0, v1);
-    }
-  }
-  if (lane == 0) { sm.scal[0] += lg; if (!ok) sm.scal[1] = 1.0; }
+  sm.pivall[k * TB + lane] = sm.piv[lane];      // the log-determinant is summed after the last step
+  if (lane == 0 && !ok) sm.scal[1] = 1.0;
+  (void)W;
 }
+
+// store the diagonal factor L_kk (column-major in sm.DT) as a row-major tile with a zero upper triangle (KEEPL);
+// done by an otherwise idle warp during the panel phase, off the look-ahead's critical path
+__device__ __forceinline__ void store_diag_tile(const double* DT, double* tile, int lane) {
+  double* dst = tile + lane * TB;
+#pragma unroll
+  for (int c = 0; c < 32; c += 2) {
+    const double v0 = (c <= lane) ? DT[c * TB + lane] : 0.0;
+    const double v1 = (c + 1 <= lane) ? DT[(c + 1) * TB + lane] : 0.0;
+    *reinterpret_cast<double2*>(dst + c) = make_double2(v0, v1);
+  }
+}
+
+// named barriers (ids 1, 2; id 0 is __syncthreads): split arrive / wait so that the look-ahead warp and the others do not
+// wait for each other's work that they do not depend on
+__device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(NTHR) : "memory"); }
+__device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NTHR) : "memory"); }
 
 // prefetch one 8 KB tile into L1/L2 (64 lines of 128 B: two per lane)
 __device__ __forceinline__ void prefetch_tile(const double* tile, int lane) {
@@ -584,6 +595,7 @@ __device__ GPF_ENGINE_INLINE bool chol_engine(const Src& src, const EngineIO& io
     const int nreg = NT - 1 - k;
     const int nx = (AUG == AUG_RHS) ? NE : ((AUG == AUG_IDENT) ? (k + 1) : 0);
     if (tid == 0) *tilectr = (nreg > 0) ? 1 : 0;   // trailing tile 0 = next diagonal tile (look-ahead)
+    if (KEEPL && warp == NW - 1) store_diag_tile(sm.DT, W + (size_t)plt(k, k) * TILE, lane);
     for (int t = warp; t < nreg + nx; t += NW) {
       const int iown = k + 1 + t;
       int slot;
@@ -651,29 +663,38 @@ __device__ GPF_ENGINE_INLINE bool chol_engine(const Src& src, const EngineIO& io
       }
     }
     GPF_STAMP(2);
-    __syncthreads();
-    GPF_STAMP(3);
     // ---------------- phase 3: trailing updates (DMMA), with look-ahead on the next diagonal tile ----------------
-    // Warp 0 first updates tile (k+1,k+1) and factors it at once (DT / rinv are idle during this phase), so the serial
-    // 32-column potrf of step k+1 runs under the other warps' tensor work.  The remaining tiles are handed out
-    // dynamically (shared-memory counter); warp 0 joins when it is done.
+    // Warp 0 updates tile (k+1,k+1) -- which only needs the panel slot it has just solved itself -- and factors it at
+    // once, so the serial 32-column potrf of step k+1 runs under the other warps' tensor work.  Two named barriers
+    // keep the two sides from waiting on work they do not depend on: barrier 1 = "all panel slots are ready" (warp 0
+    // only arrives), barrier 2 = "nobody reads the diagonal factor of step k any more" (the others only arrive; warp 0
+    // waits on it before overwriting DT).  The remaining tiles are handed out dynamically; warp 0 joins when done.
     const int T1 = nreg * (nreg + 1) / 2;
     const int T2 = nx * nreg;
     const int T3 = (AUG == AUG_IDENT) ? (k + 1) * (k + 2) / 2 : 0;
-    if (warp == 0 && nreg > 0) {
-      const int i = k + 1;
-      CFrag f;
-      if (k == 0) {
-        src.cfrag(f, i, i, g, tig);
-        cfrag_add_diag(f, sm.dvec + i * TB, g, tig);
-      } else cfrag_load(f, W + (size_t)plt(i, i) * TILE, g, tig, 4);
-      tile_mma<true>(f, sm.P + (size_t)i * TB * PS, sm.P + (size_t)i * TB * PS, g, tig, 4);
-      cfrag_to_DT(f, sm.DT, g, tig);
+    if (nreg > 0) {
+      if (warp == 0) {
+        bar_arrive(1);
+        const int i = k + 1;
+        CFrag f;
+        if (k == 0) {
+          src.cfrag(f, i, i, g, tig);
+          cfrag_add_diag(f, sm.dvec + i * TB, g, tig);
+        } else cfrag_load(f, W + (size_t)plt(i, i) * TILE, g, tig, 4);
+        tile_mma<true>(f, sm.P + (size_t)i * TB * PS, sm.P + (size_t)i * TB * PS, g, tig, 4);
+        GPF_STAMP(4);
+        bar_sync(2);
+        cfrag_to_DT(f, sm.DT, g, tig);
 #ifndef GPF_DBG_NOLOOK
-      diag_factor<FAST_TRSM, KEEPL>(i, lane, W, sm);
+        diag_factor<FAST_TRSM, KEEPL>(i, lane, W, sm);
 #endif
-      GPF_STAMP(4);
-    }
+        GPF_STAMP(7);
+      } else {
+        bar_arrive(2);
+        bar_sync(1);
+      }
+    } else __syncthreads();
+    GPF_STAMP(3);
     // dynamic hand-out of the tiles; the ticket for the next tile is drawn before working on the current one so
     // that its accumulator tile can be prefetched under the tensor work
     const int TT = T1 + T2 + T3;
@@ -755,7 +776,15 @@ __device__ GPF_ENGINE_INLINE bool chol_engine(const Src& src, const EngineIO& io
   __syncthreads();
   GPF_STAMP(1);
   GPF_STAMP_FLUSH
-  return sm.scal[1] == 0.0;
+  if (sm.scal[1] != 0.0) return false;
+  {
+    double lg = 0.0;
+    for (int t = tid; t < NT * TB; t += NTHR) lg += log(sm.pivall[t]);
+    lg = block_sum(lg, sm.red());
+    if (tid == 0) sm.scal[0] = lg;
+    __syncthreads();
+  }
+  return true;
 }
 
 // sum of sm.quad over the NE*NT partials in fixed order (call after the engine; all threads get the value)

@@ -43,10 +43,10 @@ void run(const char* name, int ctas, int NE) {
   cudaMemcpy(hc.data(), cyc, ctas * 8, cudaMemcpyDeviceToHost); cudaMemcpy(ho.data(), out, ctas * 8, cudaMemcpyDeviceToHost);
   long long tr[64]; cudaMemcpyFromSymbol(tr, gpf_trace, sizeof tr);
   printf("%-22s ctas %3d: %7lld cycles/factorisation (logdet %.6f) %s\n", name, ctas, hc[0], ho[0], cudaGetErrorString(cudaGetLastError()));
-  const char* nm[6] = {"prologue", "wait-top", "phase2", "wait-p2", "lookahead", "phase3"};
+  const char* nm[8] = {"prologue", "wait-top", "phase2", "wait-p2", "look-mma", "phase3", "-", "look-potrf"};
   for (int w = 0; w < 8; w += 1) {
     printf("   warp %d:", w);
-    for (int s = 0; s < 6; ++s) printf(" %s %6lld", nm[s], tr[w * 8 + s] / reps);
+    for (int s = 0; s < 8; ++s) printf(" %s %6lld", nm[s], tr[w * 8 + s] / reps);
     printf("\n");
   }
   cudaFree(ws); cudaFree(F); cudaFree(out); cudaFree(cyc);

@@ -44,6 +44,24 @@ __global__ void __launch_bounds__(NTHR, 2) k_prim(const double* A, double* G, do
         cfrag_load(f, Gw + (size_t)(r & 3) * TILE, g, tig, 4);
         tile_mma<true>(f, slot[warp], slot[(warp + 1) & 7], g, tig, 4);
         cfrag_store(f, Gw + (size_t)(r & 3) * TILE, g, tig, 4);
+      } else if (what >= 8 && what <= 10) {   // potrf on warp 0 under background work on the other warps
+        if (warp == 0) {
+          for (int c = 0; c < 32; ++c) DT[warp][c * 32 + lane] = A[lane * 32 + c];
+          __syncwarp();
+          acc += potrf_tile(DT[warp], rinv[warp], piv[warp]) ? 1.0 : 0.0;
+        } else if (what == 8) {               // tile_mma (LDS fragments + DMMA)
+          CFrag f; cfrag_zero(f);
+          for (int q = 0; q < 3; ++q) tile_mma<true>(f, slot[warp], slot[(warp + 1) & 7], g, tig, 4);
+          acc += f.c[0][0][0];
+        } else if (what == 9) {               // DMMA only (operands in registers)
+          double c0 = 0, c1 = 0;
+          for (int q = 0; q < 3 * 128; ++q) dmma884(c0, c1, 1.0 + q, 0.5);
+          acc += c0 + c1;
+        } else {                              // LDS only
+          double s2 = 0;
+          for (int q = 0; q < 3 * 64; ++q) s2 += slot[warp][(g * PS + tig + 4 * (q & 7) + 8 * PS * ((q >> 3) & 3))];
+          acc += s2;
+        }
       } else if (what == 6) {   // inv8
         inv8_blocks(DT[warp], rinv[warp], Linv[warp], lane);
         __syncwarp();
@@ -64,8 +82,9 @@ int main() {
   long long hc[296];
   const int SMB = (8 * TILE + 8 * TB * PS + 512 + 8 * 256) * 8;
   cudaFuncSetAttribute(k_prim, cudaFuncAttributeMaxDynamicSharedMemorySize, SMB);
-  const char* nm[7] = {"potrf_tile", "trsm_slot", "trsm_hybrid", "trsm_dmma", "phase2 tile", "phase3 tile", "inv8_blocks"};
-  for (int what = 0; what < 7; ++what) {
+  const char* nm[11] = {"potrf_tile", "trsm_slot", "trsm_hybrid", "trsm_dmma", "phase2 tile", "phase3 tile", "inv8_blocks", "-", "potrf|bg mma", "potrf|bg dmma", "potrf|bg lds"};
+  for (int what = 0; what < 11; ++what) {
+    if (what == 7) continue;
     printf("%-12s", nm[what]);
     for (int nw : {1, 4, 8}) {
       k_prim<<<148, NTHR, SMB>>>(dA, dG, dout, dc, 20, nw, what); cudaMemcpy(hc, dc, 8 * 148, cudaMemcpyDeviceToHost);
