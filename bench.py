@@ -187,8 +187,9 @@ def flops_model(n, f, P, ng_list, counts, schur):
     slice factorisation: dense n^3/3 + |g| n^2, or -- uniform grid, Schur algorithm -- (3 + |g|) n^2."""
     n3 = float(n) ** 3
     inv = counts["inverses"] * n3
-    draws = counts["draws"] * (n3 / 3 + 6.0 * n * n)
-    prior_facts = counts["chol"] - counts["inverses"] - counts["draws"] - counts["jitter"]
+    fchol = counts.get("function_chol", counts["draws"])       # functions with identical conditional precision share one
+    draws = fchol * n3 / 3 + counts["draws"] * 6.0 * n * n
+    prior_facts = counts["chol"] - counts["inverses"] - fchol - (counts["jitter"] if fchol == counts["draws"] else 0)
     gbar = float(np.mean(ng_list))
     per = (3.0 + gbar) * n * n if schur else (n3 / 3 + gbar * n * n)
     return {"kinv": inv, "function": draws, "prior_slice": prior_facts * per, "prior_factorisations": prior_facts,

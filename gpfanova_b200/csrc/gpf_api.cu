@@ -48,9 +48,14 @@ struct gpf_ctx {
   bool indep = false;                 // X^T X diagonal and nothing missing: function draws of a sweep are independent
   int* d_fn_all = nullptr;            // all functions in sampler order / their sampler ids (device)
   unsigned* d_sid_all = nullptr;
+  int ncls = 0;                       // classes of functions sharing their conditional precision (indep designs)
+  bool cls_shared = false;            // some class has more than one function
+  int *d_cls_off = nullptr, *d_cls_fn = nullptr;
+  unsigned* d_cls_sid = nullptr;
   std::vector<int> schur_warps;       // per group: warps per CTA of the Schur slice kernel (0: dense engine)
   int use_schur = 1;
   int batch = 1;                       // batch independent function draws / K_inv of all groups into one launch
+  int share = 1;                       // one factorisation per class of functions with identical conditional precision
   cudaStream_t aux[4] = {nullptr, nullptr, nullptr, nullptr};   // the groups' slice kernels of a batched sweep run concurrently
   cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_user[4] = {nullptr, nullptr, nullptr, nullptr};   // gpf_record_event / gpf_wait_event
@@ -168,6 +173,13 @@ int launch_all_functions(gpf_ctx* c, unsigned sweep) {
   }
   Timer t(c, 2);
   CK(c, cudaMemsetAsync(c->dev.sched, 0, sizeof(int), c->stream));
+  if (c->cls_shared && c->share) {   // functions with identical conditional precision share one factorisation
+    const int grid = std::min(c->dev.C * c->ncls, 2 * c->sms);
+    k_function_class<<<grid, NTHR, c->smem_fn, c->stream>>>(c->dev, c->d_cls_off, c->d_cls_fn, c->d_cls_sid, c->ncls, sweep);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    return GPF_OK;
+  }
   const int grid = std::min(c->dev.C * c->dev.f, 2 * c->sms);
   k_function<<<grid, NTHR, c->smem_fn, c->stream>>>(c->dev, 0, 0u, c->d_fn_all, c->d_sid_all, c->dev.f, sweep, nullptr,
                                                     FnOut{nullptr, nullptr, nullptr, nullptr});
@@ -378,6 +390,7 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
     cudaError_t e = allow_smem(k_group_kinv<true>, c->smem_kinv);
     if (e == cudaSuccess) e = allow_smem(k_group_kinv<false>, c->smem_kinv);
     if (e == cudaSuccess) e = allow_smem(k_function, c->smem_fn);
+    if (e == cudaSuccess) e = allow_smem(k_function_class, c->smem_fn);
     if (e == cudaSuccess) e = allow_smem(k_prior<true>, sp);
     if (e == cudaSuccess) e = allow_smem(k_prior<false>, sp);
     if (e == cudaSuccess) e = allow_smem(k_prior_schur<0>, 112 * 1024);
@@ -442,7 +455,9 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
     bool diag = true, nomiss = true;
     for (int a = 0; a < d->f; ++a)
       for (int b = 0; b < d->f; ++b)
-        if (a != b && G[(size_t)a * d->f + b] != 0.0) diag = false;
+        // couplings below 1e-13 sqrt(G_aa G_bb) are rounding noise of the contrast construction (helmertConvert
+        // rescales the Helmert columns with square roots) and do not make the draws dependent
+        if (a != b && std::fabs(G[(size_t)a * d->f + b]) > 1e-13 * std::sqrt(G[(size_t)a * d->f + a] * G[(size_t)b * d->f + b])) diag = false;
     for (unsigned char u : full) nomiss = nomiss && u;
     c->indep = diag && nomiss;
     std::vector<int> fl;
@@ -452,6 +467,34 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
     if ((rc = dev_alloc(c, &c->d_fn_all, fl.size())) || (rc = dev_alloc(c, &c->d_sid_all, sl.size()))) return fail(rc);
     cudaMemcpy(c->d_fn_all, fl.data(), sizeof(int) * fl.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(c->d_sid_all, sl.data(), sizeof(unsigned) * sl.size(), cudaMemcpyHostToDevice);
+    // classes: functions of one group with the same (X^T X)[f,f] (only meaningful when the draws are independent)
+    std::vector<int> coff(1, 0), cfn;
+    std::vector<unsigned> csid;
+    if (c->indep) {
+      std::vector<char> used(fl.size(), 0);
+      for (size_t i = 0; i < fl.size(); ++i) {
+        if (used[i]) continue;
+        int cnt = 0;
+        for (size_t j = i; j < fl.size(); ++j) {
+          if (used[j] || c->group_of_fn[fl[j]] != c->group_of_fn[fl[i]]) continue;
+          if (std::fabs(G[(size_t)fl[j] * d->f + fl[j]] - G[(size_t)fl[i] * d->f + fl[i]]) > 1e-13 * G[(size_t)fl[i] * d->f + fl[i]]) continue;
+          if (cnt == TB) { coff.push_back((int)cfn.size()); cnt = 0; }      // at most 32 functions per item
+          used[j] = 1; cfn.push_back(fl[j]); csid.push_back(sl[j]); ++cnt;
+          if (cnt > 1) c->cls_shared = true;
+        }
+        coff.push_back((int)cfn.size());
+      }
+      c->ncls = (int)coff.size() - 1;
+      double* dfws;
+      if ((rc = dev_alloc(c, &c->d_cls_off, coff.size())) || (rc = dev_alloc(c, &c->d_cls_fn, cfn.size())) ||
+          (rc = dev_alloc(c, &c->d_cls_sid, csid.size())) ||
+          (rc = dev_alloc(c, &dfws, c->cls_shared ? (size_t)ws_ctas * 2 * TB * v.NT * TB : (size_t)1)))
+        return fail(rc);
+      v.fws = dfws;
+      cudaMemcpy(c->d_cls_off, coff.data(), sizeof(int) * coff.size(), cudaMemcpyHostToDevice);
+      cudaMemcpy(c->d_cls_fn, cfn.data(), sizeof(int) * cfn.size(), cudaMemcpyHostToDevice);
+      cudaMemcpy(c->d_cls_sid, csid.data(), sizeof(unsigned) * csid.size(), cudaMemcpyHostToDevice);
+    }
   }
   cudaError_t e = cudaMemcpy(dx, d->h_x, sizeof(double) * d->n * d->p, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(dyT, yT.data(), sizeof(double) * yT.size(), cudaMemcpyHostToDevice);
@@ -572,7 +615,7 @@ int gpf_get_counters(gpf_ctx* c, unsigned long long* h, int clear) {
   CK(c, cudaMemcpyAsync(tmp, c->dev.counters, sizeof tmp, cudaMemcpyDeviceToHost, c->stream));
   if (clear) CK(c, cudaMemsetAsync(c->dev.counters, 0, sizeof tmp, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
-  for (int i = 0; i < 6; ++i) h[i] = tmp[i];
+  for (int i = 0; i < 8; ++i) h[i] = tmp[i];
   return GPF_OK;
 }
 
@@ -708,6 +751,7 @@ int gpf_sweep(gpf_ctx* c, int n_sweeps, int thin, unsigned sweep0, const int* h_
 int gpf_set_option(gpf_ctx* c, int option, int value) {
   if (option == 0) { c->use_schur = value; return GPF_OK; }
   if (option == 1) { c->batch = value; return GPF_OK; }
+  if (option == 2) { c->share = value; return GPF_OK; }
   c->err = "gpf_set_option: unknown option";
   return GPF_ERR_ARG;
 }

@@ -13,7 +13,7 @@ constexpr double LOG2PI = 1.8378770664093453;   // log(2 pi)
 constexpr double LN10 = 2.302585092994046;
 
 // counters (gpf_get_counters)
-enum { CNT_CHOL = 0, CNT_LOGP = 1, CNT_JITTER = 2, CNT_DRAW = 3, CNT_INV = 4, CNT_SLICE = 5, CNT_N = 8 };
+enum { CNT_CHOL = 0, CNT_LOGP = 1, CNT_JITTER = 2, CNT_DRAW = 3, CNT_INV = 4, CNT_SLICE = 5, CNT_FNCHOL = 6, CNT_N = 8 };
 
 // device view of one sampler context (passed by value to every kernel)
 struct CtxDev {
@@ -38,6 +38,7 @@ struct CtxDev {
   const double* Z;            // f x n   X^T y over the observed entries (NaN -> 0)
   const unsigned char* full;  // n       1 if no observation is missing at time t
   int* sched;                 // chain hand-out counter of the running launch (reset to 0 by the host before it)
+  double* fws;                // per-CTA scratch of the class-mode function kernel: 2 x 32 x NT*32 doubles each
 };
 
 // dynamic hand-out of chains to CTAs (chains differ in the number of slice evaluations they need): returns the next

@@ -289,6 +289,101 @@ __global__ void __launch_bounds__(NTHR, 2) k_function(CtxDev c, int fn_single, u
       status_merge(c.status + ch, code);
       atomicAdd(c.counters + CNT_CHOL, 1ull + (unsigned long long)tries);
       atomicAdd(c.counters + CNT_DRAW, 1ull);
+      atomicAdd(c.counters + CNT_FNCHOL, 1ull + (unsigned long long)tries);
+      if (tries) atomicAdd(c.counters + CNT_JITTER, (unsigned long long)tries);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Function._sample for a CLASS of functions that share their conditional precision matrix.
+// In a balanced design with nothing missing, n_t = (X^T X)[f,f] for every t, so functions of one prior group with equal
+// (X^T X)[f,f] have the SAME  A = K_inv + n_f/(sigma_y + offset) I  (with helmertConvert=True: every function of a group,
+// e.g. 361 interaction functions of a 20 x 20 design).  One factorisation then serves the whole class: the functions'
+// right-hand sides b_f ride along as rows of one augmented tile row, and each function gets its own two back
+// substitutions (mu_f, beta_f = L_A^-T (w_f + z_f)).  Results are identical to the one-function kernel (same A, same
+// L_A, every row of the augmented block is solved independently of the others).
+// Items = (class, chain); cls_off / cls_fn / cls_sid: CSR list of the functions (and sampler ids) of every class.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHR, 2) k_function_class(CtxDev c, const int* __restrict__ cls_off, const int* __restrict__ cls_fn,
+                                                            const unsigned* __restrict__ cls_sid, int ncls, unsigned sweep) {
+  const int NT = c.NT, n = c.n, npad = NT * TB;
+  EngineSmem sm(smem_base(), NT, 1);
+  double* xs = smem_base() + engine_smem_doubles(NT, 1);   // 2 x npad: w -> mu, w+z -> beta
+  double* red = xs + 3 * npad;                             // NW*2*32  (same carve-up as k_function)
+  const size_t tstride = (size_t)plt_tiles(NT) * TILE;
+  double* W = c.ws + (size_t)blockIdx.x * c.ws_stride;
+  double* Wx = W + tstride;
+  double* brow = c.fws + (size_t)blockIdx.x * 2 * TB * npad;   // right-hand sides of the class, 32 x npad
+  double* wrow = brow + (size_t)TB * npad;                     // forward-solved rows
+  const Stream rng{c.k0, c.k1};
+  __shared__ int s_chain;
+  for (int item = next_chain(c.sched, &s_chain); item < c.C * ncls; item = next_chain(c.sched, &s_chain)) {
+    const int ch = item % c.C, cls = item / c.C;
+    const int* fns = cls_fn + cls_off[cls];
+    const unsigned* sids = cls_sid + cls_off[cls];
+    const int nf = cls_off[cls + 1] - cls_off[cls];
+    const int f0 = fns[0], g = c.group_of_fn[f0];
+    const double* A0 = c.Kinv + ((size_t)g * c.C + ch) * tstride;
+    const double yinv = 1.0 / (exp10(c.hyper[(size_t)ch * c.H]) + c.offset);
+    const double nt = c.G[(size_t)f0 * c.f + f0];
+    __syncthreads();
+    for (int t = threadIdx.x; t < npad; t += NTHR) sm.dvec[t] = (t < n) ? nt * yinv : 0.0;
+    for (int e = threadIdx.x; e < nf * npad; e += NTHR) {
+      const int j = e / npad, t = e % npad;
+      brow[e] = (t < n) ? yinv * c.Z[(size_t)fns[j] * n + t] : 0.0;      // function.py:32 with m_t = (X^T y)[f,t]
+    }
+    int tries = 0, code = 0;
+    double jitter = 0.0;
+    for (;;) {
+      __syncthreads();
+      EngineIO io{W, Wx, RowSrc{brow, nullptr, npad, nf, n}, wrow, npad};
+      if (chol_engine<AUG_RHS, true>(SrcTiles{A0}, io, NT, 1, (nf + 7) / 8, sm)) { code = tries; break; }
+      if (tries == 0) {   // jitchol ladder on A (linalg.py:41-54)
+        double s = 0.0, bad = 0.0;
+        for (int t = threadIdx.x; t < n; t += NTHR) {
+          const double d = A0[(size_t)plt(t >> 5, t >> 5) * TILE + (t & 31) * TB + (t & 31)] + sm.dvec[t];
+          s += d;
+          if (d <= 0.0) bad += 1.0;
+        }
+        s = block_sum(s, sm.red());
+        bad = block_sum(bad, sm.red());
+        if (bad > 0.0) { code = GPF_STATUS_NONPOS_DIAG; break; }
+        jitter = s / n * 1e-6;
+        for (int t = threadIdx.x; t < n; t += NTHR) sm.dvec[t] += jitter;
+      } else {
+        for (int t = threadIdx.x; t < n; t += NTHR) sm.dvec[t] += 9.0 * jitter;
+        jitter *= 10.0;
+      }
+      ++tries;
+      if (tries > c.maxtries || !isfinite(jitter)) { code = GPF_STATUS_NOT_PD; break; }
+    }
+    __syncthreads();
+    if (code >= 0) {
+      for (int j = 0; j < nf; ++j) {
+        const int fn = fns[j];
+        for (int t = threadIdx.x; t < npad; t += NTHR) {
+          xs[t] = (t < n) ? wrow[(size_t)j * npad + t] : 0.0;
+          xs[npad + t] = 0.0;
+        }
+        __syncthreads();
+        for (int pr = threadIdx.x; 2 * pr < n; pr += NTHR) {
+          double z0, z1;
+          rng.normal_pair((unsigned)(ch + c.chain_offset), sweep, sids[j], (unsigned)pr, z0, z1);
+          xs[npad + 2 * pr] = xs[2 * pr] + z0;
+          if (2 * pr + 1 < n) xs[npad + 2 * pr + 1] = xs[2 * pr + 1] + z1;
+        }
+        __syncthreads();
+        back_solve<2>(W, NT, xs, npad, sm, red);
+        for (int t = threadIdx.x; t < n; t += NTHR) c.F[((size_t)ch * c.f + fn) * n + t] = xs[npad + t];
+        __syncthreads();
+      }
+    }
+    if (threadIdx.x == 0) {
+      status_merge(c.status + ch, code);
+      atomicAdd(c.counters + CNT_CHOL, 1ull + (unsigned long long)tries);
+      atomicAdd(c.counters + CNT_FNCHOL, 1ull + (unsigned long long)tries);
+      atomicAdd(c.counters + CNT_DRAW, (unsigned long long)nf);
       if (tries) atomicAdd(c.counters + CNT_JITTER, (unsigned long long)tries);
     }
   }

@@ -223,9 +223,9 @@ class ChainEngine(object):
         return st
 
     def counters(self, clear=False):
-        c = np.zeros(6, dtype=np.uint64)
+        c = np.zeros(8, dtype=np.uint64)
         self._ck(self._lib.gpf_get_counters(self._h, c.ctypes.data_as(C.c_void_p), int(clear)))
-        return dict(zip(["chol", "logp", "jitter", "draws", "inverses", "slice_steps"], [int(v) for v in c]))
+        return dict(zip(["chol", "logp", "jitter", "draws", "inverses", "slice_steps", "function_chol"], [int(v) for v in c[:7]]))
 
     # -- pieces of the sweep -------------------------------------------------------------------
     def group_kinv(self, g, want=True):
@@ -298,7 +298,8 @@ class ChainEngine(object):
         return int(rows.value)
 
     def set_option(self, option, value):
-        """option 0: Toeplitz/Schur slice log-likelihood on uniform grids (1, default) or dense tile engine (0)"""
+        """option 0: Toeplitz/Schur slice log-likelihood on uniform grids (1, default) or dense tile engine (0);
+        1: batched launches; 2: shared factorisation for functions with identical conditional precision"""
         self._ck(self._lib.gpf_set_option(self._h, int(option), int(value)))
 
     def sweep_host(self, n_sweeps=1, thin=0, order=None, stage_bytes=96 << 20, max_chunk_sweeps=None, on_chunk=None):

@@ -114,8 +114,9 @@ int gpf_n_samplers(gpf_ctx* ctx);         /* 1 + f + 2P: length of the non-Trans
 int gpf_get_status(gpf_ctx* ctx, int* h_status, int clear);
 
 /* counters since creation/clear: [0] factorisations, [1] log-density evaluations in slice steps,
- * [2] jitter retries, [3] function draws, [4] inverse (potri) count, [5] slice steps. */
-int gpf_get_counters(gpf_ctx* ctx, unsigned long long* h_counters6, int clear);
+ * [2] jitter retries, [3] function draws, [4] inverse (potri) count, [5] slice steps, [6] factorisations executed for
+ * function draws (fewer than [3] when functions share their conditional precision), [7] reserved. */
+int gpf_get_counters(gpf_ctx* ctx, unsigned long long* h_counters8, int clear);
 
 /* Kernel.K_inv for prior group g of every chain at the current hyper-parameters (kernel.pyx:51-64
  * with rbf.pyx:16-19); result kept inside the ctx for gpf_function_step.  g = -1: all groups.
@@ -161,7 +162,9 @@ int gpf_sweep(gpf_ctx* ctx, int n_sweeps, int thin, unsigned sweep0, const int* 
 /* options: 0 = use the O(n^2) Toeplitz (Schur algorithm) slice log-likelihood when the time grid is uniform
  * (default 1; 0 forces the dense tile engine, which is always used for non-uniform inputs);
  * 1 = batch the independent function draws (balanced design, nothing missing) and the K_inv of all groups of a sweep
- * into single launches (default 1; results are identical either way). */
+ * into single launches (default 1; results are identical either way);
+ * 2 = let functions of a group with identical conditional precision (balanced design, equal (X^T X)[f,f]) share one
+ * factorisation (default 1; results are identical either way). */
 int gpf_set_option(gpf_ctx* ctx, int option, int value);
 int gpf_set_profile(gpf_ctx* ctx, int on);
 int gpf_get_profile(gpf_ctx* ctx, double* h_ms6, unsigned long long* h_launches);

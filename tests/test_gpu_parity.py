@@ -500,25 +500,37 @@ def test_prior_loglik_paths(eng, path):
     e.close()
 
 
-def test_batched_launches_are_identical_to_sequential(eng):
-    """balanced design, nothing missing: batching all function draws / K_inv of a sweep into single launches must
-    reproduce the sequential sampler order bit for bit (gpf_set_option 1)"""
-    c = load_case("twoway_n24")
+@pytest.mark.parametrize("name", ["twoway_n24", "twoway_n24_hc"])
+def test_batched_launches_are_identical_to_sequential(eng, name):
+    """balanced design, nothing missing: batching all function draws / K_inv of a sweep into single launches, and
+    sharing one factorisation between functions with identical conditional precision (helmertConvert: every function of
+    a group), must reproduce the sequential sampler order bit for bit (gpf_set_option 1, 2)"""
+    c = load_case(name)
     C, S = 5, 4
-    outs = []
-    for batch in (1, 0):
+    outs, launches, fchol = [], [], []
+    for batch, share in ((1, 1), (1, 0), (0, 0)):
         e = make_engine(eng, c, chains=C, seed=42)
         e.set_option(1, batch)
+        e.set_option(2, share)
         hist = torch.zeros((S, C, e.H + e.f * e.n), dtype=torch.float64, device="cuda")
         e.sweep(S, history=hist)
         e.sync()
         e.status()
         outs.append(hist.cpu().numpy())
-        n_launch = e.profile()[1]
+        launches.append(e.profile()[1])
+        fchol.append(e.counters()["function_chol"])
+        assert e.counters()["draws"] == C * S * e.f
         e.close()
-        outs.append(n_launch)
-    assert np.array_equal(outs[0], outs[2])
-    assert outs[1] < outs[3]          # fewer launches when batched
+    if name.endswith("_hc"):
+        # helmertConvert contrasts make X^T X diagonal only up to rounding (couplings ~1e-16 are dropped by the batched
+        # path and the shared factorisation uses one representative (X^T X)[f,f]): equal to rounding, not bit for bit
+        assert np.allclose(outs[0], outs[2], rtol=0, atol=1e-9) and np.allclose(outs[1], outs[2], rtol=0, atol=1e-9)
+    else:
+        assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[1], outs[2])
+    assert launches[1] < launches[2]          # fewer launches when batched
+    if name.endswith("_hc"):
+        assert fchol[0] == C * S * 4          # one factorisation per prior group instead of one per function (9)
+    assert fchol[2] == C * S * 9
 
 
 def test_history_pipeline_chunking(eng):
