@@ -795,49 +795,65 @@ __device__ __forceinline__ double engine_quad_total(const EngineSmem& sm, int NT
 }
 
 /* Back substitution  L^T x = w  for NRHS vectors held in shared memory (xs[v*ldx + i], i < NT*32, in place).
- * L: tiles left in W by the engine (KEEPL); sm.rinv holds 1/L_ii.  red: NW*NRHS*32 doubles of shared memory. */
+ * L: tiles left in W by the engine (KEEPL); sm.rinv holds 1/L_ii.
+ * Right-looking by tile rows with ONE barrier per step: warp 0 solves the 32x32 diagonal block of step k (vectors
+ * interleaved for ILP), the barrier publishes x_k, then warp 0 applies the urgent update t_{k-1} -= L(k,k-1)^T x_k
+ * itself and goes straight on to the next diagonal solve while the other warps apply the updates of the tile rows
+ * further up (each tile by one warp: no cross-warp reduction).  `red` is unused (kept for the call signature). */
 template <int NRHS>
 __device__ void back_solve(const double* W, int NT, double* xs, int ldx, const EngineSmem& sm, double* red) {
+  (void)red;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int k = NT - 1; k >= 0; --k) {
+  // t_i -= L(k,i)^T x_k for one tile (k,i): lane = column of the tile = element of t_i
+  auto update = [&](int k, int i) {
+    const double* tile = W + (size_t)plt(k, i) * TILE;
     double acc[NRHS];
 #pragma unroll
     for (int v = 0; v < NRHS; ++v) acc[v] = 0.0;
-    for (int i = k + 1 + warp; i < NT; i += NW) {
-      const double* tile = W + (size_t)plt(i, k) * TILE;
 #pragma unroll 8
-      for (int r = 0; r < 32; ++r) {
-        const double l = tile[r * TB + lane];
+    for (int r = 0; r < 32; ++r) {
+      const double l = tile[r * TB + lane];
 #pragma unroll
-        for (int v = 0; v < NRHS; ++v) acc[v] = fma(l, xs[v * ldx + i * TB + r], acc[v]);
-      }
+      for (int v = 0; v < NRHS; ++v) acc[v] = fma(l, xs[v * ldx + k * TB + r], acc[v]);
     }
 #pragma unroll
-    for (int v = 0; v < NRHS; ++v) red[(warp * NRHS + v) * 32 + lane] = acc[v];
-    __syncthreads();
+    for (int v = 0; v < NRHS; ++v) xs[v * ldx + i * TB + lane] -= acc[v];
+  };
+  __syncthreads();
+  for (int k = NT - 1; k >= 0; --k) {
     if (warp == 0) {
       const double* tile = W + (size_t)plt(k, k) * TILE;
       double a[32];   // a[r] = L[r][lane]
 #pragma unroll
       for (int r = 0; r < 32; ++r) a[r] = tile[r * TB + lane];
+      if (k > 0) prefetch_tile(W + (size_t)plt(k, k - 1) * TILE, lane);
       const double* rinv = sm.rinv + k * TB;
+      double t[NRHS], x[NRHS];
 #pragma unroll
-      for (int v = 0; v < NRHS; ++v) {
-        double t = xs[v * ldx + k * TB + lane];
+      for (int v = 0; v < NRHS; ++v) { t[v] = xs[v * ldx + k * TB + lane]; x[v] = 0.0; }
 #pragma unroll
-        for (int w = 0; w < NW; ++w) t -= red[(w * NRHS + v) * 32 + lane];
-        double x = 0.0;
+      for (int c = 31; c >= 0; --c) {
+        const double rc = rinv[c];
 #pragma unroll
-        for (int c = 31; c >= 0; --c) {
-          const double xc = __shfl_sync(FULLMASK, t, c) * rinv[c];
-          if (lane == c) x = xc;
-          if (lane < c) t = fma(-a[c], xc, t);
+        for (int v = 0; v < NRHS; ++v) {
+          const double xc = __shfl_sync(FULLMASK, t[v], c) * rc;
+          if (lane == c) x[v] = xc;
+          if (lane < c) t[v] = fma(-a[c], xc, t[v]);
         }
-        xs[v * ldx + k * TB + lane] = x;
       }
+#pragma unroll
+      for (int v = 0; v < NRHS; ++v) xs[v * ldx + k * TB + lane] = x[v];
     }
-    __syncthreads();
+    __syncthreads();                       // x_k is published; every update of earlier steps has been applied
+    if (k == 0) break;
+    if (warp == 0) {
+      update(k, k - 1);                    // urgent: the next diagonal solve needs it
+      __syncwarp();
+    } else {
+      for (int i = k - 1 - warp; i >= 0; i -= (NW - 1)) update(k, i);   // tiles (k, k-2), (k, k-3), ... over warps 1..
+    }
   }
+  __syncthreads();
 }
 
 }  // namespace gpf
