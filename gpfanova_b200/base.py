@@ -5,7 +5,8 @@ fused device sweep (gpf_sweep) for `chains` independent chains instead of loopin
 `parameter_cache` / `parameter_history` keep the reference's schema and always describe chain 0; all chains are
 available through `chain_state()` / `chain_history()`.
 
-New, additive keyword arguments: chains=1, seed=None, device=None, store_chains=True.
+New, additive keyword arguments: chains=1, seed=None, device=None, devices=None (list of GPU ordinals: the chains are
+sharded over them, no inter-GPU communication), store_chains=True.
 """
 import logging
 import random as pyrandom
@@ -23,7 +24,7 @@ from .sample import Function, SamplerContainer, Slice
 class Base(SamplerContainer):
     """Subclasses implement _buildDesignMatrix and priorGroups (base.py:7-14)."""
 
-    def __init__(self, x, y, hyperparam_kwargs={}, derivatives=False, chains=1, seed=None, device=None,
+    def __init__(self, x, y, hyperparam_kwargs={}, derivatives=False, chains=1, seed=None, device=None, devices=None,
                  store_chains=True, *args, **kwargs):
         self.x = x
         self.y = y
@@ -35,6 +36,7 @@ class Base(SamplerContainer):
         self.chains = int(chains)
         self.seed = int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else int(seed)
         self.device = device
+        self.devices = None if devices is None else list(devices)     # several GPUs of one box: chains are sharded
         self.store_chains = store_chains
         if derivatives:
             raise NotImplementedError("derivatives=True (FunctionDerivative, sample/function.py:43-66) is not part of "
@@ -195,8 +197,13 @@ class Base(SamplerContainer):
                 self._eng.close()
             w = [a for a, _ in self._slice_wm]
             m = [b for _, b in self._slice_wm]
-            self._eng = _engine.ChainEngine(self.x, self.y, self.design_matrix, self._groups, chains=self.chains,
-                                            seed=self.seed, device=self.device, slice_w=w, slice_m=m)
+            if self.devices is not None and len(self.devices) > 1:
+                self._eng = _engine.EngineGroup(self.x, self.y, self.design_matrix, self._groups, self.chains, self.seed,
+                                                self.devices, slice_w=w, slice_m=m)
+            else:
+                dev = self.device if self.devices is None else self.devices[0]
+                self._eng = _engine.ChainEngine(self.x, self.y, self.design_matrix, self._groups, chains=self.chains,
+                                                seed=self.seed, device=dev, slice_w=w, slice_m=m)
             self._eng_key = key
         return self._eng
 

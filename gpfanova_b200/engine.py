@@ -367,3 +367,104 @@ class ChainEngine(object):
         nl = C.c_ulonglong(0)
         self._ck(self._lib.gpf_get_profile(self._h, ms.ctypes.data_as(C.c_void_p), C.byref(nl)))
         return dict(zip(["total", "kinv", "function", "prior_slice", "y_sigma", "store"], ms.tolist())), int(nl.value)
+
+
+class EngineGroup(object):
+    """The chains of one model spread over several GPUs of one box: one ChainEngine (context + stream) per device,
+    contiguous blocks of chains, no inter-GPU communication on the sampling path; the stored states are gathered on the
+    host.  Same interface as ChainEngine for everything Base uses.  Because the Philox stream is keyed by the GLOBAL
+    chain index, results do not depend on the number of devices."""
+
+    def __init__(self, x, y, X, groups, chains, seed, devices, **kw):
+        devices = list(devices)
+        D = len(devices)
+        assert 1 <= D <= chains
+        base, rem = divmod(int(chains), D)
+        self.counts = [base + (1 if i < rem else 0) for i in range(D)]
+        self.offsets = [int(v) for v in np.concatenate([[0], np.cumsum(self.counts)[:-1]])]
+        self.engines = [ChainEngine(x, y, X, groups, chains=c, seed=seed, device=d, chain_offset=o, **kw)
+                        for c, d, o in zip(self.counts, devices, self.offsets)]
+        e0 = self.engines[0]
+        self.C = int(chains)
+        self.x, self.y, self.X = e0.x, e0.y, e0.X
+        self.n, self.p, self.m, self.f, self.P, self.H = e0.n, e0.p, e0.m, e0.f, e0.P, e0.H
+        self.order, self.sampler_id, self.dev = e0.order, e0.sampler_id, e0.dev
+
+    def _slices(self):
+        return [slice(o, o + c) for o, c in zip(self.offsets, self.counts)]
+
+    @property
+    def sweeps_done(self):
+        return self.engines[0].sweeps_done
+
+    def close(self):
+        for e in self.engines:
+            e.close()
+
+    def sync(self):
+        for e in self.engines:
+            e.sync()
+
+    def set_option(self, option, value):
+        for e in self.engines:
+            e.set_option(option, value)
+
+    def set_state(self, F=None, hyper=None):
+        for e, s in zip(self.engines, self._slices()):
+            Fe = None if F is None else np.broadcast_to(np.asarray(F, dtype=np.float64), (self.C, self.f, self.n))[s]
+            he = None if hyper is None else np.broadcast_to(np.asarray(hyper, dtype=np.float64), (self.C, self.H))[s]
+            e.set_state(F=Fe, hyper=he)
+
+    def get_state(self):
+        parts = [e.get_state() for e in self.engines]
+        return np.concatenate([p[0] for p in parts], axis=0), np.concatenate([p[1] for p in parts], axis=0)
+
+    def status(self, clear=True, raise_on_error=True):
+        st = np.concatenate([e.status(clear=clear, raise_on_error=False) for e in self.engines])
+        if raise_on_error and (st < 0).any():
+            bad = np.nonzero(st < 0)[0]
+            what = ("not pd: non-positive diagonal elements" if (st[bad] == _capi.STATUS_NONPOS_DIAG).any()
+                    else "not positive definite, even with jitter.")
+            raise np.linalg.LinAlgError("%s (chains %s)" % (what, bad[:8].tolist()))
+        return st
+
+    def counters(self, clear=False):
+        out = {}
+        for e in self.engines:
+            for k, v in e.counters(clear=clear).items():
+                out[k] = out.get(k, 0) + v
+        return out
+
+    def sweep_host(self, n_sweeps=1, thin=0, order=None, on_chunk=None, **kw):
+        from concurrent.futures import ThreadPoolExecutor
+
+        def run(i):
+            return self.engines[i].sweep_host(n_sweeps, thin=thin, order=order, on_chunk=on_chunk if i == 0 else None, **kw)
+        with ThreadPoolExecutor(max_workers=len(self.engines)) as ex:       # ctypes calls release the GIL
+            parts = list(ex.map(run, range(len(self.engines))))
+        return np.concatenate(parts, axis=1)
+
+    def sweep(self, n_sweeps=1, thin=0, history=None, order=None, sweep0=None):
+        assert history is None, "device-side history is per engine: use sweep_host() or the engines directly"
+        for e in self.engines:
+            e.sweep(n_sweeps, thin=thin, order=order, sweep0=sweep0)
+        return 0
+
+    # per-sampler entry points: run on every device, report the engine holding chain 0 / concatenated per-chain values
+    def function_step(self, fn, sweep=0, z=None, want=("mu", "LA", "mt", "nt")):
+        outs = []
+        for e, s in zip(self.engines, self._slices()):
+            outs.append(e.function_step(fn, sweep=sweep, z=None if z is None else np.asarray(z)[s], want=want))
+        return outs[0]
+
+    def slice_step(self, h, sweep=0, u=None):
+        return np.concatenate([e.slice_step(h, sweep=sweep, u=None if u is None else np.asarray(u)[s])
+                               for e, s in zip(self.engines, self._slices())])
+
+    def obs_loglik(self, cand):
+        cand = np.broadcast_to(np.asarray(cand, dtype=np.float64), (self.C,))
+        return np.concatenate([e.obs_loglik(cand[s]) for e, s in zip(self.engines, self._slices())])
+
+    def prior_loglik(self, g, which, cand):
+        cand = np.broadcast_to(np.asarray(cand, dtype=np.float64), (self.C,))
+        return np.concatenate([e.prior_loglik(g, which, cand[s]) for e, s in zip(self.engines, self._slices())])

@@ -219,3 +219,21 @@ def test_not_pd_surfaces_as_linalgerror(cuda):
     m.parameter_cache["prior0_sigma"] = 400.0      # sigma = 1e400 = inf -> K is not finite
     with pytest.raises(np.linalg.LinAlgError):
         m.sample(1)
+
+
+@gpu
+def test_chains_sharded_over_devices_match_single_device(cuda):
+    """devices=[0, 1]: contiguous blocks of chains per GPU, Philox keyed by the global chain index -> the same samples as
+    on one device (needs two GPUs; on a one-GPU box the same device is used twice, which exercises the same code)"""
+    c = load_case("twoway_n24")
+    devs = [0, 1] if cuda.cuda.device_count() >= 2 else [0, 0]
+    outs = []
+    for kw in (dict(device=0), dict(devices=devs)):
+        m = build(c, chains=5, seed=12, **kw)
+        install_state(m, c)
+        m.sample(4, thin=2)
+        outs.append((m.chain_history().copy(), m.parameter_history.values.astype(float).copy(), m.chain_state()))
+        assert m.counters()["draws"] == 5 * 4 * m.f
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert np.array_equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][2][0], outs[1][2][0]) and np.array_equal(outs[0][2][1], outs[1][2][1])
