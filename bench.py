@@ -183,10 +183,11 @@ def fp64_peak():
 
 def flops_model(n, f, P, ng_list, counts, schur):
     """algorithmic FP64 flops of what was executed (counted by the kernels), SURVEY.md 8d / DESIGN.md 5:
-    K_inv n^3 (chol + triangular inverse + L^-T L^-1); function draw n^3/3 + 6 n^2 (chol, forward + 2 back solves);
+    K_inv n^3 (chol + triangular inverse + L^-T L^-1) -- uniform grid with even n >= 64: two n/2 inverses through the
+    centrosymmetric split, n^3/4; function draw n^3/3 + 6 n^2 (chol, forward + 2 back solves);
     slice factorisation: dense n^3/3 + |g| n^2, or -- uniform grid, Schur algorithm -- (3 + |g|) n^2."""
     n3 = float(n) ** 3
-    inv = counts["inverses"] * n3
+    inv = counts["inverses"] * (n3 / 4 if (schur and n % 2 == 0 and n >= 64) else n3)
     fchol = counts.get("function_chol", counts["draws"])       # functions with identical conditional precision share one
     draws = fchol * n3 / 3 + counts["draws"] * 6.0 * n * n
     prior_facts = counts["chol"] - counts["inverses"] - fchol - (counts["jitter"] if fchol == counts["draws"] else 0)
@@ -303,7 +304,7 @@ def main():
     schur = bool(np.allclose(np.diff(x[:, 0]), np.diff(x[:, 0])[0], rtol=0, atol=1e-13)) and x.shape[1] == 1
     fm = flops_model(n, f, P, [len(g) for g in groups], counts_prof, schur)
     fm_timed = flops_model(n, f, P, [len(g) for g in groups], counts, schur)
-    kern = {"kinv": ("k_group_kinv (Kernel.K_inv of every prior group: RBF build + jitchol + in-place inverse)", args.steps),
+    kern = {"kinv": ("k_group_kinv (Kernel.K_inv of every prior group: RBF build + jitchol + in-place inverse; centrosymmetric split on uniform grids)", args.steps),
             "function": ("k_function (Function._sample: residual projection, jitchol(A), solves, Philox draw; one launch per sweep for balanced designs)", args.steps),
             "prior_slice": ("k_prior_schur (sigma+lengthscale slice steps: Toeplitz/Schur GP log-likelihood)" if schur else
                             "k_prior (sigma+lengthscale slice steps: dense GP log-likelihood)", P * args.steps)}

@@ -45,6 +45,7 @@ struct gpf_ctx {
   std::vector<Samp> order;
   std::vector<char> kinv_valid;
   bool toeplitz = false;
+  bool centro_ok = false;
   bool indep = false;                 // X^T X diagonal and nothing missing: function draws of a sweep are independent
   int* d_fn_all = nullptr;            // all functions in sampler order / their sampler ids (device)
   unsigned* d_sid_all = nullptr;
@@ -60,7 +61,7 @@ struct gpf_ctx {
   cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_user[4] = {nullptr, nullptr, nullptr, nullptr};   // gpf_record_event / gpf_wait_event
   std::vector<void*> allocs;
-  size_t smem_kinv = 0, smem_fn = 0;
+  size_t smem_kinv = 0, smem_kinv2 = 0, smem_fn = 0;
   std::vector<size_t> smem_prior;
   unsigned long long launches = 0;
   int profile = 0;                     // 0 off, 1 per-kernel + total CUDA-event timing, 2 total only
@@ -141,8 +142,9 @@ int launch_kinv(gpf_ctx* c, int g, int count = 1) {
   Timer t(c, 1);
   CK(c, cudaMemsetAsync(c->dev.sched, 0, sizeof(int), c->stream));
   const int grid = std::min(c->dev.C * count, 2 * c->sms);
-  if (c->toeplitz) k_group_kinv<true><<<grid, NTHR, c->smem_kinv, c->stream>>>(c->dev, g, count);
-  else k_group_kinv<false><<<grid, NTHR, c->smem_kinv, c->stream>>>(c->dev, g, count);
+  if (c->dev.centro) k_group_kinv<2><<<grid, NTHR, c->smem_kinv2, c->stream>>>(c->dev, g, count);
+  else if (c->toeplitz) k_group_kinv<1><<<grid, NTHR, c->smem_kinv, c->stream>>>(c->dev, g, count);
+  else k_group_kinv<0><<<grid, NTHR, c->smem_kinv, c->stream>>>(c->dev, g, count);
   ++c->launches;
   CK(c, cudaGetLastError());
   for (int q = g; q < g + count; ++q) c->kinv_valid[q] = 1;
@@ -367,9 +369,10 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
   // shared-memory budgets
   const size_t xsd = (size_t)d->n * d->p + d->n;
   c->smem_kinv = (engine_smem_doubles(v.NT, 0) + xsd) * sizeof(double);
+  c->smem_kinv2 = (2 * engine_smem_doubles((d->n / 2 + TB - 1) / TB, 0) + xsd) * sizeof(double);   // centrosymmetric split
   c->smem_fn = (engine_smem_doubles(v.NT, 1) + 3 * (size_t)v.NT * TB + NW * 2 * 32) * sizeof(double);
   c->smem_prior.resize(d->P);
-  size_t smax = std::max(c->smem_kinv, c->smem_fn);
+  size_t smax = std::max(std::max(c->smem_kinv, c->smem_kinv2), c->smem_fn);
   for (int g = 0; g < d->P; ++g) {
     const int NE = ((int)c->groups[g].size() + TB - 1) / TB;
     c->smem_prior[g] = (engine_smem_doubles(v.NT, NE) + xsd) * sizeof(double);
@@ -387,8 +390,9 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
   }
   {
     const size_t sp = *std::max_element(c->smem_prior.begin(), c->smem_prior.end());
-    cudaError_t e = allow_smem(k_group_kinv<true>, c->smem_kinv);
-    if (e == cudaSuccess) e = allow_smem(k_group_kinv<false>, c->smem_kinv);
+    cudaError_t e = allow_smem(k_group_kinv<0>, c->smem_kinv);
+    if (e == cudaSuccess) e = allow_smem(k_group_kinv<1>, c->smem_kinv);
+    if (e == cudaSuccess) e = allow_smem(k_group_kinv<2>, c->smem_kinv2);
     if (e == cudaSuccess) e = allow_smem(k_function, c->smem_fn);
     if (e == cudaSuccess) e = allow_smem(k_function_class, c->smem_fn);
     if (e == cudaSuccess) e = allow_smem(k_prior<true>, sp);
@@ -428,6 +432,9 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
       for (int k = 0; k < d->n; ++k) d2[k] = (double)((k * h) * (k * h));
     }
   }
+  // symmetric Toeplitz => centrosymmetric: K_inv from two half-size inverses (n even; small n gains nothing)
+  c->centro_ok = c->toeplitz && d->n % 2 == 0 && d->n >= 64;
+  v.centro = c->centro_ok ? 1 : 0;
   // X^T X, X^T y (observed entries) and the per-time-point "nothing missing" flag for the residual projection
   std::vector<double> G((size_t)d->f * d->f, 0.0), Z((size_t)d->f * d->n, 0.0);
   std::vector<unsigned char> full(d->n, 1);
@@ -752,6 +759,11 @@ int gpf_set_option(gpf_ctx* c, int option, int value) {
   if (option == 0) { c->use_schur = value; return GPF_OK; }
   if (option == 1) { c->batch = value; return GPF_OK; }
   if (option == 2) { c->share = value; return GPF_OK; }
+  if (option == 3) {   // centrosymmetric split of K_inv on uniform grids (on by default where it applies)
+    c->dev.centro = c->centro_ok ? value : 0;   // (debug builds: bit 1 skips the assembly, bit 2 the second half)
+    for (auto& q : c->kinv_valid) q = 0;
+    return GPF_OK;
+  }
   c->err = "gpf_set_option: unknown option";
   return GPF_ERR_ARG;
 }

@@ -18,6 +18,7 @@ enum { CNT_CHOL = 0, CNT_LOGP = 1, CNT_JITTER = 2, CNT_DRAW = 3, CNT_INV = 4, CN
 // device view of one sampler context (passed by value to every kernel)
 struct CtxDev {
   int n, p, m, f, P, C, H, NT, NEmax, chain_offset, maxtries;
+  int centro;                 // uniform grid, n even and >= 64: K_inv through the centrosymmetric split (two n/2 inverses)
   const double* x;            // n x p
   const double* yT;           // m x n (transposed observations, NaN = missing)
   const double* X;            // m x f

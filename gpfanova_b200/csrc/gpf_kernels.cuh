@@ -124,13 +124,15 @@ __global__ void __launch_bounds__(NTHR) k_tiles_to_dense(const double* tiles, si
 // ---------------------------------------------------------------------------------------------------------
 // Kernel.K_inv of prior group g for every chain at the current hyper-parameters
 //   kernel/kernel.pyx:51-64 (K + 1e-9 I, jitchol, L^-T L^-1) with rbf.pyx:16-19 generated on chip at first touch
-//   (TOEP: uniform grid, one exp per lag; else one exp per element).
+//   (MODE 1: uniform grid, one exp per lag; MODE 0: one exp per element; MODE 2: uniform grid with even n -- the
+//   centrosymmetric split, two n/2 inverses in the CTA's workspace assembled into c.Kinv).
 // The inverse is built in place in its destination (c.Kinv), never as a separate L / L^-1.
 // ---------------------------------------------------------------------------------------------------------
-template <bool TOEP>
+template <int MODE>
 __global__ void __launch_bounds__(NTHR, 2) k_group_kinv(CtxDev c, int g_first, int g_count) {
-  EngineSmem sm(smem_base(), c.NT, 0);
-  double* xs = smem_base() + engine_smem_doubles(c.NT, 0);   // TOEP: lag table (n); else scaled inputs (n*p) + xsq (n)
+  EngineSmem sm(smem_base(), (MODE == 2) ? (c.n / 2 + TB - 1) / TB : c.NT, 0);
+  // MODE >= 1: lag table (n); else scaled inputs (n*p) + xsq (n).  MODE 2 keeps two half-size engines in shared memory
+  double* xs = smem_base() + ((MODE == 2) ? 2 * engine_smem_doubles((c.n / 2 + TB - 1) / TB, 0) : engine_smem_doubles(c.NT, 0));
   double* xsq = xs + (size_t)c.n * c.p;
   const size_t tstride = (size_t)plt_tiles(c.NT) * TILE;
   __shared__ int s_chain;
@@ -141,18 +143,36 @@ __global__ void __launch_bounds__(NTHR, 2) k_group_kinv(CtxDev c, int g_first, i
     const double ls = exp10(c.hyper[(size_t)ch * c.H + 2 + 2 * g]);
     double* W = c.Kinv + ((size_t)g * c.C + ch) * tstride;
     __syncthreads();
-    if constexpr (TOEP) toeplitz_table(c.d2, c.n, sigma, ls, xs, sm.red());
+    if constexpr (MODE >= 1) toeplitz_table(c.d2, c.n, sigma, ls, xs, sm.red());
     else rbf_scale_inputs(c.x, c.n, c.p, ls, xs, xsq);
     int tries = 0, code = 0;
     double jitter = 0.0;
+    constexpr bool centro = (MODE == 2);
+    const int h = c.n / 2, NTh = (h + TB - 1) / TB;
+    double* Wh = c.ws + (size_t)blockIdx.x * c.ws_stride;          // centro: the two half-size inverses
+    const size_t hstride = (size_t)plt_tiles(NTh) * TILE;
     for (;;) {
       __syncthreads();
-      for (int t = threadIdx.x; t < c.NT * TB; t += NTHR) sm.dvec[t] = (t < c.n) ? c.offset + jitter : 0.0;
-      __syncthreads();
-      EngineIO io{W, nullptr, RowSrc{nullptr, nullptr, 0, 0, 0}, nullptr, 0};
-      bool ok;
-      if constexpr (TOEP) ok = chol_engine<AUG_IDENT, false>(SrcToeplitz{xs, c.n}, io, c.NT, 0, 0, sm);
-      else ok = chol_engine<AUG_IDENT, false>(SrcRbf{xs, xsq, c.n, c.p, sigma}, io, c.NT, 0, 0, sm);
+      bool ok = true;
+      if constexpr (centro) {
+        // the two halves side by side: warps [0, NW/2) invert B+, warps [NW/2, NW) invert B-, each half a sub-engine
+        // with its own shared memory and barriers (twice the matrices in flight per SM for these latency-bound sizes)
+        constexpr int NWH = NW / 2;
+        const int sub = threadIdx.x / (NWH * 32);
+        const EngineSmem smh(smem_base() + (size_t)sub * engine_smem_doubles(NTh, 0), NTh, 0);
+        for (int t = threadIdx.x - sub * NWH * 32; t < NTh * TB; t += NWH * 32) smh.dvec[t] = (t < h) ? c.offset + jitter : 0.0;
+        __syncthreads();
+        EngineIO io{Wh + sub * hstride, nullptr, RowSrc{nullptr, nullptr, 0, 0, 0}, nullptr, 0};
+        const bool okh = chol_engine<AUG_IDENT, false, SrcCentro, NWH>(SrcCentro{xs, c.n, h, sub ? -1.0 : 1.0}, io, NTh, 0, 0, smh, sub);
+        ok = !__syncthreads_or(okh ? 0 : 1);
+      }
+      if constexpr (!centro) {
+        for (int t = threadIdx.x; t < c.NT * TB; t += NTHR) sm.dvec[t] = (t < c.n) ? c.offset + jitter : 0.0;
+        __syncthreads();
+        EngineIO io{W, nullptr, RowSrc{nullptr, nullptr, 0, 0, 0}, nullptr, 0};
+        if constexpr (MODE == 1) ok = chol_engine<AUG_IDENT, false>(SrcToeplitz{xs, c.n}, io, c.NT, 0, 0, sm);
+        else ok = chol_engine<AUG_IDENT, false>(SrcRbf{xs, xsq, c.n, c.p, sigma}, io, c.NT, 0, 0, sm);
+      }
       if (ok) { code = tries; break; }
       // jitchol ladder (linalg.py:41-54): diag(K + offset I) = sigma + offset everywhere
       const double dm = sigma + c.offset;
@@ -162,6 +182,100 @@ __global__ void __launch_bounds__(NTHR, 2) k_group_kinv(CtxDev c, int g_first, i
       } else jitter *= 10.0;
       ++tries;
       if (tries > c.maxtries || !isfinite(jitter)) { code = GPF_STATUS_NOT_PD; break; }
+    }
+    if constexpr (centro) if (code >= 0 && !(c.centro & 2)) {
+      // K^-1 = 1/2 [[S, D J], [J D, J S J]],  S = M+ + M-,  D = M+ - M-  (M+- = B+-^-1, symmetric, lower tiles valid)
+      __syncthreads();
+      const double* M1 = Wh;
+      const double* M2 = Wh + hstride;
+      const int n = c.n;
+      auto msym = [&](const double* M, int a, int b) {
+        if (a < b) { const int q = a; a = b; b = q; }
+        return M[(size_t)plt(a >> 5, b >> 5) * TILE + (a & 31) * TB + (b & 31)];
+      };
+      if ((n & 63) == 0) {
+        // tile-aligned halves: every output tile is one tile of M+ (+/-) M-, possibly row-flipped (coalesced 16-byte
+        // copies) or flipped and transposed (through the warp's idle panel slot)
+        constexpr int NWH = NW / 2;
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, T = c.NT, Th = T / 2;
+        const int per = (Th < NWH) ? Th : NWH, nwk = 2 * per;           // warps with a panel slot of their own
+        const int wq = (warp / NWH) * per + (warp % NWH);
+        if ((warp % NWH) < per) {
+          const EngineSmem smw(smem_base() + (size_t)(warp / NWH) * engine_smem_doubles(NTh, 0), NTh, 0);
+          double* slot = smw.P + (size_t)(warp % NWH) * TB * PS;
+          for (int t = wq; t < plt_tiles(T); t += nwk) {
+            int bi = 0, bj = t;
+            while (bj > bi) { bj -= bi + 1; ++bi; }
+            double* tile = W + (size_t)plt(bi, bj) * TILE;
+            int ta, tb;
+            double sg = 1.0;
+            bool flip = false, transp = false;
+            if (bi < Th) { ta = bi; tb = bj; }
+            else if (bj < Th) {
+              sg = -1.0; ta = T - 1 - bi; tb = bj; flip = true;
+              if (ta < tb) { const int q = ta; ta = tb; tb = q; transp = true; }   // out[r][c] = D[tb*32 + c][ta*32 + 31 - r]
+            } else { ta = T - 1 - bj; tb = T - 1 - bi; flip = true; transp = true; }  // out[r][c] = S[ta*32+31-c][tb*32+31-r]
+            const double* s1 = M1 + (size_t)plt(ta, tb) * TILE;
+            const double* s2 = M2 + (size_t)plt(ta, tb) * TILE;
+            if (!transp) {
+#pragma unroll
+              for (int q = 0; q < 16; ++q) {
+                const int idx = q * 32 + lane, row = idx >> 4, ch2 = 2 * (idx & 15), srow = flip ? 31 - row : row;
+                const double2 a = *reinterpret_cast<const double2*>(s1 + srow * TB + ch2);
+                const double2 b = *reinterpret_cast<const double2*>(s2 + srow * TB + ch2);
+                __stcs(reinterpret_cast<double2*>(tile + row * TB + ch2), make_double2(0.5 * fma(sg, b.x, a.x), 0.5 * fma(sg, b.y, a.y)));
+              }
+            } else {
+              __syncwarp();
+#pragma unroll
+              for (int q = 0; q < 16; ++q) {
+                const int idx = q * 32 + lane, row = idx >> 4, ch2 = 2 * (idx & 15);
+                const double2 a = *reinterpret_cast<const double2*>(s1 + row * TB + ch2);
+                const double2 b = *reinterpret_cast<const double2*>(s2 + row * TB + ch2);
+                *reinterpret_cast<double2*>(slot + row * PS + ch2) = make_double2(0.5 * fma(sg, b.x, a.x), 0.5 * fma(sg, b.y, a.y));
+              }
+              __syncwarp();
+              // lower-left block: source element (c, 31 - r); lower-right block: source element (31 - c, 31 - r)
+              const int srow = (bj < Th) ? lane : 31 - lane;
+#pragma unroll 8
+              for (int r = 0; r < 32; ++r) __stcs(tile + r * TB + lane, slot[srow * PS + 31 - r]);
+            }
+          }
+        }
+      } else {
+      // 8 independent element pairs in flight per thread (the loads come from L2: latency, not bandwidth)
+      constexpr int U = 8;
+      for (int bi = 0; bi < c.NT; ++bi)
+        for (int bj = 0; bj <= bi; ++bj) {
+          double* tile = W + (size_t)plt(bi, bj) * TILE;
+          for (int e0 = threadIdx.x; e0 < TILE; e0 += NTHR * U) {
+            double m1[U], m2[U], sg[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const int e = e0 + u * NTHR;
+              int R = bi * TB + (e >> 5), Cc = bj * TB + (e & 31);
+              m1[u] = 0.0; m2[u] = 0.0; sg[u] = 0.0;
+              if (e < TILE) {
+                if (R >= n || Cc >= n) { m1[u] = (R == Cc) ? 2.0 : 0.0; }
+                else {
+                  if (R < Cc) { const int q = R; R = Cc; Cc = q; }
+                  int a, b;
+                  if (R < h) { a = R; b = Cc; sg[u] = 1.0; }
+                  else if (Cc < h) { a = n - 1 - R; b = Cc; sg[u] = -1.0; }
+                  else { a = n - 1 - R; b = n - 1 - Cc; sg[u] = 1.0; }
+                  m1[u] = msym(M1, a, b);
+                  m2[u] = msym(M2, a, b);
+                }
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const int e = e0 + u * NTHR;
+              if (e < TILE) tile[e] = 0.5 * fma(sg[u], m2[u], m1[u]);
+            }
+          }
+        }
+      }
     }
     if (threadIdx.x == 0) {
       status_merge(c.status + ch, code);

@@ -417,8 +417,10 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 
 // shared-memory footprint (doubles) of the engine for NT matrix tile rows + NE extra panel slots
 __host__ __device__ inline size_t engine_smem_doubles(int NT, int NE) {
-  return (size_t)TILE /*DT*/ + 256 /*Linv*/ + (size_t)(NT + NE) * TB * PS + (size_t)NT * TB /*rinv*/ + (size_t)NT * TB /*dvec*/ +
-         (size_t)TB /*piv*/ + (size_t)NT * TB /*pivall*/ + (size_t)(NE > 0 ? NE : 1) * NT /*quadpart*/ + 16;
+  const size_t d = (size_t)TILE /*DT*/ + 256 /*Linv*/ + (size_t)(NT + NE) * TB * PS + (size_t)NT * TB /*rinv*/ +
+                   (size_t)NT * TB /*dvec*/ + (size_t)TB /*piv*/ + (size_t)NT * TB /*pivall*/ +
+                   (size_t)(NE > 0 ? NE : 1) * NT /*quadpart*/ + 16;
+  return (d + 3) & ~(size_t)3;   // 32-byte granularity: two engines may sit back to back in one CTA
 }
 
 struct EngineSmem {
@@ -468,14 +470,31 @@ __device__ __forceinline__ void slot_to_tile(const double* slot, double* __restr
 // tiles in memory, packed lower-triangular by tile
 struct SrcTiles {
   const double* A0;
+  // The source matrix is read exactly once: streaming loads (evict-first), so that it does not push the CTAs' workspaces
+  // -- which are re-read many times per factorisation -- out of L2.
   __device__ __forceinline__ void rows(double (&a)[32], int bi, int bj, int lane) const {
-    rows_load(a, A0 + (size_t)plt(bi, bj) * TILE, lane);
+    const double2* p = reinterpret_cast<const double2*>(A0 + (size_t)plt(bi, bj) * TILE + lane * TB);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) { const double2 v = __ldcs(p + c); a[2 * c] = v.x; a[2 * c + 1] = v.y; }
   }
   __device__ __forceinline__ void cfrag(CFrag& f, int bi, int bj, int g, int tig) const {
-    cfrag_load(f, A0 + (size_t)plt(bi, bj) * TILE, g, tig, 4);
+    const double* tile = A0 + (size_t)plt(bi, bj) * TILE;
+#pragma unroll
+    for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+      for (int tj = 0; tj < 4; ++tj) {
+        const double2 v = __ldcs(reinterpret_cast<const double2*>(tile + (8 * ti + g) * TB + 8 * tj + 2 * tig));
+        f.c[ti][tj][0] = v.x; f.c[ti][tj][1] = v.y;
+      }
   }
   __device__ __forceinline__ void fill_slot(double* slot, int bi, int bj, int lane) const {
-    tile_to_slot(A0 + (size_t)plt(bi, bj) * TILE, slot, lane);
+    const double* tile = A0 + (size_t)plt(bi, bj) * TILE;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int idx = q * 32 + lane;
+      const double2 v = __ldcs(reinterpret_cast<const double2*>(tile + 2 * idx));
+      *reinterpret_cast<double2*>(slot + (idx >> 4) * PS + 2 * (idx & 15)) = v;
+    }
   }
 };
 // stationary kernel on a uniform grid: K[i][j] = tab[|i-j|] (tab in shared memory, sigma folded in); identity padding
@@ -486,6 +505,38 @@ struct SrcToeplitz {
     if (R >= n || Cc >= n) return (R == Cc) ? 1.0 : 0.0;
     const int d = R - Cc;
     return tab[d < 0 ? -d : d];
+  }
+  __device__ __forceinline__ void rows(double (&a)[32], int bi, int bj, int lane) const {
+#pragma unroll
+    for (int c = 0; c < 32; ++c) a[c] = at(bi * TB + lane, bj * TB + c);
+  }
+  __device__ __forceinline__ void cfrag(CFrag& f, int bi, int bj, int g, int tig) const {
+#pragma unroll
+    for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+      for (int tj = 0; tj < 4; ++tj) {
+        f.c[ti][tj][0] = at(bi * TB + 8 * ti + g, bj * TB + 8 * tj + 2 * tig);
+        f.c[ti][tj][1] = at(bi * TB + 8 * ti + g, bj * TB + 8 * tj + 2 * tig + 1);
+      }
+  }
+  __device__ __forceinline__ void fill_slot(double* slot, int bi, int bj, int lane) const {
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) slot[r * PS + lane] = at(bi * TB + r, bj * TB + lane);
+  }
+};
+
+// Symmetric Toeplitz matrices are centrosymmetric: with n = 2h and J the h x h exchange matrix,
+//   K = Q^T diag(B+, B-) Q,   B+- = K11 +- K12 J,   Q = [[I, J], [I, -J]] / sqrt(2)   (orthogonal),
+// so K^-1 follows from the inverses of two h x h matrices (a quarter of the flops).  This source presents
+//   B+-[i][j] = tab[|i-j|] +- tab[n-1-i-j],  i, j < h;  identity padding.
+struct SrcCentro {
+  const double* tab;
+  int n, h;
+  double sign;
+  __device__ __forceinline__ double at(int R, int Cc) const {
+    if (R >= h || Cc >= h) return (R == Cc) ? 1.0 : 0.0;
+    const int d = R - Cc;
+    return fma(sign, tab[n - 1 - R - Cc], tab[d < 0 ? -d : d]);
   }
   __device__ __forceinline__ void rows(double (&a)[32], int bi, int bj, int lane) const {
 #pragma unroll
@@ -540,8 +591,10 @@ __device__ __forceinline__ void store_diag_tile(const double* DT, double* tile, 
 
 // named barriers (ids 1, 2; id 0 is __syncthreads): split arrive / wait so that the look-ahead warp and the others do not
 // wait for each other's work that they do not depend on
-__device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(NTHR) : "memory"); }
-__device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NTHR) : "memory"); }
+template <int NTE = NTHR>
+__device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(NTE) : "memory"); }
+template <int NTE = NTHR>
+__device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NTE) : "memory"); }
 
 // prefetch one 8 KB tile into L1/L2 (64 lines of 128 B: two per lane)
 __device__ __forceinline__ void prefetch_tile(const double* tile, int lane) {
@@ -559,22 +612,30 @@ __device__ __forceinline__ void cfrag_to_DT(const CFrag& f, double* DT, int g, i
       DT[(8 * tj + 2 * tig + 1) * TB + 8 * ti + g] = f.c[ti][tj][1];
     }
 }
-/* The engine.  All NTHR threads of the CTA call it with identical arguments.
+/* The engine.  All NTHR threads of the CTA call it with identical arguments -- or, with NWE < NW, the NWE warps of
+ * sub-engine `sub` (threads sub*NWE*32 ...), several independent sub-engines side by side in one CTA, each with its own
+ * EngineSmem and its own hardware barriers 1+3*sub .. 3+3*sub.
  *   AUG_RHS  : NE extra tile rows; the last extra tile row uses only nti_last 8-row strips.
  * Returns false if a pivot failed (matrix not PD); logdet (= 2 sum log L_ii) is in sm.scal[0] on success,
  * sm.quad[e*NT+k] hold the sums of squares of the finished augmented rows.
  */
-template <int AUG, bool KEEPL, class Src>
+template <int AUG, bool KEEPL, class Src, int NWE = NW>
 __device__ GPF_ENGINE_INLINE bool chol_engine(const Src& src, const EngineIO& io, int NT, int NE, int nti_last,
-                                            const EngineSmem& sm) {
+                                            const EngineSmem& sm, int sub = 0) {
   constexpr bool FAST_TRSM = (AUG == AUG_RHS) && !KEEPL;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
+  constexpr int NTE = NWE * 32;
+  const int tid = threadIdx.x - sub * NTE, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
+  const int bar0 = (NWE == NW) ? 0 : 1 + 3 * sub;     // bar0: all threads of the (sub-)engine; bar0+1, bar0+2: split barriers
+  auto eng_sync = [&]() {
+    if constexpr (NWE == NW) __syncthreads();
+    else bar_sync<NTE>(bar0);
+  };
   double* W = io.W;
   double* Wx = io.Wx;
   int* tilectr = reinterpret_cast<int*>(sm.scal + 10);
   GPF_STAMP_INIT
   if (tid == 0) { sm.scal[0] = 0.0; sm.scal[1] = 0.0; }
-  __syncthreads();
+  eng_sync();
   // ---------------- prologue: factor diagonal tile 0 (warp 0) ----------------
   if (warp == 0) {
     double a[32];
@@ -586,7 +647,7 @@ __device__ GPF_ENGINE_INLINE bool chol_engine(const Src& src, const EngineIO& io
   }
   GPF_STAMP(0);
   for (int k = 0; k < NT; ++k) {
-    __syncthreads();                      // diagonal factor k (DT, rinv[k]) and the step-(k-1) updates are complete
+    eng_sync();                      // diagonal factor k (DT, rinv[k]) and the step-(k-1) updates are complete
     GPF_STAMP(1);
 #ifndef GPF_DBG_NOFAIL
     if (sm.scal[1] != 0.0) return false;
@@ -595,8 +656,8 @@ __device__ GPF_ENGINE_INLINE bool chol_engine(const Src& src, const EngineIO& io
     const int nreg = NT - 1 - k;
     const int nx = (AUG == AUG_RHS) ? NE : ((AUG == AUG_IDENT) ? (k + 1) : 0);
     if (tid == 0) *tilectr = (nreg > 0) ? 1 : 0;   // trailing tile 0 = next diagonal tile (look-ahead)
-    if (KEEPL && warp == NW - 1) store_diag_tile(sm.DT, W + (size_t)plt(k, k) * TILE, lane);
-    for (int t = warp; t < nreg + nx; t += NW) {
+    if (KEEPL && warp == NWE - 1) store_diag_tile(sm.DT, W + (size_t)plt(k, k) * TILE, lane);
+    for (int t = warp; t < nreg + nx; t += NWE) {
       const int iown = k + 1 + t;
       int slot;
       if (t < nreg) {
@@ -674,7 +735,7 @@ __device__ GPF_ENGINE_INLINE bool chol_engine(const Src& src, const EngineIO& io
     const int T3 = (AUG == AUG_IDENT) ? (k + 1) * (k + 2) / 2 : 0;
     if (nreg > 0) {
       if (warp == 0) {
-        bar_arrive(1);
+        bar_arrive<NTE>(bar0 + 1);
         const int i = k + 1;
         CFrag f;
         if (k == 0) {
@@ -683,17 +744,17 @@ __device__ GPF_ENGINE_INLINE bool chol_engine(const Src& src, const EngineIO& io
         } else cfrag_load(f, W + (size_t)plt(i, i) * TILE, g, tig, 4);
         tile_mma<true>(f, sm.P + (size_t)i * TB * PS, sm.P + (size_t)i * TB * PS, g, tig, 4);
         GPF_STAMP(4);
-        bar_sync(2);
+        bar_sync<NTE>(bar0 + 2);
         cfrag_to_DT(f, sm.DT, g, tig);
 #ifndef GPF_DBG_NOLOOK
         diag_factor<FAST_TRSM, KEEPL>(i, lane, W, sm);
 #endif
         GPF_STAMP(7);
       } else {
-        bar_arrive(2);
-        bar_sync(1);
+        bar_arrive<NTE>(bar0 + 2);
+        bar_sync<NTE>(bar0 + 1);
       }
-    } else __syncthreads();
+    } else eng_sync();
     GPF_STAMP(3);
     // dynamic hand-out of the tiles; the ticket for the next tile is drawn before working on the current one so
     // that its accumulator tile can be prefetched under the tensor work
@@ -773,16 +834,24 @@ __device__ GPF_ENGINE_INLINE bool chol_engine(const Src& src, const EngineIO& io
     }
     GPF_STAMP(5);
   }
-  __syncthreads();
+  eng_sync();
   GPF_STAMP(1);
   GPF_STAMP_FLUSH
   if (sm.scal[1] != 0.0) return false;
-  {
+  if constexpr (NWE == NW) {
     double lg = 0.0;
     for (int t = tid; t < NT * TB; t += NTHR) lg += log(sm.pivall[t]);
     lg = block_sum(lg, sm.red());
     if (tid == 0) sm.scal[0] = lg;
     __syncthreads();
+  } else {
+    if (warp == 0) {
+      double lg = 0.0;
+      for (int t = lane; t < NT * TB; t += 32) lg += log(sm.pivall[t]);
+      lg = warp_sum(lg);
+      if (lane == 0) sm.scal[0] = lg;
+    }
+    eng_sync();
   }
   return true;
 }

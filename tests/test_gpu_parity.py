@@ -418,6 +418,46 @@ def test_full_size_identities(eng):
     e.close()
 
 
+@pytest.mark.parametrize("n", [64, 66, 100, 130, 192, 256])
+def test_centrosymmetric_kinv_matches_direct_inverse(eng, n):
+    """uniform grid, even n >= 64: K + 1e-9 I is symmetric Toeplitz => centrosymmetric, and k_group_kinv assembles K_inv
+    from the inverses of K11 +- K12 J (option 3).  Same accuracy class as the direct n x n inverse of kernel.pyx:51-64:
+    both within the conditioning-limited tolerance of the oracle, same residual bound, and the conditional mean that is
+    built on it moves by no more than that tolerance."""
+    rng = np.random.default_rng(n)
+    x = np.linspace(-1, 1, n)[:, None]
+    C = 5
+    y = rng.normal(size=(n, 6))
+    X = np.ones((6, 1))
+    e = eng.ChainEngine(x, y, X, [[0]], chains=C, seed=3)
+    hyper = np.stack([np.full(C, -1.0), rng.uniform(-1, 1, C), rng.uniform(-0.9, 0.3, C)], axis=1)
+    z = rng.standard_normal((C, n))
+    res = {}
+    for opt in (0, 1):
+        e.set_option(3, opt)
+        e.set_state(F=np.zeros((C, 1, n)), hyper=hyper)
+        Kinv = e.group_kinv(0).cpu().numpy().copy()
+        mu = e.function_step(0, z=z)["mu"].cpu().numpy().copy()
+        e.status()
+        res[opt] = (Kinv, mu)
+    for ch in range(C):
+        K = orc.rbf_K(x, 10.0 ** hyper[ch, 1], 10.0 ** hyper[ch, 2]) + 1e-9 * np.eye(n)
+        ref = orc.K_inv(K - 1e-9 * np.eye(n))[0]
+        cond = np.linalg.cond(K)
+        for opt in (0, 1):
+            Kinv = res[opt][0][ch]
+            assert relerr(Kinv, ref) < cond_tol(cond, n), (opt, ch, relerr(Kinv, ref), cond)
+            assert np.max(np.abs(K @ Kinv - np.eye(n))) <= max(1e-12, 32 * n * EPS * cond), (opt, ch)
+            assert np.array_equal(Kinv, Kinv.T) or relerr(Kinv, Kinv.T) < 1e-15
+        # the split respects the structure exactly: K_inv is persymmetric (J K_inv J = K_inv)
+        Kc = res[1][0][ch]
+        assert relerr(Kc[::-1, ::-1], Kc) < 1e-15
+        st = orc.function_conditional(np.nansum(y, 1), np.full(n, 6.0), hyper[ch, 0], res[0][0][ch])
+        tol = cond_tol(np.linalg.cond(st["A"]), n, floor=1e-9)
+        assert relerr(res[1][1][ch], res[0][1][ch]) < tol, (ch, relerr(res[1][1][ch], res[0][1][ch]), tol)
+    e.close()
+
+
 def test_full_size_sweep_statistics(eng):
     """many chains at n = 256: the sampler must recover the generating functions (posterior mean close to truth,
     y_sigma near its true value) -- a size-independent sanity property of the whole path."""

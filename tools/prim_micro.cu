@@ -62,6 +62,31 @@ __global__ void __launch_bounds__(NTHR, 2) k_prim(const double* A, double* G, do
           for (int q = 0; q < 3 * 64; ++q) s2 += slot[warp][(g * PS + tig + 4 * (q & 7) + 8 * PS * ((q >> 3) & 3))];
           acc += s2;
         }
+      } else if (what == 11) {  // coalesced tile load: global (L2) -> slot
+        tile_to_slot(Gw + (size_t)(r & 3) * TILE, slot[warp], lane);
+        __syncwarp();
+        acc += slot[warp][lane * PS + (r & 31)];
+      } else if (what == 12) {  // coalesced tile store: slot -> global
+        slot_to_tile(slot[warp], Gw + (size_t)(r & 3) * TILE, lane);
+      } else if (what == 13) {  // accumulator fragment load + store
+        CFrag f;
+        cfrag_load(f, Gw + (size_t)(r & 3) * TILE, g, tig, 4);
+        f.c[0][0][0] += 1.0;
+        cfrag_store(f, Gw + (size_t)((r + 1) & 3) * TILE, g, tig, 4);
+      } else if (what == 14) {  // tile load from a tile just written by this warp
+        slot_to_tile(slot[warp], Gw + (size_t)(r & 3) * TILE, lane);
+        __syncwarp();
+        tile_to_slot(Gw + (size_t)(r & 3) * TILE, slot[warp], lane);
+        __syncwarp();
+        acc += slot[warp][lane * PS + (r & 31)];
+      } else if (what >= 15 && what <= 18) {  // global stores followed by a CTA barrier and a shared-memory load
+        CFrag f;
+        cfrag_zero(f);
+        f.c[0][0][0] = acc;
+        if (what != 16) cfrag_store(f, Gw + (size_t)(r & 3) * TILE, g, tig, 4);
+        if (what == 18) __threadfence_block();
+        if (what != 17) asm volatile("bar.sync 1, %0;" ::"r"(nw * 32) : "memory");
+        acc += slot[warp][lane * PS + (r & 31)];
       } else if (what == 6) {   // inv8
         inv8_blocks(DT[warp], rinv[warp], Linv[warp], lane);
         __syncwarp();
@@ -82,11 +107,11 @@ int main() {
   long long hc[296];
   const int SMB = (8 * TILE + 8 * TB * PS + 512 + 8 * 256) * 8;
   cudaFuncSetAttribute(k_prim, cudaFuncAttributeMaxDynamicSharedMemorySize, SMB);
-  const char* nm[11] = {"potrf_tile", "trsm_slot", "trsm_hybrid", "trsm_dmma", "phase2 tile", "phase3 tile", "inv8_blocks", "-", "potrf|bg mma", "potrf|bg dmma", "potrf|bg lds"};
-  for (int what = 0; what < 11; ++what) {
+  const char* nm[19] = {"potrf_tile", "trsm_slot", "trsm_hybrid", "trsm_dmma", "phase2 tile", "phase3 tile", "inv8_blocks", "-", "potrf|bg mma", "potrf|bg dmma", "potrf|bg lds", "tile->slot", "slot->tile", "cfrag ld+st", "st then ld", "st;bar;lds", "bar;lds", "st;lds", "st;fence;bar;lds"};
+  for (int what = 0; what < 19; ++what) {
     if (what == 7) continue;
     printf("%-12s", nm[what]);
-    for (int nw : {1, 4, 8}) {
+    for (int nw : {1, 4, NW}) {
       k_prim<<<148, NTHR, SMB>>>(dA, dG, dout, dc, 20, nw, what); cudaMemcpy(hc, dc, 8 * 148, cudaMemcpyDeviceToHost);
       printf("  %dw: %6lld", nw, hc[0]);
     }
