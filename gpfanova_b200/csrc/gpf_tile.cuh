@@ -419,7 +419,7 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 __host__ __device__ inline size_t engine_smem_doubles(int NT, int NE) {
   const size_t d = (size_t)TILE /*DT*/ + 256 /*Linv*/ + (size_t)(NT + NE) * TB * PS + (size_t)NT * TB /*rinv*/ +
                    (size_t)NT * TB /*dvec*/ + (size_t)TB /*piv*/ + (size_t)NT * TB /*pivall*/ +
-                   (size_t)(NE > 0 ? NE : 1) * NT /*quadpart*/ + 16;
+                   (size_t)(NE > 0 ? NE : 1) * NT /*quadpart*/ + 16 + (size_t)(NT + NE + 2) / 2 /*slot flags*/;
   return (d + 3) & ~(size_t)3;   // 32-byte granularity: two engines may sit back to back in one CTA
 }
 
@@ -433,6 +433,7 @@ struct EngineSmem {
   double* pivall; // NT*32: every pivot of the factorisation (log-determinant is summed once at the end)
   double* quad;   // NE*NT partial sums of squares of finished augmented rows (deterministic reduction)
   double* scal;   // [0] logdet, [1] fail flag (as double), [2..9] block_sum scratch, [10] tile counter
+  int* ready;     // NT+NE: ready[slot] = k+1 once the panel slot holds its solved tile of step k
   __device__ EngineSmem(double* base, int NT, int NE) {
     DT = base;
     Linv = DT + TILE;
@@ -443,6 +444,7 @@ struct EngineSmem {
     pivall = piv + TB;
     quad = pivall + NT * TB;
     scal = quad + (size_t)(NE > 0 ? NE : 1) * NT;
+    ready = reinterpret_cast<int*>(scal + 16);
   }
   __device__ double* red() const { return scal + 2; }
 };
@@ -596,6 +598,19 @@ __device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0
 template <int NTE = NTHR>
 __device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NTE) : "memory"); }
 
+// panel-slot hand-off inside a CTA: the solving warp publishes, consumers spin (all warps of a CTA are resident)
+__device__ __forceinline__ void slot_publish(int* flag, int v, int lane) {
+  __syncwarp();
+  if (lane == 0) asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(flag)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void slot_wait(const int* flag, int v) {
+  int cur;
+  do {
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(cur) : "r"(smem_u32(flag)) : "memory");
+  } while (cur < v);
+  __syncwarp();
+}
+
 // prefetch one 8 KB tile into L1/L2 (64 lines of 128 B: two per lane)
 __device__ __forceinline__ void prefetch_tile(const double* tile, int lane) {
   asm volatile("prefetch.global.L1 [%0];" ::"l"(tile + lane * 16));
@@ -632,9 +647,10 @@ __device__ GPF_ENGINE_INLINE bool chol_engine(const Src& src, const EngineIO& io
   };
   double* W = io.W;
   double* Wx = io.Wx;
-  int* tilectr = reinterpret_cast<int*>(sm.scal + 10);
+  int* tilectr2 = reinterpret_cast<int*>(sm.scal + 10);   // two ticket counters, alternating by step parity
   GPF_STAMP_INIT
-  if (tid == 0) { sm.scal[0] = 0.0; sm.scal[1] = 0.0; }
+  if (tid == 0) { sm.scal[0] = 0.0; sm.scal[1] = 0.0; tilectr2[0] = (NT > 1) ? 1 : 0; }
+  if (tid < NT + NE) sm.ready[tid] = 0;
   eng_sync();
   // ---------------- prologue: factor diagonal tile 0 (warp 0) ----------------
   if (warp == 0) {
@@ -655,7 +671,10 @@ __device__ GPF_ENGINE_INLINE bool chol_engine(const Src& src, const EngineIO& io
     // ---------------- phase 2: panel solves  X <- X L_kk^-T, in place in the panel slots ----------------
     const int nreg = NT - 1 - k;
     const int nx = (AUG == AUG_RHS) ? NE : ((AUG == AUG_IDENT) ? (k + 1) : 0);
-    if (tid == 0) *tilectr = (nreg > 0) ? 1 : 0;   // trailing tile 0 = next diagonal tile (look-ahead)
+    // trailing tile 0 = next diagonal tile (look-ahead).  The counter of the NEXT step is initialised here: a warp
+    // without a panel tile goes straight to this step's tickets, so this step's counter must be ready at the barrier.
+    int* tilectr = tilectr2 + (k & 1);
+    if (tid == 0) tilectr2[(k + 1) & 1] = (NT - 2 - k > 0) ? 1 : 0;
     if (KEEPL && warp == NWE - 1) store_diag_tile(sm.DT, W + (size_t)plt(k, k) * TILE, lane);
     for (int t = warp; t < nreg + nx; t += NWE) {
       const int iown = k + 1 + t;
@@ -701,6 +720,7 @@ __device__ GPF_ENGINE_INLINE bool chol_engine(const Src& src, const EngineIO& io
       if (FAST_TRSM) trsm_dmma(slotp, sm.DT, sm.Linv, g, tig);
       else trsm_hybrid(slotp, sm.DT, sm.rinv + k * TB, lane);
 #endif
+      slot_publish(sm.ready + slot, k + 1, lane);     // consumers of this slot need not wait for the whole panel
       if (t < nreg) {
         if (KEEPL) slot_to_tile(slotp, W + (size_t)plt(k + 1 + t, k) * TILE, lane);
 
@@ -726,16 +746,16 @@ __device__ GPF_ENGINE_INLINE bool chol_engine(const Src& src, const EngineIO& io
     GPF_STAMP(2);
     // ---------------- phase 3: trailing updates (DMMA), with look-ahead on the next diagonal tile ----------------
     // Warp 0 updates tile (k+1,k+1) -- which only needs the panel slot it has just solved itself -- and factors it at
-    // once, so the serial 32-column potrf of step k+1 runs under the other warps' tensor work.  Two named barriers
-    // keep the two sides from waiting on work they do not depend on: barrier 1 = "all panel slots are ready" (warp 0
-    // only arrives), barrier 2 = "nobody reads the diagonal factor of step k any more" (the others only arrive; warp 0
-    // waits on it before overwriting DT).  The remaining tiles are handed out dynamically; warp 0 joins when done.
+    // once, so the serial 32-column potrf of step k+1 runs under the other warps' tensor work.  Neither side waits
+    // for work it does not depend on: every panel slot carries a ready flag (a consumer waits for exactly the two slots
+    // of its tile, not for the whole panel), and one named barrier says "nobody reads the diagonal factor of step k any
+    // more" (the others only arrive; warp 0 waits on it before overwriting DT).  The remaining tiles are handed out
+    // dynamically; warp 0 joins when done.
     const int T1 = nreg * (nreg + 1) / 2;
     const int T2 = nx * nreg;
     const int T3 = (AUG == AUG_IDENT) ? (k + 1) * (k + 2) / 2 : 0;
     if (nreg > 0) {
       if (warp == 0) {
-        bar_arrive<NTE>(bar0 + 1);
         const int i = k + 1;
         CFrag f;
         if (k == 0) {
@@ -752,7 +772,6 @@ __device__ GPF_ENGINE_INLINE bool chol_engine(const Src& src, const EngineIO& io
         GPF_STAMP(7);
       } else {
         bar_arrive<NTE>(bar0 + 2);
-        bar_sync<NTE>(bar0 + 1);
       }
     } else eng_sync();
     GPF_STAMP(3);
@@ -801,6 +820,8 @@ __device__ GPF_ENGINE_INLINE bool chol_engine(const Src& src, const EngineIO& io
           src.cfrag(f, i, j, g, tig);
           if (i == j) cfrag_add_diag(f, sm.dvec + i * TB, g, tig);
         } else cfrag_load(f, W + (size_t)plt(i, j) * TILE, g, tig, 4);
+        slot_wait(sm.ready + i, k + 1);
+        slot_wait(sm.ready + j, k + 1);
         tile_mma<true>(f, sm.P + (size_t)i * TB * PS, sm.P + (size_t)j * TB * PS, g, tig, 4);
         cfrag_store(f, W + (size_t)plt(i, j) * TILE, g, tig, 4);
       } else if (t < T1 + T2) {
@@ -811,11 +832,15 @@ __device__ GPF_ENGINE_INLINE bool chol_engine(const Src& src, const EngineIO& io
           const int nti = (e == NE - 1) ? nti_last : 4;
           if (k == 0) cfrag_from_rows(f, io.rows, e * TB, j * TB, g, tig, nti);
           else cfrag_load(f, wt, g, tig, nti);
+          slot_wait(sm.ready + NT + e, k + 1);
+          slot_wait(sm.ready + j, k + 1);
           tile_mma<true>(f, sm.P + (size_t)(NT + e) * TB * PS, sm.P + (size_t)j * TB * PS, g, tig, nti);
           cfrag_store(f, wt, g, tig, nti);
         } else {
           if (k == e) cfrag_zero(f);
           else cfrag_load(f, wt, g, tig, 4);
+          slot_wait(sm.ready + e, k + 1);
+          slot_wait(sm.ready + j, k + 1);
           tile_mma<true>(f, sm.P + (size_t)e * TB * PS, sm.P + (size_t)j * TB * PS, g, tig, 4);
           cfrag_store(f, wt, g, tig, 4);
         }
@@ -827,6 +852,8 @@ __device__ GPF_ENGINE_INLINE bool chol_engine(const Src& src, const EngineIO& io
         double* kt = W + (size_t)plt(aa, bb) * TILE;
         if (k == aa) cfrag_zero(f);
         else cfrag_load(f, kt, g, tig, 4);
+        slot_wait(sm.ready + aa, k + 1);
+        slot_wait(sm.ready + bb, k + 1);
         tile_mma<false>(f, sm.P + (size_t)aa * TB * PS, sm.P + (size_t)bb * TB * PS, g, tig, 4);
         cfrag_store(f, kt, g, tig, 4);
       }
