@@ -697,9 +697,10 @@ int gpf_sweep(gpf_ctx* c, int n_sweeps, int thin, unsigned sweep0, const int* h_
       //   y_sigma | K_inv of all groups | all functions | slices per group   (same Philox counters, same inputs)
       int rc = launch_slice(c, 0, 1, nullptr, nullptr, 0u, sweep, nullptr, 0, nullptr);
       if (!rc) rc = launch_all_functions(c, sweep);
-      // the groups' slice kernels are independent of each other: run them concurrently on auxiliary streams when the
-      // chain count alone does not fill the GPU (and per-kernel timing is off -- the timers sit on the main stream)
-      bool conc = c->profile != 1 && c->dev.C < 8 * c->sms;
+      // the groups' slice kernels are independent of each other: run them concurrently on auxiliary streams (a small
+      // chain count does not fill the GPU alone; a large one leaves a tail of long slice steps that the next group's
+      // CTAs fill) -- unless per-kernel timing is on: the timers sit on the main stream
+      bool conc = c->profile != 1;
       for (int g = 0; g < c->dev.P; ++g) conc = conc && uses_schur(c, g);   // the dense slice kernel owns the per-CTA workspace
       if (conc && !rc) CK(c, cudaEventRecord(c->ev_fork, c->stream));
       int used = 0;
