@@ -318,7 +318,13 @@ def main():
                                    "launches_per_step": kern[k][1] / args.steps} for k in kern},
                 "whole_step": {"achieved": fm_timed["total"] / (dev_ms * 1e-3) / 1e12,
                                "frac": fm_timed["total"] / (dev_ms * 1e-3) / 1e12 / peak,
-                               "note": "algorithmic flops of the executed algorithm (Schur slices are O(n^2))"},
+                               "note": "algorithmic flops of the executed algorithm (Schur slices are O(n^2), "
+                                       "centrosymmetric K_inv is n^3/4)",
+                               # SURVEY 8(d)'s work model of the reference's dense algorithm for the same sweeps:
+                               # P n^3 + f (n^3/3 + 6 n^2) + (n^3/3) * (slice factorisations), per chain and sweep
+                               "reference_algorithm_tflops": (
+                                   (counts["inverses"] * float(n) ** 3 + counts["draws"] * (float(n) ** 3 / 3 + 6.0 * n * n) +
+                                    fm_timed["prior_factorisations"] * float(n) ** 3 / 3) / (dev_ms * 1e-3) / 1e12)},
                 "counted": {"factorisations_per_sweep_per_chain": counts["chol"] / (C * args.steps),
                             "logp_evals_per_slice_step": counts["logp"] / max(1, counts["slice_steps"]),
                             "jitter_retries": counts["jitter"]}}
