@@ -46,6 +46,7 @@ struct gpf_ctx {
   std::vector<char> kinv_valid;
   bool toeplitz = false;
   bool centro_ok = false;
+  const double* d_bhat = nullptr;     // least-squares functions for the observation likelihood (balanced designs)
   bool indep = false;                 // X^T X diagonal and nothing missing: function draws of a sweep are independent
   int* d_fn_all = nullptr;            // all functions in sampler order / their sampler ids (device)
   unsigned* d_sid_all = nullptr;
@@ -467,6 +468,27 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
         if (a != b && std::fabs(G[(size_t)a * d->f + b]) > 1e-13 * std::sqrt(G[(size_t)a * d->f + a] * G[(size_t)b * d->f + b])) diag = false;
     for (unsigned char u : full) nomiss = nomiss && u;
     c->indep = diag && nomiss;
+    v.bhat = nullptr;
+    v.rss0 = 0.0;
+    if (c->indep) {   // observation likelihood about the least-squares fit (k_obs)
+      std::vector<double> bh((size_t)d->f * d->n);
+      for (int a = 0; a < d->f; ++a)
+        for (int t = 0; t < d->n; ++t) bh[(size_t)a * d->n + t] = Z[(size_t)a * d->n + t] / G[(size_t)a * d->f + a];
+      long double rss = 0.0L;
+      for (int t = 0; t < d->n; ++t)
+        for (int o = 0; o < d->m; ++o) {
+          long double pred = 0.0L;
+          for (int a = 0; a < d->f; ++a) pred += (long double)d->h_X[(size_t)o * d->f + a] * bh[(size_t)a * d->n + t];
+          const long double r = (long double)d->h_y[(size_t)t * d->m + o] - pred;
+          rss += r * r;
+        }
+      double* dbh;
+      if ((rc = dev_alloc(c, &dbh, bh.size()))) return fail(rc);
+      cudaMemcpy(dbh, bh.data(), sizeof(double) * bh.size(), cudaMemcpyHostToDevice);
+      v.bhat = dbh;
+      c->d_bhat = dbh;
+      v.rss0 = (double)rss;
+    }
     std::vector<int> fl;
     std::vector<unsigned> sl;
     for (size_t i = 0; i < c->order.size(); ++i)
@@ -765,6 +787,7 @@ int gpf_set_option(gpf_ctx* c, int option, int value) {
     for (auto& q : c->kinv_valid) q = 0;
     return GPF_OK;
   }
+  if (option == 4) { c->dev.bhat = value ? c->d_bhat : nullptr; return GPF_OK; }
   c->err = "gpf_set_option: unknown option";
   return GPF_ERR_ARG;
 }

@@ -40,6 +40,8 @@ struct CtxDev {
   const unsigned char* full;  // n       1 if no observation is missing at time t
   int* sched;                 // chain hand-out counter of the running launch (reset to 0 by the host before it)
   double* fws;                // per-CTA scratch of the class-mode function kernel: 2 x 32 x NT*32 doubles each
+  const double* bhat;         // f x n  least-squares functions Z[f,t] / G[f,f] (balanced design, nothing missing), else null
+  double rss0;                // sum of squared residuals of y about X bhat (host, extended precision)
 };
 
 // dynamic hand-out of chains to CTAs (chains differ in the number of slice evaluations they need): returns the next

@@ -523,6 +523,17 @@ __global__ void __launch_bounds__(NTHR) k_obs(CtxDev c, int mode, const double* 
   for (int ch = blockIdx.x; ch < c.C; ch += gridDim.x) {
     const double* Fc = c.F + (size_t)ch * c.f * n;
     double sse = 0.0, cnt = 0.0;
+    if (c.bhat) {
+      // balanced design, nothing missing: the residual sum of squares splits orthogonally about the least-squares fit,
+      //   ||y - X F||^2 = ||y - X bhat||^2 + sum_f (X^T X)[f,f] ||F_f - bhat_f||^2
+      // (all terms non-negative: no cancellation), O(f n) per chain instead of O(n m f)
+      for (int e = threadIdx.x; e < c.f * n; e += NTHR) {
+        const int q = e / n;
+        const double dlt = Fc[e] - c.bhat[e];
+        sse = fma(c.G[(size_t)q * c.f + q] * dlt, dlt, sse);
+      }
+      if (threadIdx.x == 0) { sse += c.rss0; cnt = (double)n * (double)c.m; }
+    } else
     for (int t = threadIdx.x; t < n; t += NTHR) {
       for (int o = 0; o < c.m; ++o) {
         const double yv = c.yT[(size_t)o * n + t];

@@ -300,7 +300,8 @@ class ChainEngine(object):
     def set_option(self, option, value):
         """option 0: Toeplitz/Schur slice log-likelihood on uniform grids (1, default) or dense tile engine (0);
         1: batched launches; 2: shared factorisation for functions with identical conditional precision;
-        3: centrosymmetric split of K_inv on uniform grids (even n >= 64)"""
+        3: centrosymmetric split of K_inv on uniform grids (even n >= 64); 4: observation likelihood about the
+        least-squares fit (balanced designs, nothing missing)"""
         self._ck(self._lib.gpf_set_option(self._h, int(option), int(value)))
 
     def sweep_host(self, n_sweeps=1, thin=0, order=None, stage_bytes=96 << 20, max_chunk_sweeps=None, on_chunk=None):

@@ -168,7 +168,10 @@ int gpf_sweep(gpf_ctx* ctx, int n_sweeps, int thin, unsigned sweep0, const int* 
  * 3 = uniform grid with an even number (>= 64) of time points: K + offset I is symmetric Toeplitz, hence
  * centrosymmetric, and K_inv is assembled from the inverses of the two n/2 x n/2 blocks K11 +- K12 J of its
  * orthogonal block diagonalisation -- a quarter of the flops of base.py:133's n x n inverse, same backward-stable
- * Cholesky inverse on each block (default 1; 0 = invert the n x n matrix directly). */
+ * Cholesky inverse on each block (default 1; 0 = invert the n x n matrix directly);
+ * 4 = balanced design with nothing missing: the residual sum of squares of base.py:196-214 is evaluated about the
+ * least-squares fit, ||y - X F||^2 = ||y - X bhat||^2 + sum_f (X^T X)[f,f] ||F_f - bhat_f||^2 (O(f n) per chain instead
+ * of O(n m f), all terms non-negative; default 1; 0 = per-observation loop, always used otherwise). */
 int gpf_set_option(gpf_ctx* ctx, int option, int value);
 int gpf_set_profile(gpf_ctx* ctx, int on);
 int gpf_get_profile(gpf_ctx* ctx, double* h_ms6, unsigned long long* h_launches);

@@ -458,6 +458,34 @@ def test_centrosymmetric_kinv_matches_direct_inverse(eng, n):
     e.close()
 
 
+@pytest.mark.parametrize("name", ["twoway_n24", "twoway_n24_hc", "full"])
+def test_observation_likelihood_about_the_least_squares_fit(eng, name):
+    """balanced design, nothing missing (option 4): ||y - XF||^2 = ||y - X bhat||^2 + sum_f G_ff ||F_f - bhat_f||^2 gives
+    the value of the per-observation loop of base.py:196-214 (and the oracle's) to rounding"""
+    rng = np.random.default_rng(5)
+    if name == "full":
+        x, y, d, groups, F = cfg5_problem(256)
+        X, C = d.X, 4
+        e = eng.ChainEngine(x, y, X, groups, chains=C, seed=1)
+        Fs = np.stack([F.T + 0.05 * rng.standard_normal(F.T.shape) for _ in range(C)])
+    else:
+        c = load_case(name)
+        x, y, X, C = c["x"], c["y"], c["design_matrix"], 3
+        e = make_engine(eng, c, chains=C)
+        Fs = np.stack([c["F"].T + 0.1 * rng.standard_normal(c["F"].T.shape) for _ in range(C)])
+    e.set_state(F=Fs)
+    cand = rng.uniform(-3, 1, size=C)
+    vals = {}
+    for opt in (0, 1):
+        e.set_option(4, opt)
+        vals[opt] = e.obs_loglik(cand)
+    for ch in range(C):
+        o = orc.observation_loglik(y, X, Fs[ch].T, cand[ch])
+        assert abs(vals[1][ch] - vals[0][ch]) <= 1e-12 * abs(o), (ch, vals[1][ch], vals[0][ch])
+        assert abs(vals[1][ch] - o) <= 1e-10 * abs(o)
+    e.close()
+
+
 def test_full_size_sweep_statistics(eng):
     """many chains at n = 256: the sampler must recover the generating functions (posterior mean close to truth,
     y_sigma near its true value) -- a size-independent sanity property of the whole path."""
