@@ -8,6 +8,8 @@ available through `chain_state()` / `chain_history()`.
 New, additive keyword arguments: chains=1, seed=None, device=None, devices=None (list of GPU ordinals: the chains are
 sharded over them, no inter-GPU communication), store_chains=True.
 """
+import os
+import sys
 import logging
 import random as pyrandom
 import time
@@ -351,8 +353,10 @@ class Base(SamplerContainer):
             def progress(done):
                 logger.info("%d/%d iterations (%.2lf%s) finished in %.2lf minutes" % (
                     done, n, 100. * done / n, '%', (time.time() - start_time) / 60))
+        t_sw = time.time()
         blocks = eng.sweep_host(n, thin=step, order=order, on_chunk=progress,
                                 max_chunk_sweeps=max(step, n // 10) if verbose else None)
+        t_sw1 = time.time()
         try:
             eng.status()
         except np.linalg.LinAlgError as e:        # keep what was sampled, then propagate like the reference
@@ -360,6 +364,9 @@ class Base(SamplerContainer):
         self._pull_state()
         if blocks.shape[0]:
             self._store_blocks(blocks)
+        if os.environ.get("GPFANOVA_B200_TIMING"):
+            sys.stderr.write("sample: push %.3f s  sweep_host %.3f s  pull+store %.3f s\n" % (
+                t_sw - start_time, t_sw1 - t_sw, time.time() - t_sw1))
         if verbose:
             logger.info("%d samples finished in %.2lf minutes" % (n, (time.time() - start_time) / 60))
         if err is not None:

@@ -6,6 +6,10 @@ happens in the sm_100a kernels behind the ctypes boundary.
 """
 import ctypes as C
 
+import os
+import sys
+import time
+
 import numpy as np
 import torch
 
@@ -96,6 +100,18 @@ def kinv(A, offset=OFFSET, device=None):
 # ----------------------------------------------------------------------------------------------
 # sampler context
 # ----------------------------------------------------------------------------------------------
+_COPY_THREADS = max(1, int(os.environ.get("GPFANOVA_B200_COPY_THREADS", "4")))
+_POOL = None
+
+
+def _copy_pool():
+    global _POOL
+    if _POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL = ThreadPoolExecutor(max_workers=_COPY_THREADS)
+    return _POOL
+
+
 class ChainEngine(object):
     """C chains of  y (n x m) = F (n x f) X^T + noise  on one GPU.
 
@@ -320,20 +336,43 @@ class ChainEngine(object):
             self.sync()
             return np.zeros((0, self.C, cols))
         rowbytes = self.C * cols * 8
-        crow = max(1, int(stage_bytes // rowbytes))            # rows per chunk
+        # rows per chunk: bounded by the staging size, and at most a quarter of the call so that the drain of one chunk
+        # overlaps the kernels of the next (the last chunk's drain is the only one exposed)
+        cap = max(1, int(stage_bytes // rowbytes))            # rows the staging buffers hold (allocated once, reused)
+        crow = max(1, min(cap, -(-rows_total // 4)))
         if max_chunk_sweeps:
             crow = max(1, min(crow, int(max_chunk_sweeps) // step))
-        if getattr(self, "_stage", None) is None or self._stage[0].shape[0] < crow:
-            self._stage = [torch.empty((crow, self.C, cols), dtype=torch.float64, pin_memory=True) for _ in range(2)]
-            self._dev_hist = [torch.empty((crow, self.C, cols), dtype=torch.float64, device=self.dev) for _ in range(2)]
+        if getattr(self, "_stage", None) is None or self._stage[0].shape[0] < cap:
+            self._stage = [torch.empty((cap, self.C, cols), dtype=torch.float64, pin_memory=True) for _ in range(2)]
+            self._dev_hist = [torch.empty((cap, self.C, cols), dtype=torch.float64, device=self.dev) for _ in range(2)]
+        t_begin = time.perf_counter()
         out = np.empty((rows_total, self.C, cols))
         pending = []                                           # (buffer index, first row, rows)
         done, row0, i = 0, 0, 0
 
+        tm = {"wait": 0.0, "copy": 0.0, "launch": 0.0} if os.environ.get("GPFANOVA_B200_TIMING") else None
+
         def drain():
             b, r0, nr = pending.pop(0)
+            t0 = time.perf_counter()
             self._ck(self._lib.gpf_wait_event(self._h, b))
-            np.copyto(out[r0:r0 + nr], self._stage[b].numpy()[:nr])
+            t1 = time.perf_counter()
+            _drain_copy(b, r0, nr)
+            if tm is not None:
+                tm["wait"] += t1 - t0
+                tm["copy"] += time.perf_counter() - t1
+
+        def _drain_copy(b, r0, nr):
+            dst = out[r0:r0 + nr].reshape(-1)
+            src = self._stage[b].numpy()[:nr].reshape(-1)
+            # the copy into fresh pageable memory is page-fault bound (~2 GB/s per thread): spread it over a few threads
+            # (numpy releases the GIL while copying)
+            nt = _COPY_THREADS if dst.size >= (1 << 20) else 1
+            if nt <= 1:
+                np.copyto(dst, src)
+            else:
+                cut = [dst.size * j // nt for j in range(nt + 1)]
+                list(_copy_pool().map(lambda j: np.copyto(dst[cut[j]:cut[j + 1]], src[cut[j]:cut[j + 1]]), range(nt)))
 
         while done < n_sweeps:
             k = min(crow * step, n_sweeps - done)
@@ -358,6 +397,9 @@ class ChainEngine(object):
         while pending:
             drain()
         self.sync()
+        if tm is not None:
+            sys.stderr.write("sweep_host: rows %d chunk rows %d  event wait %.3f s  copy %.3f s  total %.3f s\n" % (
+                row0, crow, tm["wait"], tm["copy"], time.perf_counter() - t_begin))
         return out[:row0]
 
     def set_profile(self, on=1):
