@@ -783,7 +783,7 @@ int gpf_set_option(gpf_ctx* c, int option, int value) {
   if (option == 1) { c->batch = value; return GPF_OK; }
   if (option == 2) { c->share = value; return GPF_OK; }
   if (option == 3) {   // centrosymmetric split of K_inv on uniform grids (on by default where it applies)
-    c->dev.centro = c->centro_ok ? value : 0;   // (debug builds: bit 1 skips the assembly, bit 2 the second half)
+    c->dev.centro = (value && c->centro_ok) ? 1 : 0;
     for (auto& q : c->kinv_valid) q = 0;
     return GPF_OK;
   }

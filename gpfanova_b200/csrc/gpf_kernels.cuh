@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(NTHR, 2) k_group_kinv(CtxDev c, int g_first, i
       ++tries;
       if (tries > c.maxtries || !isfinite(jitter)) { code = GPF_STATUS_NOT_PD; break; }
     }
-    if constexpr (centro) if (code >= 0 && !(c.centro & 2)) {
+    if constexpr (centro) if (code >= 0) {
       // K^-1 = 1/2 [[S, D J], [J D, J S J]],  S = M+ + M-,  D = M+ - M-  (M+- = B+-^-1, symmetric, lower tiles valid)
       __syncthreads();
       const double* M1 = Wh;

@@ -418,7 +418,7 @@ def test_full_size_identities(eng):
     e.close()
 
 
-@pytest.mark.parametrize("n", [64, 66, 100, 130, 192, 256])
+@pytest.mark.parametrize("n", [64, 66, 100, 130, 192, 256, 320, 512])
 def test_centrosymmetric_kinv_matches_direct_inverse(eng, n):
     """uniform grid, even n >= 64: K + 1e-9 I is symmetric Toeplitz => centrosymmetric, and k_group_kinv assembles K_inv
     from the inverses of K11 +- K12 J (option 3).  Same accuracy class as the direct n x n inverse of kernel.pyx:51-64:

@@ -9,7 +9,7 @@ groups = [list(g) for g in model.priorGroups()]
 eng = engine.ChainEngine(x, y, model.design_matrix, groups, chains=C, seed=1, device=0)
 eng.set_state(hyper=synthetic.chain_starts(C, len(groups)))
 eng.sweep(5)
-for opt in (1,):
+for opt in (0, 1):
     eng.set_option(3, opt)
     eng.set_profile(1)
     eng.sweep(4); eng.sync()
