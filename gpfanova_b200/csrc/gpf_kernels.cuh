@@ -217,22 +217,42 @@ __global__ void __launch_bounds__(NTHR, 2) k_group_kinv(CtxDev c, int g_first, i
             } else { ta = T - 1 - bj; tb = T - 1 - bi; flip = true; transp = true; }  // out[r][c] = S[ta*32+31-c][tb*32+31-r]
             const double* s1 = M1 + (size_t)plt(ta, tb) * TILE;
             const double* s2 = M2 + (size_t)plt(ta, tb) * TILE;
+            // loads in batches of 8 + 8 before the first store: the source (workspace) and the destination may alias as far
+            // as the compiler knows, and a load -> store -> load chain would pay one L2 latency per 16 bytes
             if (!transp) {
 #pragma unroll
-              for (int q = 0; q < 16; ++q) {
-                const int idx = q * 32 + lane, row = idx >> 4, ch2 = 2 * (idx & 15), srow = flip ? 31 - row : row;
-                const double2 a = *reinterpret_cast<const double2*>(s1 + srow * TB + ch2);
-                const double2 b = *reinterpret_cast<const double2*>(s2 + srow * TB + ch2);
-                __stcs(reinterpret_cast<double2*>(tile + row * TB + ch2), make_double2(0.5 * fma(sg, b.x, a.x), 0.5 * fma(sg, b.y, a.y)));
+              for (int q0 = 0; q0 < 16; q0 += 8) {
+                double2 a[8], b[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const int idx = (q0 + q) * 32 + lane, row = idx >> 4, ch2 = 2 * (idx & 15), srow = flip ? 31 - row : row;
+                  a[q] = *reinterpret_cast<const double2*>(s1 + srow * TB + ch2);
+                  b[q] = *reinterpret_cast<const double2*>(s2 + srow * TB + ch2);
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const int idx = (q0 + q) * 32 + lane, row = idx >> 4, ch2 = 2 * (idx & 15);
+                  __stcs(reinterpret_cast<double2*>(tile + row * TB + ch2),
+                         make_double2(0.5 * fma(sg, b[q].x, a[q].x), 0.5 * fma(sg, b[q].y, a[q].y)));
+                }
               }
             } else {
               __syncwarp();
 #pragma unroll
-              for (int q = 0; q < 16; ++q) {
-                const int idx = q * 32 + lane, row = idx >> 4, ch2 = 2 * (idx & 15);
-                const double2 a = *reinterpret_cast<const double2*>(s1 + row * TB + ch2);
-                const double2 b = *reinterpret_cast<const double2*>(s2 + row * TB + ch2);
-                *reinterpret_cast<double2*>(slot + row * PS + ch2) = make_double2(0.5 * fma(sg, b.x, a.x), 0.5 * fma(sg, b.y, a.y));
+              for (int q0 = 0; q0 < 16; q0 += 8) {
+                double2 a[8], b[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const int idx = (q0 + q) * 32 + lane, row = idx >> 4, ch2 = 2 * (idx & 15);
+                  a[q] = *reinterpret_cast<const double2*>(s1 + row * TB + ch2);
+                  b[q] = *reinterpret_cast<const double2*>(s2 + row * TB + ch2);
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const int idx = (q0 + q) * 32 + lane, row = idx >> 4, ch2 = 2 * (idx & 15);
+                  *reinterpret_cast<double2*>(slot + row * PS + ch2) =
+                      make_double2(0.5 * fma(sg, b[q].x, a[q].x), 0.5 * fma(sg, b[q].y, a[q].y));
+                }
               }
               __syncwarp();
               // lower-left block: source element (c, 31 - r); lower-right block: source element (31 - c, 31 - r)
