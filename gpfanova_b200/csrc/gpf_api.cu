@@ -726,17 +726,27 @@ int gpf_sweep(gpf_ctx* c, int n_sweeps, int thin, unsigned sweep0, const int* h_
       for (int g = 0; g < c->dev.P; ++g) conc = conc && uses_schur(c, g);   // the dense slice kernel owns the per-CTA workspace
       if (conc && !rc) CK(c, cudaEventRecord(c->ev_fork, c->stream));
       int used = 0;
-      for (int k = 0; k < ns && !rc; ++k)
-        if (c->order[k].kind == 0 && c->order[k].arg >= 1 && (c->order[k].arg - 1) % 2 == 0) {
-          const int g = (c->order[k].arg - 1) / 2, slot = conc ? g % 4 : -1;
-          if (conc && used < 4 && slot == used) { CK(c, cudaStreamWaitEvent(c->aux[slot], c->ev_fork, 0)); ++used; }
-          rc = launch_prior(c, g, 4, nullptr, nullptr, (unsigned)k, sweep, nullptr, 0, nullptr, slot);
-        }
+      // largest groups first: their slice steps are the longest, and the smaller groups' CTAs then fill their tail
+      std::vector<std::pair<int, int>> todo;     // (sampler index, group)
+      for (int k = 0; k < ns; ++k)
+        if (c->order[k].kind == 0 && c->order[k].arg >= 1 && (c->order[k].arg - 1) % 2 == 0) todo.push_back({k, (c->order[k].arg - 1) / 2});
+      if (conc)
+        std::stable_sort(todo.begin(), todo.end(), [&](const std::pair<int, int>& a, const std::pair<int, int>& b) {
+          return c->groups[a.second].size() > c->groups[b.second].size();
+        });
+      std::vector<char> forked(4, 0);
+      for (size_t q = 0; q < todo.size() && !rc; ++q) {
+        const int k = todo[q].first, g = todo[q].second, slot = conc ? g % 4 : -1;
+        if (conc && !forked[slot]) { CK(c, cudaStreamWaitEvent(c->aux[slot], c->ev_fork, 0)); forked[slot] = 1; ++used; }
+        rc = launch_prior(c, g, 4, nullptr, nullptr, (unsigned)k, sweep, nullptr, 0, nullptr, slot);
+      }
       if (conc && !rc)
-        for (int i = 0; i < used; ++i) {
-          CK(c, cudaEventRecord(c->ev_join[i], c->aux[i]));
-          CK(c, cudaStreamWaitEvent(c->stream, c->ev_join[i], 0));
-        }
+        for (int i = 0; i < 4; ++i)
+          if (forked[i]) {
+            CK(c, cudaEventRecord(c->ev_join[i], c->aux[i]));
+            CK(c, cudaStreamWaitEvent(c->stream, c->ev_join[i], 0));
+          }
+      (void)used;
       if (rc) return rc;
     } else
     for (int k = 0; k < ns; ++k) {
