@@ -46,6 +46,7 @@ struct gpf_ctx {
   std::vector<char> kinv_valid;
   bool toeplitz = false;
   bool centro_ok = false;
+  bool cls_big = false;               // some class has three or more functions: batched draws
   const double* d_bhat = nullptr;     // least-squares functions for the observation likelihood (balanced designs)
   bool indep = false;                 // X^T X diagonal and nothing missing: function draws of a sweep are independent
   int* d_fn_all = nullptr;            // all functions in sampler order / their sampler ids (device)
@@ -178,7 +179,8 @@ int launch_all_functions(gpf_ctx* c, unsigned sweep) {
   CK(c, cudaMemsetAsync(c->dev.sched, 0, sizeof(int), c->stream));
   if (c->cls_shared && c->share) {   // functions with identical conditional precision share one factorisation
     const int grid = std::min(c->dev.C * c->ncls, 2 * c->sms);
-    k_function_class<<<grid, NTHR, c->smem_fn, c->stream>>>(c->dev, c->d_cls_off, c->d_cls_fn, c->d_cls_sid, c->ncls, sweep);
+    if (c->cls_big) k_function_class<true><<<grid, NTHR, c->smem_fn, c->stream>>>(c->dev, c->d_cls_off, c->d_cls_fn, c->d_cls_sid, c->ncls, sweep);
+    else k_function_class<false><<<grid, NTHR, c->smem_fn, c->stream>>>(c->dev, c->d_cls_off, c->d_cls_fn, c->d_cls_sid, c->ncls, sweep);
     ++c->launches;
     CK(c, cudaGetLastError());
     return GPF_OK;
@@ -395,7 +397,8 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
     if (e == cudaSuccess) e = allow_smem(k_group_kinv<1>, c->smem_kinv);
     if (e == cudaSuccess) e = allow_smem(k_group_kinv<2>, c->smem_kinv2);
     if (e == cudaSuccess) e = allow_smem(k_function, c->smem_fn);
-    if (e == cudaSuccess) e = allow_smem(k_function_class, c->smem_fn);
+    if (e == cudaSuccess) e = allow_smem(k_function_class<false>, c->smem_fn);
+    if (e == cudaSuccess) e = allow_smem(k_function_class<true>, c->smem_fn);
     if (e == cudaSuccess) e = allow_smem(k_prior<true>, sp);
     if (e == cudaSuccess) e = allow_smem(k_prior<false>, sp);
     if (e == cudaSuccess) e = allow_smem(k_prior_schur<0>, 112 * 1024);
@@ -510,6 +513,7 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
           if (cnt == TB) { coff.push_back((int)cfn.size()); cnt = 0; }      // at most 32 functions per item
           used[j] = 1; cfn.push_back(fl[j]); csid.push_back(sl[j]); ++cnt;
           if (cnt > 1) c->cls_shared = true;
+          if (cnt > 2) c->cls_big = true;
         }
         coff.push_back((int)cfn.size());
       }

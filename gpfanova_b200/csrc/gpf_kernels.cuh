@@ -429,6 +429,40 @@ __global__ void __launch_bounds__(NTHR, 2) k_function(CtxDev c, int fn_single, u
   }
 }
 
+// draws of up to R functions of one class in one pass: beta_j = L_A^-T (w_j + z_j), the R right-hand sides solved together
+// (each tile of L_A is read once per R functions instead of once per function; per right-hand side the arithmetic and its
+// order are those of back_solve<2>, so the draws are bit-identical).  The right-hand sides live in the panel slots, which
+// the finished factorisation no longer needs.  Separate function: keeps the register allocation of the engine loops of
+// the calling kernel untouched.
+template <int R>
+__device__ __noinline__ void class_draw_batch(const CtxDev& c, const double* W, int NT, const EngineSmem& sm,
+                                              const double* __restrict__ wrow, const int* __restrict__ fns,
+                                              const unsigned* __restrict__ sids, int j0, int cnt, int ch, unsigned sweep) {
+  const int n = c.n, npad = NT * TB;
+  const Stream rng{c.k0, c.k1};
+  double* xs = sm.P;                                   // R x npad
+  __syncthreads();
+  for (int e = threadIdx.x; e < R * npad; e += NTHR) {
+    const int v = e / npad, t = e % npad;
+    xs[e] = (v < cnt && t < n) ? wrow[(size_t)(j0 + v) * npad + t] : 0.0;
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < cnt * ((n + 1) / 2); q += NTHR) {
+    const int v = q / ((n + 1) / 2), pr = q % ((n + 1) / 2);
+    double z0, z1;
+    rng.normal_pair((unsigned)(ch + c.chain_offset), sweep, sids[j0 + v], (unsigned)pr, z0, z1);
+    xs[v * npad + 2 * pr] += z0;
+    if (2 * pr + 1 < n) xs[v * npad + 2 * pr + 1] += z1;
+  }
+  __syncthreads();
+  back_solve<R>(W, NT, xs, npad, sm, nullptr);
+  for (int e = threadIdx.x; e < cnt * n; e += NTHR) {
+    const int v = e / n, t = e % n;
+    c.F[((size_t)ch * c.f + fns[j0 + v]) * n + t] = xs[v * npad + t];
+  }
+  __syncthreads();
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Function._sample for a CLASS of functions that share their conditional precision matrix.
 // In a balanced design with nothing missing, n_t = (X^T X)[f,f] for every t, so functions of one prior group with equal
@@ -439,6 +473,8 @@ __global__ void __launch_bounds__(NTHR, 2) k_function(CtxDev c, int fn_single, u
 // L_A, every row of the augmented block is solved independently of the others).
 // Items = (class, chain); cls_off / cls_fn / cls_sid: CSR list of the functions (and sampler ids) of every class.
 // ---------------------------------------------------------------------------------------------------------
+template <bool BATCH>   // BATCH: classes of three or more functions draw in batches of 8 right-hand sides (own instantiation:
+                        // the call must not perturb the register allocation of the few-functions kernel)
 __global__ void __launch_bounds__(NTHR, 2) k_function_class(CtxDev c, const int* __restrict__ cls_off, const int* __restrict__ cls_fn,
                                                             const unsigned* __restrict__ cls_sid, int ncls, unsigned sweep) {
   const int NT = c.NT, n = c.n, npad = NT * TB;
@@ -493,7 +529,10 @@ __global__ void __launch_bounds__(NTHR, 2) k_function_class(CtxDev c, const int*
       if (tries > c.maxtries || !isfinite(jitter)) { code = GPF_STATUS_NOT_PD; break; }
     }
     __syncthreads();
-    if (code >= 0) {
+    if (BATCH && code >= 0 && nf >= 3) {
+      // many functions per class (helmertConvert designs): draws in batches of 8 right-hand sides
+      for (int j0 = 0; j0 < nf; j0 += 8) class_draw_batch<8>(c, W, NT, sm, wrow, fns, sids, j0, (nf - j0 < 8) ? nf - j0 : 8, ch, sweep);
+    } else if (code >= 0) {
       for (int j = 0; j < nf; ++j) {
         const int fn = fns[j];
         for (int t = threadIdx.x; t < npad; t += NTHR) {
