@@ -535,19 +535,15 @@ __global__ void __launch_bounds__(NTHR, 2) k_function_class(CtxDev c, const int*
     } else if (code >= 0) {
       for (int j = 0; j < nf; ++j) {
         const int fn = fns[j];
-        for (int t = threadIdx.x; t < npad; t += NTHR) {
-          xs[t] = (t < n) ? wrow[(size_t)j * npad + t] : 0.0;
-          xs[npad + t] = 0.0;
+        const double* wj = wrow + (size_t)j * npad;
+        for (int pr = threadIdx.x; 2 * pr < npad; pr += NTHR) {
+          double z0 = 0.0, z1 = 0.0;
+          if (2 * pr < n) rng.normal_pair((unsigned)(ch + c.chain_offset), sweep, sids[j], (unsigned)pr, z0, z1);
+          xs[npad + 2 * pr] = (2 * pr < n) ? wj[2 * pr] + z0 : 0.0;
+          xs[npad + 2 * pr + 1] = (2 * pr + 1 < n) ? wj[2 * pr + 1] + z1 : 0.0;
         }
         __syncthreads();
-        for (int pr = threadIdx.x; 2 * pr < n; pr += NTHR) {
-          double z0, z1;
-          rng.normal_pair((unsigned)(ch + c.chain_offset), sweep, sids[j], (unsigned)pr, z0, z1);
-          xs[npad + 2 * pr] = xs[2 * pr] + z0;
-          if (2 * pr + 1 < n) xs[npad + 2 * pr + 1] = xs[2 * pr + 1] + z1;
-        }
-        __syncthreads();
-        back_solve<2>(W, NT, xs, npad, sm, red);
+        back_solve<1>(W, NT, xs + npad, npad, sm, red);   // only the draw is kept in a sweep (mu is not an output here)
         for (int t = threadIdx.x; t < n; t += NTHR) c.F[((size_t)ch * c.f + fn) * n + t] = xs[npad + t];
         __syncthreads();
       }
