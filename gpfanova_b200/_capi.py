@@ -40,6 +40,7 @@ SIGNATURES = {
     "gpf_set_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "gpf_get_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "gpf_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "gpf_memcpy_d2h_event": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
     "gpf_record_event": (C.c_int, [C.c_void_p, C.c_int]),
     "gpf_wait_event": (C.c_int, [C.c_void_p, C.c_int]),
     "gpf_device_F": (C.c_void_p, [C.c_void_p]),

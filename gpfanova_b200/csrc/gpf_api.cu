@@ -62,6 +62,8 @@ struct gpf_ctx {
   cudaStream_t aux[4] = {nullptr, nullptr, nullptr, nullptr};   // the groups' slice kernels of a batched sweep run concurrently
   cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_user[4] = {nullptr, nullptr, nullptr, nullptr};   // gpf_record_event / gpf_wait_event
+  cudaStream_t copy = nullptr;         // device -> host history copies run beside the kernels of the next sweeps
+  cudaEvent_t ev_copy = nullptr;
   std::vector<void*> allocs;
   size_t smem_kinv = 0, smem_kinv2 = 0, smem_fn = 0;
   std::vector<size_t> smem_prior;
@@ -339,6 +341,8 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
       if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_user[i], cudaEventDisableTiming | cudaEventBlockingSync);
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming);
     if (e != cudaSuccess) { c->err = cudaGetErrorString(e); return fail(GPF_ERR_CUDA); }
   }
   CtxDev& v = c->dev;
@@ -565,6 +569,8 @@ void gpf_destroy(gpf_ctx* c) {
     if (c->ev_user[i]) cudaEventDestroy(c->ev_user[i]);
   }
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->copy) { cudaStreamSynchronize(c->copy); cudaStreamDestroy(c->copy); }
+  if (c->ev_copy) cudaEventDestroy(c->ev_copy);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -575,6 +581,7 @@ void* gpf_stream(gpf_ctx* c) { return c ? (void*)c->stream : nullptr; }
 int gpf_sync(gpf_ctx* c) {
   CK(c, cudaSetDevice(c->device));
   CK(c, cudaStreamSynchronize(c->stream));
+  CK(c, cudaStreamSynchronize(c->copy));
   return GPF_OK;
 }
 
@@ -602,6 +609,16 @@ int gpf_get_state(gpf_ctx* c, double* h_F, double* h_hyper) {
 int gpf_memcpy_d2h(gpf_ctx* c, void* h_dst, const void* d_src, size_t bytes) {
   CK(c, cudaSetDevice(c->device));
   CK(c, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  return GPF_OK;
+}
+
+int gpf_memcpy_d2h_event(gpf_ctx* c, void* h_dst, const void* d_src, size_t bytes, int idx) {
+  if (idx < 0 || idx > 3) { c->err = "gpf_memcpy_d2h_event: idx must be 0..3"; return GPF_ERR_ARG; }
+  CK(c, cudaSetDevice(c->device));
+  CK(c, cudaEventRecord(c->ev_copy, c->stream));                 // everything queued so far on the ctx stream ...
+  CK(c, cudaStreamWaitEvent(c->copy, c->ev_copy, 0));            // ... precedes the copy, which runs on its own stream
+  CK(c, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->copy));
+  CK(c, cudaEventRecord(c->ev_user[idx], c->copy));
   return GPF_OK;
 }
 

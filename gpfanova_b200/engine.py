@@ -112,6 +112,17 @@ def _copy_pool():
     return _POOL
 
 
+_PREFAULT = None
+
+
+def _prefault_pool():
+    global _PREFAULT
+    if _PREFAULT is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _PREFAULT = ThreadPoolExecutor(max_workers=1)
+    return _PREFAULT
+
+
 class ChainEngine(object):
     """C chains of  y (n x m) = F (n x f) X^T + noise  on one GPU.
 
@@ -324,8 +335,8 @@ class ChainEngine(object):
         """sweep() with the stored states delivered to the host as ONE numpy array (rows, C, H + f*n).
 
         Double-buffered pipeline: the stored rows of a chunk of sweeps are copied device -> PINNED staging buffer on the
-        context's stream right behind the chunk's kernels (DMA speed, no pageable staging), and drained into the result
-        array by the host while the GPU already runs the next chunk.  The staging buffers (2 x <= stage_bytes) and the
+        context's copy stream right behind the chunk's kernels (DMA speed, no pageable staging, beside the kernels of the
+        next chunk), and drained into the result array by the host while the GPU already runs the next chunk.  The staging buffers (2 x <= stage_bytes) and the
         device history buffers are kept by the engine and reused by later calls."""
         step = 1 if thin <= 0 else int(thin)
         cols = self.H + self.f * self.n
@@ -347,6 +358,16 @@ class ChainEngine(object):
             self._dev_hist = [torch.empty((cap, self.C, cols), dtype=torch.float64, device=self.dev) for _ in range(2)]
         t_begin = time.perf_counter()
         out = np.empty((rows_total, self.C, cols))
+        if out.nbytes >= (64 << 20):
+            # fresh pageable memory: the first write to every 4 KB page faults (~2 GB/s per thread).  Touch the pages from
+            # a background thread while the GPU runs the first sweeps, so that the drains copy at memcpy speed
+            flat = out.reshape(-1)
+            blk = 8 << 20                                      # doubles per block (64 MB), in drain order
+
+            def prefault():
+                for a in range(0, flat.size, blk):
+                    flat[a:a + blk:512] = 0.0
+            _prefault_pool().submit(prefault)
         pending = []                                           # (buffer index, first row, rows)
         done, row0, i = 0, 0, 0
 
@@ -385,9 +406,8 @@ class ChainEngine(object):
                 self.sweep(k, thin=step, order=sub)
             else:
                 got = self.sweep(k, thin=step, history=self._dev_hist[b][:rows], order=sub)
-                self._ck(self._lib.gpf_memcpy_d2h(self._h, C.c_void_p(self._stage[b].data_ptr()), _ptr(self._dev_hist[b]),
-                                                  got * rowbytes))
-                self._ck(self._lib.gpf_record_event(self._h, b))
+                self._ck(self._lib.gpf_memcpy_d2h_event(self._h, C.c_void_p(self._stage[b].data_ptr()),
+                                                        _ptr(self._dev_hist[b]), got * rowbytes, b))
                 pending.append((b, row0, got))
                 row0 += got
                 i += 1

@@ -104,6 +104,10 @@ int gpf_memcpy_d2h(gpf_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
  * lets the caller drain history chunks from pinned staging buffers while the next sweeps run. */
 int gpf_record_event(gpf_ctx* ctx, int idx);
 int gpf_wait_event(gpf_ctx* ctx, int idx);
+/* device -> host copy on the ctx's COPY stream, ordered after everything queued so far on the ctx stream, with user
+ * event idx recorded behind it: the kernels of later gpf_sweep calls run beside the transfer (the source must not be
+ * overwritten before gpf_wait_event(ctx, idx) has returned). */
+int gpf_memcpy_d2h_event(gpf_ctx* ctx, void* h_dst, const void* d_src, size_t bytes, int idx);
 double* gpf_device_F(gpf_ctx* ctx);       /* device pointers to the live state (chains x f x n) */
 double* gpf_device_hyper(gpf_ctx* ctx);   /* chains x H */
 int gpf_invalidate(gpf_ctx* ctx);         /* call after writing through gpf_device_hyper(): cached K_inv are stale */
