@@ -38,10 +38,12 @@ __device__ long long gpf_trace[8 * 8];
 #define GPF_STAMP_FLUSH
 #endif
 
-// warps per CTA: measured 8 -> 49.1, 6 -> 47.7, 4 -> 47.2 ms per cfg5 sweep (the engine is bound by the serial
-// pivot / panel chain of each matrix, not by warp-level throughput); 6 leaves 168 registers per thread at 2 CTAs/SM
+// warps per CTA (2 CTAs per SM, set by shared memory): measured with the final engine 8 -> 37.2, 6 -> 36.4, 4 -> 34.4 ms
+// per cfg5 sweep.  The engine is bound by the serial pivot / panel chain of each matrix and by warp-level latency
+// chains, not by warp-level throughput: fewer warps contend less for the issue slots of the look-ahead warp, and at
+// 128 threads per CTA nothing caps the registers per thread (the K_inv halves run as two 2-warp sub-engines).
 #ifndef GPF_NW
-#define GPF_NW 6
+#define GPF_NW 4
 #endif
 #ifndef GPF_ENGINE_INLINE
 #define GPF_ENGINE_INLINE __forceinline__
