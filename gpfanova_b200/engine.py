@@ -433,6 +433,18 @@ class ChainEngine(object):
         return dict(zip(["total", "kinv", "function", "prior_slice", "y_sigma", "store"], ms.tolist())), int(nl.value)
 
 
+def split_chains(chains, parts):
+    """contiguous blocks of chains for `parts` devices (or ranks): (counts, offsets); the first chains % parts blocks get
+    one chain more.  The offset of a block is the `chain_offset` of its engine (Philox is keyed by the global chain index)."""
+    chains, parts = int(chains), int(parts)
+    if not 1 <= parts <= chains:
+        raise ValueError("need 1 <= number of devices <= chains")
+    base, rem = divmod(chains, parts)
+    counts = [base + (1 if i < rem else 0) for i in range(parts)]
+    offsets = [sum(counts[:i]) for i in range(parts)]
+    return counts, offsets
+
+
 class EngineGroup(object):
     """The chains of one model spread over several GPUs of one box: one ChainEngine (context + stream) per device,
     contiguous blocks of chains, no inter-GPU communication on the sampling path; the stored states are gathered on the
@@ -441,11 +453,7 @@ class EngineGroup(object):
 
     def __init__(self, x, y, X, groups, chains, seed, devices, **kw):
         devices = list(devices)
-        D = len(devices)
-        assert 1 <= D <= chains
-        base, rem = divmod(int(chains), D)
-        self.counts = [base + (1 if i < rem else 0) for i in range(D)]
-        self.offsets = [int(v) for v in np.concatenate([[0], np.cumsum(self.counts)[:-1]])]
+        self.counts, self.offsets = split_chains(chains, len(devices))
         self.engines = [ChainEngine(x, y, X, groups, chains=c, seed=seed, device=d, chain_offset=o, **kw)
                         for c, d, o in zip(self.counts, devices, self.offsets)]
         e0 = self.engines[0]

@@ -54,3 +54,15 @@ def test_bench_reference_arm_nonzero_ranks_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                        env=env, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_chain_blocks_for_devices():
+    """engine.split_chains: the partition EngineGroup (devices=[...]) and a torchrun launch both use"""
+    from gpfanova_b200.engine import split_chains
+    assert split_chains(4096, 8) == ([512] * 8, [512 * i for i in range(8)])
+    counts, offsets = split_chains(10, 4)
+    assert counts == [3, 3, 2, 2] and offsets == [0, 3, 6, 8]
+    assert split_chains(5, 5) == ([1] * 5, list(range(5)))
+    import pytest
+    with pytest.raises(ValueError):
+        split_chains(3, 4)
