@@ -181,6 +181,27 @@ def fp64_peak():
         return 37.0, "fallback 37 TFLOP/s (B200 FP64 datasheet order; profiles/fp64_peak_r01.json missing)"
 
 
+def ncu_traffic(kernel_file, n, chains_per_gpu):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel from the committed ncu --set full
+    summary (profiles/, captured on the default workload: n = 256, 4096 chains on one GPU); None for other workloads"""
+    if n != 256 or chains_per_gpu != 4096:
+        return None
+    path = os.path.join(ROOT, "profiles", kernel_file)
+    try:
+        tot, seen = 0.0, 0
+        for line in open(path):
+            t = line.split()
+            if len(t) >= 3 and t[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and seen < 2:
+                scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(t[2], None)
+                if scale is None:
+                    return None
+                tot += float(t[1]) * scale
+                seen += 1
+        return tot if seen == 2 else None
+    except (OSError, ValueError):
+        return None
+
+
 def flops_model(n, f, P, ng_list, counts, schur):
     """algorithmic FP64 flops of what was executed (counted by the kernels), SURVEY.md 8d / DESIGN.md 5:
     K_inv n^3 (chol + triangular inverse + L^-T L^-1) -- uniform grid with even n >= 64: two n/2 inverses through the
@@ -311,7 +332,15 @@ def main():
     dom = max(("kinv", "function", "prior_slice"), key=lambda k: prof[k])
     tf = {k: (fm[k] / (prof[k] * 1e-3) / 1e12 if prof[k] > 0 else 0.0) for k in kern}
     roofline = {"bound": "tensor", "kernel": kern[dom][0], "achieved": tf[dom], "peak": peak, "unit": "TFLOP/s",
-                "frac": tf[dom] / peak, "traffic": None, "peak_source": peak_src,
+                "frac": tf[dom] / peak,
+                "traffic": ncu_traffic({"function": "ncu_r01_final_k_function_class.txt",
+                                        "kinv": "ncu_r01_final_k_group_kinv.txt"}.get(dom, ""), n, C),
+                "traffic_note": "bytes per launch from profiles/ncu_r01_final_*.txt (one ncu --set full capture of this "
+                                "workload); the kernel is FP64-tensor bound, its algorithmic HBM bytes are the K_inv tiles "
+                                "read once per factorisation (%.1f GB per launch) -- the rest is workspace traffic that "
+                                "falls out of L2" % (counts_prof.get("function_chol", 0) / max(1, args.steps) *
+                                                   (n // 32) * (n // 32 + 1) / 2 * 8192 / 1e9),
+                "peak_source": peak_src,
                 "flops_per_launch": fm[dom] / kern[dom][1], "ms_per_launch": prof[dom] / kern[dom][1],
                 "share_of_step": prof[dom] / prof["total"] if prof["total"] else None,
                 "per_kernel": {k: {"ms_per_step": prof[k] / args.steps, "tflops": tf[k], "frac": tf[k] / peak,
