@@ -173,10 +173,16 @@ class ClockSampler(object):
 
 def fp64_peak():
     """measured FP64 tensor (DMMA) peak of this pool's B200: MEASURED_PEAKS.json has no FP64 entry, so the denominator is
-    our own microbenchmark (tools/fp64_peak.cu, result committed as profiles/fp64_peak_r01.json)"""
+    our own microbenchmark (tools/fp64_peak.cu, result committed as profiles/fp64_peak_r0*.json)"""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak_r01.json")))
-        return float(d["dmma884_tflops"]), "profiles/fp64_peak_r01.json (tools/fp64_peak.cu, DMMA m8n8k4 burst, measured on this pool)"
+        for nm in ("fp64_peak_r02.json", "fp64_peak_r01.json"):
+            path = os.path.join(ROOT, "profiles", nm)
+            if os.path.exists(path):
+                d = json.load(open(path))
+                key = "dmma884_tflops_sustained" if "dmma884_tflops_sustained" in d else "dmma884_tflops"
+                return float(d[key]), "profiles/%s (tools/fp64_peak.cu, DMMA m8n8k4 %s, measured on this pool)" % (
+                    nm, "sustained" if key.endswith("sustained") else "burst")
+        raise OSError("no FP64 peak file")
     except Exception:
         return 37.0, "fallback 37 TFLOP/s (B200 FP64 datasheet order; profiles/fp64_peak_r01.json missing)"
 
@@ -203,15 +209,20 @@ def ncu_traffic(kernel_file, n, chains_per_gpu):
 
 
 def flops_model(n, f, P, ng_list, counts, schur):
-    """algorithmic FP64 flops of what was executed (counted by the kernels), SURVEY.md 8d / DESIGN.md 5:
-    K_inv n^3 (chol + triangular inverse + L^-T L^-1) -- uniform grid with even n >= 64: two n/2 inverses through the
-    centrosymmetric split, n^3/4; function draw n^3/3 + 6 n^2 (chol, forward + 2 back solves);
+    """algorithmic FP64 flops of what was executed (counted by the kernels), DESIGN.md 5:
+    factor of K_o = K + 1e-9 I per (prior group, chain, sweep) and factor of C = I + c K_o per class of functions: n^3/3
+    each -- on a uniform grid with even n >= 64 two n/2 blocks through the centrosymmetric split, n^3/12;
+    per function draw two triangular solves (the forward one rides along the factorisation) and three triangular
+    products: 5 n^2 (split: 2.5 n^2);  K_inv operator (not on the sweep path): n^3 (split: n^3/4);
     slice factorisation: dense n^3/3 + |g| n^2, or -- uniform grid, Schur algorithm -- (3 + |g|) n^2."""
     n3 = float(n) ** 3
-    inv = counts["inverses"] * (n3 / 4 if (schur and n % 2 == 0 and n >= 64) else n3)
+    split = schur and n % 2 == 0 and n >= 64
+    per_fact = n3 / 12 if split else n3 / 3
+    bfact = counts.get("ko_factor", 0)
     fchol = counts.get("function_chol", counts["draws"])       # functions with identical conditional precision share one
-    draws = fchol * n3 / 3 + counts["draws"] * 6.0 * n * n
-    prior_facts = counts["chol"] - counts["inverses"] - fchol - (counts["jitter"] if fchol == counts["draws"] else 0)
+    inv = counts["inverses"] * (n3 / 4 if split else n3)
+    draws = (bfact + fchol) * per_fact + counts["draws"] * (2.5 if split else 5.0) * n * n
+    prior_facts = counts["chol"] - counts["inverses"] - fchol - bfact
     gbar = float(np.mean(ng_list))
     per = (3.0 + gbar) * n * n if schur else (n3 / 3 + gbar * n * n)
     return {"kinv": inv, "function": draws, "prior_slice": prior_facts * per, "prior_factorisations": prior_facts,
@@ -325,21 +336,21 @@ def main():
     schur = bool(np.allclose(np.diff(x[:, 0]), np.diff(x[:, 0])[0], rtol=0, atol=1e-13)) and x.shape[1] == 1
     fm = flops_model(n, f, P, [len(g) for g in groups], counts_prof, schur)
     fm_timed = flops_model(n, f, P, [len(g) for g in groups], counts, schur)
-    kern = {"kinv": ("k_group_kinv (Kernel.K_inv of every prior group: RBF build + jitchol + in-place inverse; centrosymmetric split on uniform grids)", args.steps),
-            "function": ("k_function (Function._sample: residual projection, jitchol(A), solves, Philox draw; one launch per sweep for balanced designs)", args.steps),
+    kern = {"kinv": ("k_group_factor (jitchol(K + 1e-9 I) of every prior group; only launched by sequential sweeps)", args.steps),
+            "function": ("k_group_fused (all Function._sample draws of a sweep, one (prior group, chain) item per CTA: RBF build + "
+                         "jitchol(K_o) + per class jitchol(I + c K_o) with the right-hand sides riding along, solves, Philox draws; "
+                         "centrosymmetric split: half-size blocks)", args.steps),
             "prior_slice": ("k_prior_schur (sigma+lengthscale slice steps: Toeplitz/Schur GP log-likelihood)" if schur else
                             "k_prior (sigma+lengthscale slice steps: dense GP log-likelihood)", P * args.steps)}
     dom = max(("kinv", "function", "prior_slice"), key=lambda k: prof[k])
     tf = {k: (fm[k] / (prof[k] * 1e-3) / 1e12 if prof[k] > 0 else 0.0) for k in kern}
     roofline = {"bound": "tensor", "kernel": kern[dom][0], "achieved": tf[dom], "peak": peak, "unit": "TFLOP/s",
                 "frac": tf[dom] / peak,
-                "traffic": ncu_traffic({"function": "ncu_r01_final_k_function_class.txt",
-                                        "kinv": "ncu_r01_final_k_group_kinv.txt"}.get(dom, ""), n, C),
-                "traffic_note": "bytes per launch from profiles/ncu_r01_final_*.txt (one ncu --set full capture of this "
-                                "workload); the kernel is FP64-tensor bound, its algorithmic HBM bytes are the K_inv tiles "
-                                "read once per factorisation (%.1f GB per launch) -- the rest is workspace traffic that "
-                                "falls out of L2" % (counts_prof.get("function_chol", 0) / max(1, args.steps) *
-                                                   (n // 32) * (n // 32 + 1) / 2 * 8192 / 1e9),
+                "traffic": ncu_traffic({"function": "ncu_r02_k_group_fused.txt"}.get(dom, ""), n, C),
+                "traffic_note": "bytes per launch from profiles/ncu_r02_*.txt (one ncu --set full capture of this workload); "
+                                "the kernel is FP64-tensor/latency bound: its algorithmic HBM bytes are the function values it "
+                                "writes (%.0f MB per launch) plus the shared L2-resident inputs; matrices never leave the "
+                                "CTA's L2-resident workspace" % (C * f * n * 8 / 1e6),
                 "peak_source": peak_src,
                 "flops_per_launch": fm[dom] / kern[dom][1], "ms_per_launch": prof[dom] / kern[dom][1],
                 "share_of_step": prof[dom] / prof["total"] if prof["total"] else None,
@@ -348,11 +359,11 @@ def main():
                 "whole_step": {"achieved": fm_timed["total"] / (dev_ms * 1e-3) / 1e12,
                                "frac": fm_timed["total"] / (dev_ms * 1e-3) / 1e12 / peak,
                                "note": "algorithmic flops of the executed algorithm (Schur slices are O(n^2), "
-                                       "centrosymmetric K_inv is n^3/4)",
+                                       "split factorisations are n^3/12, no inverse is formed)",
                                # SURVEY 8(d)'s work model of the reference's dense algorithm for the same sweeps:
                                # P n^3 + f (n^3/3 + 6 n^2) + (n^3/3) * (slice factorisations), per chain and sweep
                                "reference_algorithm_tflops": (
-                                   (counts["inverses"] * float(n) ** 3 + counts["draws"] * (float(n) ** 3 / 3 + 6.0 * n * n) +
+                                   (counts.get("ko_factor", 0) * float(n) ** 3 + counts["draws"] * (float(n) ** 3 / 3 + 6.0 * n * n) +
                                     fm_timed["prior_factorisations"] * float(n) ** 3 / 3) / (dev_ms * 1e-3) / 1e12)},
                 "counted": {"factorisations_per_sweep_per_chain": counts["chol"] / (C * args.steps),
                             "logp_evals_per_slice_step": counts["logp"] / max(1, counts["slice_steps"]),

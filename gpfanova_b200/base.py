@@ -259,13 +259,25 @@ class Base(SamplerContainer):
 
     def _device_function_step(self, f, z=None, want_conditional=False):
         eng = self._push_state()
-        zz = None if z is None else np.broadcast_to(np.asarray(z, dtype=float), (self.chains, self.n))
-        out = eng.function_step(f, sweep=self._next_manual_sweep(), z=zz, want=("mu", "LA") if want_conditional else ())
+        zz = None if z is None else np.broadcast_to(np.asarray(z, dtype=float), (self.chains, 2 * self.n))
+        out = eng.function_step(f, sweep=self._next_manual_sweep(), z=zz, want=("mu", "LC", "nt") if want_conditional else ())
         eng.status()
         self._pull_state()
         if want_conditional:
-            return out["mu"][0].cpu().numpy(), out["LA"][0].cpu().numpy()
+            return self._conditional_from_device(f, out)
         return self._F[0, f].copy()
+
+    def _conditional_from_device(self, f, out):
+        """(mu, Sigma) of function f's conditional (chain 0) from the device quantities: Sigma = K_o - W^T W with
+        W = L_C^-1 S K_o (C = I + S K_o S, S = sqrt(n_t / (sigma_y + 1e-9)), K_o = K + 1e-9 I)"""
+        mu = out["mu"][0].cpu().numpy()
+        LC = out["LC"][0]
+        nt = out["nt"][0]
+        yinv = 1.0 / (pow(10.0, float(self._hyper[0, 0])) + self.offset())
+        Ko = torch.as_tensor(self.kernels[self.functionPrior(f)].K(self.x) + self.offset() * np.eye(self.n)).to(LC.device)
+        sd = torch.sqrt(nt * yinv)
+        Wm = torch.linalg.solve_triangular(LC, sd[:, None] * Ko, upper=False)
+        return mu, (Ko - Wm.T @ Wm).cpu().numpy()
 
     def _device_slice_step(self, h, x):
         self.parameter_cache[self._hyper_names[h]] = x

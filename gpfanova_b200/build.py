@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libgpfanova_b200.so")
 SOURCES = ["gpf_api.cu"]
-DEPS = ["gpf_api.cu", "gpf_kernels.cuh", "gpf_common.cuh", "gpf_tile.cuh", "gpf_philox.cuh"]
+DEPS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh")))     # every source under csrc/
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-extended-lambda", "-Xcompiler", "-fPIC", "-shared"]
 

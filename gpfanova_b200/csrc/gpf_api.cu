@@ -12,6 +12,7 @@
 
 #include "../../include/gpfanova_b200.h"
 #include "gpf_kernels.cuh"
+#include "gpf_cond.cuh"
 #include "gpf_schur.cuh"
 
 using namespace gpf;
@@ -43,18 +44,19 @@ struct gpf_ctx {
   std::vector<int> group_of_fn;
   std::vector<std::vector<int>> groups;
   std::vector<Samp> order;
-  std::vector<char> kinv_valid;
+  std::vector<char> lb_valid;         // per group: c.LB holds jitchol(K_g + offset I) at the current hyper-parameters
   bool toeplitz = false;
   bool centro_ok = false;
-  bool cls_big = false;               // some class has three or more functions: batched draws
   const double* d_bhat = nullptr;     // least-squares functions for the observation likelihood (balanced designs)
   bool indep = false;                 // X^T X diagonal and nothing missing: function draws of a sweep are independent
   int* d_fn_all = nullptr;            // all functions in sampler order / their sampler ids (device)
   unsigned* d_sid_all = nullptr;
   int ncls = 0;                       // classes of functions sharing their conditional precision (indep designs)
-  bool cls_shared = false;            // some class has more than one function
-  int *d_cls_off = nullptr, *d_cls_fn = nullptr;
+  int rb = 8;                         // right-hand-side rows per factorisation pass of the fused kernel (8 or 32)
+  int *d_cls_off = nullptr, *d_cls_fn = nullptr, *d_gcls_off = nullptr, *d_gorder = nullptr;
+  int *d_cls1_off = nullptr, *d_gcls1_off = nullptr;   // option 2 = 0: every function its own class
   unsigned* d_cls_sid = nullptr;
+  double* d_kinv_tmp = nullptr;       // scratch of the K_inv operator (gpf_group_kinv with an output buffer)
   std::vector<int> schur_warps;       // per group: warps per CTA of the Schur slice kernel (0: dense engine)
   int use_schur = 1;
   int batch = 1;                       // batch independent function draws / K_inv of all groups into one launch
@@ -65,7 +67,7 @@ struct gpf_ctx {
   cudaStream_t copy = nullptr;         // device -> host history copies run beside the kernels of the next sweeps
   cudaEvent_t ev_copy = nullptr;
   std::vector<void*> allocs;
-  size_t smem_kinv = 0, smem_kinv2 = 0, smem_fn = 0;
+  size_t smem_kinv = 0, smem_kinv2 = 0, smem_fn[3] = {0, 0, 0}, smem_fact[3] = {0, 0, 0}, smem_fused[3] = {0, 0, 0};
   std::vector<size_t> smem_prior;
   unsigned long long launches = 0;
   int profile = 0;                     // 0 off, 1 per-kernel + total CUDA-event timing, 2 total only
@@ -142,54 +144,79 @@ int dev_alloc(gpf_ctx* c, T** p, size_t count) {
   return GPF_OK;
 }
 
-int launch_kinv(gpf_ctx* c, int g, int count = 1) {
+int mode_of(const gpf_ctx* c) { return c->dev.centro ? 2 : (c->toeplitz ? 1 : 0); }
+
+// Kernel.K_inv of group g into the scratch buffer (inspection operator; the sweep itself never forms K_inv)
+int launch_kinv(gpf_ctx* c, int g) {
+  Timer t(c, 1);
+  const size_t tstride = (size_t)plt_tiles(c->dev.NT) * TILE;
+  if (!c->d_kinv_tmp) {
+    void* q = nullptr;
+    CK(c, cudaMalloc(&q, (size_t)c->dev.C * tstride * sizeof(double)));
+    c->allocs.push_back(q);
+    c->d_kinv_tmp = (double*)q;
+  }
+  CtxDev dev = c->dev;
+  dev.Kinv = c->d_kinv_tmp - (size_t)g * c->dev.C * tstride;     // the kernel indexes (group, chain)
+  CK(c, cudaMemsetAsync(c->dev.sched, 0, sizeof(int), c->stream));
+  const int grid = std::min(c->dev.C, 2 * c->sms);
+  if (c->dev.centro) k_group_kinv<2><<<grid, NTHR, c->smem_kinv2, c->stream>>>(dev, g, 1);
+  else if (c->toeplitz) k_group_kinv<1><<<grid, NTHR, c->smem_kinv, c->stream>>>(dev, g, 1);
+  else k_group_kinv<0><<<grid, NTHR, c->smem_kinv, c->stream>>>(dev, g, 1);
+  ++c->launches;
+  CK(c, cudaGetLastError());
+  return GPF_OK;
+}
+
+// jitchol(K_g + offset I) of groups g .. g+count-1 into c.LB (sequential sweeps: the function steps read it)
+int launch_factor(gpf_ctx* c, int g, int count = 1) {
   Timer t(c, 1);
   CK(c, cudaMemsetAsync(c->dev.sched, 0, sizeof(int), c->stream));
   const int grid = std::min(c->dev.C * count, 2 * c->sms);
-  if (c->dev.centro) k_group_kinv<2><<<grid, NTHR, c->smem_kinv2, c->stream>>>(c->dev, g, count);
-  else if (c->toeplitz) k_group_kinv<1><<<grid, NTHR, c->smem_kinv, c->stream>>>(c->dev, g, count);
-  else k_group_kinv<0><<<grid, NTHR, c->smem_kinv, c->stream>>>(c->dev, g, count);
+  const int mode = mode_of(c);
+  if (mode == 2) k_group_factor<2><<<grid, NTHR, c->smem_fact[2], c->stream>>>(c->dev, g, count);
+  else if (mode == 1) k_group_factor<1><<<grid, NTHR, c->smem_fact[1], c->stream>>>(c->dev, g, count);
+  else k_group_factor<0><<<grid, NTHR, c->smem_fact[0], c->stream>>>(c->dev, g, count);
   ++c->launches;
   CK(c, cudaGetLastError());
-  for (int q = g; q < g + count; ++q) c->kinv_valid[q] = 1;
+  for (int q = g; q < g + count; ++q) c->lb_valid[q] = 1;
+  return GPF_OK;
+}
+
+int launch_function_kernel(gpf_ctx* c, int grid, int fn, unsigned sid, const int* fl, const unsigned* sl, int nfn, unsigned sweep,
+                           const double* z, FnOut out) {
+  const int mode = mode_of(c);
+  if (mode == 2) k_function<2><<<grid, NTHR, c->smem_fn[2], c->stream>>>(c->dev, fn, sid, fl, sl, nfn, sweep, z, out);
+  else if (mode == 1) k_function<1><<<grid, NTHR, c->smem_fn[1], c->stream>>>(c->dev, fn, sid, fl, sl, nfn, sweep, z, out);
+  else k_function<0><<<grid, NTHR, c->smem_fn[0], c->stream>>>(c->dev, fn, sid, fl, sl, nfn, sweep, z, out);
+  ++c->launches;
+  CK(c, cudaGetLastError());
   return GPF_OK;
 }
 
 int launch_function(gpf_ctx* c, int fn, unsigned sampler_id, unsigned sweep, const double* z, FnOut out) {
   const int g = c->group_of_fn[fn];
-  if (!c->kinv_valid[g]) {
-    int rc = launch_kinv(c, g);
+  if (!c->lb_valid[g]) {
+    int rc = launch_factor(c, g);
     if (rc) return rc;
   }
   Timer t(c, 2);
   CK(c, cudaMemsetAsync(c->dev.sched, 0, sizeof(int), c->stream));
-  k_function<<<c->grid, NTHR, c->smem_fn, c->stream>>>(c->dev, fn, sampler_id, nullptr, nullptr, 1, sweep, z, out);
-  ++c->launches;
-  CK(c, cudaGetLastError());
-  return GPF_OK;
+  return launch_function_kernel(c, c->grid, fn, sampler_id, nullptr, nullptr, 1, sweep, z, out);
 }
 
-// every function of the model in one launch (only when the draws are independent of each other, c->indep)
+// every function of the model in one launch (only when the draws are independent of each other, c->indep):
+// one item per (prior group, chain) -- factor of K_o, then the group's classes (k_group_fused)
 int launch_all_functions(gpf_ctx* c, unsigned sweep) {
-  bool all_valid = true;
-  for (char v : c->kinv_valid) all_valid = all_valid && v;
-  if (!all_valid) {
-    int rc = launch_kinv(c, 0, c->dev.P);
-    if (rc) return rc;
-  }
   Timer t(c, 2);
   CK(c, cudaMemsetAsync(c->dev.sched, 0, sizeof(int), c->stream));
-  if (c->cls_shared && c->share) {   // functions with identical conditional precision share one factorisation
-    const int grid = std::min(c->dev.C * c->ncls, 2 * c->sms);
-    if (c->cls_big) k_function_class<true><<<grid, NTHR, c->smem_fn, c->stream>>>(c->dev, c->d_cls_off, c->d_cls_fn, c->d_cls_sid, c->ncls, sweep);
-    else k_function_class<false><<<grid, NTHR, c->smem_fn, c->stream>>>(c->dev, c->d_cls_off, c->d_cls_fn, c->d_cls_sid, c->ncls, sweep);
-    ++c->launches;
-    CK(c, cudaGetLastError());
-    return GPF_OK;
-  }
-  const int grid = std::min(c->dev.C * c->dev.f, 2 * c->sms);
-  k_function<<<grid, NTHR, c->smem_fn, c->stream>>>(c->dev, 0, 0u, c->d_fn_all, c->d_sid_all, c->dev.f, sweep, nullptr,
-                                                    FnOut{nullptr, nullptr, nullptr, nullptr});
+  const int grid = std::min(c->dev.C * c->dev.P, 2 * c->sms);
+  FusedArgs a{c->d_gorder, c->share ? c->d_gcls_off : c->d_gcls1_off, c->share ? c->d_cls_off : c->d_cls1_off, c->d_cls_fn,
+              c->d_cls_sid, sweep, c->rb};
+  const int mode = mode_of(c);
+  if (mode == 2) k_group_fused<2><<<grid, NTHR, c->smem_fused[2], c->stream>>>(c->dev, a);
+  else if (mode == 1) k_group_fused<1><<<grid, NTHR, c->smem_fused[1], c->stream>>>(c->dev, a);
+  else k_group_fused<0><<<grid, NTHR, c->smem_fused[0], c->stream>>>(c->dev, a);
   ++c->launches;
   CK(c, cudaGetLastError());
   return GPF_OK;
@@ -228,7 +255,7 @@ int launch_prior(gpf_ctx* c, int g, int mode, const double* cand, double* outv, 
   else k_prior<false><<<c->grid, NTHR, c->smem_prior[g], st>>>(dev, a);
   ++c->launches;
   CK(c, cudaGetLastError());
-  if (mode >= 2) c->kinv_valid[g] = 0;
+  if (mode >= 2) c->lb_valid[g] = 0;
   return GPF_OK;
 }
 
@@ -372,14 +399,88 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
     ngmax = std::max(ngmax, (int)c->groups[g].size());
   }
   v.NEmax = (ngmax + TB - 1) / TB;
-  c->kinv_valid.assign(d->P, 0);
+  c->lb_valid.assign(d->P, 0);
+  // uniform grid?  then every RBF matrix is Toeplitz: K[i][j] = k(|i-j| h) and needs one exp per lag
+  std::vector<double> d2(d->n, 0.0);
+  c->toeplitz = false;
+  if (d->p == 1) {
+    const long double x0 = d->h_x[0], h = d->n > 1 ? ((long double)d->h_x[d->n - 1] - x0) / (d->n - 1) : 0.0L;
+    const double tol = 1e-14 * (std::fabs(d->h_x[0]) + std::fabs(d->h_x[d->n - 1]));
+    bool uni = true;
+    for (int i = 0; i < d->n && uni; ++i) uni = std::fabs((double)(x0 + i * h - (long double)d->h_x[i])) <= tol;
+    if (uni) {
+      c->toeplitz = true;
+      for (int k = 0; k < d->n; ++k) d2[k] = (double)((k * h) * (k * h));
+    }
+  }
+  // symmetric Toeplitz => centrosymmetric: everything n^3 runs on the two half-size blocks (n even; small n gains nothing)
+  c->centro_ok = c->toeplitz && d->n % 2 == 0 && d->n >= 64;
+  v.centro = c->centro_ok ? 1 : 0;
+  // X^T X (decides whether the function draws of a sweep are independent) and the classes of functions that share their
+  // conditional precision
+  std::vector<double> G((size_t)d->f * d->f, 0.0);
+  for (int a = 0; a < d->f; ++a)
+    for (int b = 0; b < d->f; ++b) {
+      double s = 0.0;
+      for (int o = 0; o < d->m; ++o) s += d->h_X[(size_t)o * d->f + a] * d->h_X[(size_t)o * d->f + b];
+      G[(size_t)a * d->f + b] = s;
+    }
+  bool nomiss = true;
+  for (size_t i = 0; i < (size_t)d->n * d->m; ++i) nomiss = nomiss && (d->h_y[i] == d->h_y[i]);
+  bool diag = true;
+  for (int a = 0; a < d->f; ++a) {
+    // a function no observation loads on (all-zero design column): rank deficient (base.py:42-44 logs it and draws from
+    // the prior); the least-squares shortcuts divide by (X^T X)[a,a], so such a design takes the general path
+    if (!(G[(size_t)a * d->f + a] > 0.0)) diag = false;
+    for (int b = 0; b < d->f; ++b)
+      // couplings below 1e-13 sqrt(G_aa G_bb) are rounding noise of the contrast construction (helmertConvert
+      // rescales the Helmert columns with square roots) and do not make the draws dependent
+      if (a != b && std::fabs(G[(size_t)a * d->f + b]) > 1e-13 * std::sqrt(G[(size_t)a * d->f + a] * G[(size_t)b * d->f + b])) diag = false;
+  }
+  c->indep = diag && nomiss;
+  // sampler ids of the functions, classes per group (same (X^T X)[f,f] within a group)
+  std::vector<int> fl, coff(1, 0), cfn, gcoff(1, 0), coff1(1, 0), gcoff1(1, 0);
+  std::vector<unsigned> sl, csid;
+  std::vector<unsigned> sid_of(d->f, 0u);
+  for (size_t i = 0; i < c->order.size(); ++i)
+    if (c->order[i].kind == 1) { fl.push_back(c->order[i].arg); sl.push_back((unsigned)i); sid_of[c->order[i].arg] = (unsigned)i; }
+  int maxcls = 1;
+  for (int g = 0; g < d->P; ++g) {
+    const std::vector<int>& grp = c->groups[g];
+    std::vector<char> used(grp.size(), 0);
+    for (size_t i = 0; i < grp.size(); ++i) {
+      if (used[i]) continue;
+      const double gi = G[(size_t)grp[i] * d->f + grp[i]];
+      int cnt = 0;
+      for (size_t j = i; j < grp.size(); ++j) {
+        if (used[j]) continue;
+        if (std::fabs(G[(size_t)grp[j] * d->f + grp[j]] - gi) > 1e-13 * gi) continue;
+        used[j] = 1; cfn.push_back(grp[j]); csid.push_back(sid_of[grp[j]]); ++cnt;
+        coff1.push_back((int)cfn.size());
+      }
+      coff.push_back((int)cfn.size());
+      maxcls = std::max(maxcls, cnt);
+    }
+    gcoff.push_back((int)coff.size() - 1);
+    gcoff1.push_back((int)coff1.size() - 1);
+  }
+  c->ncls = (int)coff.size() - 1;
+  c->rb = maxcls > 8 ? 32 : 8;
   // shared-memory budgets
   const size_t xsd = (size_t)d->n * d->p + d->n;
   c->smem_kinv = (engine_smem_doubles(v.NT, 0) + xsd) * sizeof(double);
   c->smem_kinv2 = (2 * engine_smem_doubles((d->n / 2 + TB - 1) / TB, 0) + xsd) * sizeof(double);   // centrosymmetric split
-  c->smem_fn = (engine_smem_doubles(v.NT, 1) + 3 * (size_t)v.NT * TB + NW * 2 * 32) * sizeof(double);
   c->smem_prior.resize(d->P);
-  size_t smax = std::max(std::max(c->smem_kinv, c->smem_kinv2), c->smem_fn);
+  size_t smax = std::max(c->smem_kinv, c->smem_kinv2);
+  for (int mode = 0; mode < 3; ++mode) {
+    if (mode == 2 && !c->centro_ok) continue;
+    if (mode == 1 && !c->toeplitz) continue;
+    const int nsub = mode == 2 ? 2 : 1, NTm = ((mode == 2 ? d->n / 2 : d->n) + TB - 1) / TB;
+    c->smem_fn[mode] = function_smem_doubles(d->n, d->p, v.NT, mode) * sizeof(double);
+    c->smem_fact[mode] = ((size_t)nsub * engine_smem_doubles(NTm, 0) + xsd) * sizeof(double);
+    c->smem_fused[mode] = fused_smem_doubles(d->n, d->p, mode, c->rb) * sizeof(double);
+    smax = std::max(smax, std::max(c->smem_fn[mode], std::max(c->smem_fact[mode], c->indep ? c->smem_fused[mode] : (size_t)0)));
+  }
   for (int g = 0; g < d->P; ++g) {
     const int NE = ((int)c->groups[g].size() + TB - 1) / TB;
     c->smem_prior[g] = (engine_smem_doubles(v.NT, NE) + xsd) * sizeof(double);
@@ -400,9 +501,15 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
     cudaError_t e = allow_smem(k_group_kinv<0>, c->smem_kinv);
     if (e == cudaSuccess) e = allow_smem(k_group_kinv<1>, c->smem_kinv);
     if (e == cudaSuccess) e = allow_smem(k_group_kinv<2>, c->smem_kinv2);
-    if (e == cudaSuccess) e = allow_smem(k_function, c->smem_fn);
-    if (e == cudaSuccess) e = allow_smem(k_function_class<false>, c->smem_fn);
-    if (e == cudaSuccess) e = allow_smem(k_function_class<true>, c->smem_fn);
+    if (e == cudaSuccess) e = allow_smem(k_function<0>, c->smem_fn[0]);
+    if (e == cudaSuccess) e = allow_smem(k_function<1>, c->smem_fn[1]);
+    if (e == cudaSuccess) e = allow_smem(k_function<2>, c->smem_fn[2]);
+    if (e == cudaSuccess) e = allow_smem(k_group_factor<0>, c->smem_fact[0]);
+    if (e == cudaSuccess) e = allow_smem(k_group_factor<1>, c->smem_fact[1]);
+    if (e == cudaSuccess) e = allow_smem(k_group_factor<2>, c->smem_fact[2]);
+    if (e == cudaSuccess) e = allow_smem(k_group_fused<0>, c->smem_fused[0]);
+    if (e == cudaSuccess) e = allow_smem(k_group_fused<1>, c->smem_fused[1]);
+    if (e == cudaSuccess) e = allow_smem(k_group_fused<2>, c->smem_fused[2]);
     if (e == cudaSuccess) e = allow_smem(k_prior<true>, sp);
     if (e == cudaSuccess) e = allow_smem(k_prior<false>, sp);
     if (e == cudaSuccess) e = allow_smem(k_prior_schur<0>, 112 * 1024);
@@ -412,46 +519,35 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
   const int ws_ctas = 2 * c->sms;     // batched launches (several functions / groups per launch) may fill the GPU even for small C
   // device buffers
   const size_t tstride = (size_t)plt_tiles(v.NT) * TILE;
-  v.ws_stride = tstride + (size_t)v.NEmax * v.NT * TILE;
-  double *dx, *dyT, *dX, *dF, *dh, *dK, *dws, *dd2, *dG, *dZ;
+  const int NTh = (d->n / 2 + TB - 1) / TB;
+  const size_t hstride2 = 2 * (size_t)plt_tiles(NTh) * TILE;                      // the two half-size factors
+  v.lb_stride = c->centro_ok ? std::max(tstride, hstride2) : tstride;
+  // per-CTA workspace: dense slice kernel / general function kernel (matrix + right-hand-side tile rows), fused kernel
+  // (factor(s) of K_o, factor(s) of C, one right-hand-side tile row each)
+  v.ws_stride = tstride + (size_t)std::max(v.NEmax, 1) * v.NT * TILE;
+  v.ws_stride = std::max(v.ws_stride, 2 * tstride + (size_t)v.NT * TILE);
+  if (c->centro_ok) v.ws_stride = std::max(v.ws_stride, 2 * hstride2 + 2 * (size_t)NTh * TILE);
+  v.fws_stride = 2 * (size_t)c->rb * std::max((size_t)v.NT * TB, (size_t)2 * NTh * TB);
+  double *dx, *dyT, *dX, *dF, *dh, *dLB, *dBj, *dws, *dd2, *dG, *dZ, *dfws;
   unsigned char* dfull;
   int *dgof, *dgf, *dgo, *dst, *dsched;
   unsigned long long* dcn;
   int rc;
   if ((rc = dev_alloc(c, &dx, (size_t)d->n * d->p)) || (rc = dev_alloc(c, &dyT, (size_t)d->n * d->m)) ||
       (rc = dev_alloc(c, &dX, (size_t)d->m * d->f)) || (rc = dev_alloc(c, &dF, (size_t)v.C * d->f * d->n)) ||
-      (rc = dev_alloc(c, &dh, (size_t)v.C * v.H)) || (rc = dev_alloc(c, &dK, (size_t)d->P * v.C * tstride)) ||
+      (rc = dev_alloc(c, &dh, (size_t)v.C * v.H)) || (rc = dev_alloc(c, &dLB, (size_t)d->P * v.C * v.lb_stride)) ||
+      (rc = dev_alloc(c, &dBj, (size_t)d->P * v.C)) ||
       (rc = dev_alloc(c, &dws, (size_t)ws_ctas * v.ws_stride)) || (rc = dev_alloc(c, &dgof, (size_t)d->f)) ||
       (rc = dev_alloc(c, &dgf, (size_t)d->f)) || (rc = dev_alloc(c, &dgo, (size_t)d->P + 1)) ||
       (rc = dev_alloc(c, &dst, (size_t)v.C)) || (rc = dev_alloc(c, &dcn, (size_t)CNT_N)) ||
       (rc = dev_alloc(c, &dsched, (size_t)8)) || (rc = dev_alloc(c, &dd2, (size_t)d->n)) || (rc = dev_alloc(c, &dG, (size_t)d->f * d->f)) ||
-      (rc = dev_alloc(c, &dZ, (size_t)d->f * d->n)) || (rc = dev_alloc(c, &dfull, (size_t)d->n)))
+      (rc = dev_alloc(c, &dZ, (size_t)d->f * d->n)) || (rc = dev_alloc(c, &dfull, (size_t)d->n)) ||
+      (rc = dev_alloc(c, &dfws, (size_t)ws_ctas * v.fws_stride)))
     return fail(rc);
-  // uniform grid?  then every RBF matrix is Toeplitz: K[i][j] = k(|i-j| h) and needs one exp per lag
-  std::vector<double> d2(d->n, 0.0);
-  c->toeplitz = false;
-  if (d->p == 1) {
-    const long double x0 = d->h_x[0], h = d->n > 1 ? ((long double)d->h_x[d->n - 1] - x0) / (d->n - 1) : 0.0L;
-    const double tol = 1e-14 * (std::fabs(d->h_x[0]) + std::fabs(d->h_x[d->n - 1]));
-    bool uni = true;
-    for (int i = 0; i < d->n && uni; ++i) uni = std::fabs((double)(x0 + i * h - (long double)d->h_x[i])) <= tol;
-    if (uni) {
-      c->toeplitz = true;
-      for (int k = 0; k < d->n; ++k) d2[k] = (double)((k * h) * (k * h));
-    }
-  }
-  // symmetric Toeplitz => centrosymmetric: K_inv from two half-size inverses (n even; small n gains nothing)
-  c->centro_ok = c->toeplitz && d->n % 2 == 0 && d->n >= 64;
-  v.centro = c->centro_ok ? 1 : 0;
-  // X^T X, X^T y (observed entries) and the per-time-point "nothing missing" flag for the residual projection
-  std::vector<double> G((size_t)d->f * d->f, 0.0), Z((size_t)d->f * d->n, 0.0);
+  v.fws = dfws;
+  // X^T y (observed entries) and the per-time-point "nothing missing" flag for the residual projection
+  std::vector<double> Z((size_t)d->f * d->n, 0.0);
   std::vector<unsigned char> full(d->n, 1);
-  for (int a = 0; a < d->f; ++a)
-    for (int b = 0; b < d->f; ++b) {
-      double s = 0.0;
-      for (int o = 0; o < d->m; ++o) s += d->h_X[(size_t)o * d->f + a] * d->h_X[(size_t)o * d->f + b];
-      G[(size_t)a * d->f + b] = s;
-    }
   for (int t = 0; t < d->n; ++t)
     for (int o = 0; o < d->m; ++o) {
       const double yv = d->h_y[(size_t)t * d->m + o];
@@ -467,17 +563,9 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
     go.push_back((int)gf.size());
   }
   {
-    bool diag = true, nomiss = true;
-    for (int a = 0; a < d->f; ++a)
-      for (int b = 0; b < d->f; ++b)
-        // couplings below 1e-13 sqrt(G_aa G_bb) are rounding noise of the contrast construction (helmertConvert
-        // rescales the Helmert columns with square roots) and do not make the draws dependent
-        if (a != b && std::fabs(G[(size_t)a * d->f + b]) > 1e-13 * std::sqrt(G[(size_t)a * d->f + a] * G[(size_t)b * d->f + b])) diag = false;
-    for (unsigned char u : full) nomiss = nomiss && u;
-    c->indep = diag && nomiss;
     v.bhat = nullptr;
     v.rss0 = 0.0;
-    if (c->indep) {   // observation likelihood about the least-squares fit (k_obs)
+    if (c->indep) {   // least-squares functions: observation likelihood about the fit (k_obs), right-hand sides of the fused kernel
       std::vector<double> bh((size_t)d->f * d->n);
       for (int a = 0; a < d->f; ++a)
         for (int t = 0; t < d->n; ++t) bh[(size_t)a * d->n + t] = Z[(size_t)a * d->n + t] / G[(size_t)a * d->f + a];
@@ -496,42 +584,25 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
       c->d_bhat = dbh;
       v.rss0 = (double)rss;
     }
-    std::vector<int> fl;
-    std::vector<unsigned> sl;
-    for (size_t i = 0; i < c->order.size(); ++i)
-      if (c->order[i].kind == 1) { fl.push_back(c->order[i].arg); sl.push_back((unsigned)i); }
-    if ((rc = dev_alloc(c, &c->d_fn_all, fl.size())) || (rc = dev_alloc(c, &c->d_sid_all, sl.size()))) return fail(rc);
+    // groups ordered by descending work for the fused kernel's dynamic hand-out (largest items first)
+    std::vector<int> gorder(d->P);
+    for (int g = 0; g < d->P; ++g) gorder[g] = g;
+    std::stable_sort(gorder.begin(), gorder.end(), [&](int a, int b) { return c->groups[a].size() > c->groups[b].size(); });
+    if ((rc = dev_alloc(c, &c->d_fn_all, fl.size())) || (rc = dev_alloc(c, &c->d_sid_all, sl.size())) ||
+        (rc = dev_alloc(c, &c->d_cls_off, coff.size())) || (rc = dev_alloc(c, &c->d_cls_fn, cfn.size())) ||
+        (rc = dev_alloc(c, &c->d_cls_sid, csid.size())) || (rc = dev_alloc(c, &c->d_gcls_off, gcoff.size())) ||
+        (rc = dev_alloc(c, &c->d_cls1_off, coff1.size())) || (rc = dev_alloc(c, &c->d_gcls1_off, gcoff1.size())) ||
+        (rc = dev_alloc(c, &c->d_gorder, gorder.size())))
+      return fail(rc);
     cudaMemcpy(c->d_fn_all, fl.data(), sizeof(int) * fl.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(c->d_sid_all, sl.data(), sizeof(unsigned) * sl.size(), cudaMemcpyHostToDevice);
-    // classes: functions of one group with the same (X^T X)[f,f] (only meaningful when the draws are independent)
-    std::vector<int> coff(1, 0), cfn;
-    std::vector<unsigned> csid;
-    if (c->indep) {
-      std::vector<char> used(fl.size(), 0);
-      for (size_t i = 0; i < fl.size(); ++i) {
-        if (used[i]) continue;
-        int cnt = 0;
-        for (size_t j = i; j < fl.size(); ++j) {
-          if (used[j] || c->group_of_fn[fl[j]] != c->group_of_fn[fl[i]]) continue;
-          if (std::fabs(G[(size_t)fl[j] * d->f + fl[j]] - G[(size_t)fl[i] * d->f + fl[i]]) > 1e-13 * G[(size_t)fl[i] * d->f + fl[i]]) continue;
-          if (cnt == TB) { coff.push_back((int)cfn.size()); cnt = 0; }      // at most 32 functions per item
-          used[j] = 1; cfn.push_back(fl[j]); csid.push_back(sl[j]); ++cnt;
-          if (cnt > 1) c->cls_shared = true;
-          if (cnt > 2) c->cls_big = true;
-        }
-        coff.push_back((int)cfn.size());
-      }
-      c->ncls = (int)coff.size() - 1;
-      double* dfws;
-      if ((rc = dev_alloc(c, &c->d_cls_off, coff.size())) || (rc = dev_alloc(c, &c->d_cls_fn, cfn.size())) ||
-          (rc = dev_alloc(c, &c->d_cls_sid, csid.size())) ||
-          (rc = dev_alloc(c, &dfws, c->cls_shared ? (size_t)ws_ctas * 2 * TB * v.NT * TB : (size_t)1)))
-        return fail(rc);
-      v.fws = dfws;
-      cudaMemcpy(c->d_cls_off, coff.data(), sizeof(int) * coff.size(), cudaMemcpyHostToDevice);
-      cudaMemcpy(c->d_cls_fn, cfn.data(), sizeof(int) * cfn.size(), cudaMemcpyHostToDevice);
-      cudaMemcpy(c->d_cls_sid, csid.data(), sizeof(unsigned) * csid.size(), cudaMemcpyHostToDevice);
-    }
+    cudaMemcpy(c->d_cls_off, coff.data(), sizeof(int) * coff.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(c->d_cls_fn, cfn.data(), sizeof(int) * cfn.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(c->d_cls_sid, csid.data(), sizeof(unsigned) * csid.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(c->d_gcls_off, gcoff.data(), sizeof(int) * gcoff.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(c->d_cls1_off, coff1.data(), sizeof(int) * coff1.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(c->d_gcls1_off, gcoff1.data(), sizeof(int) * gcoff1.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(c->d_gorder, gorder.data(), sizeof(int) * gorder.size(), cudaMemcpyHostToDevice);
   }
   cudaError_t e = cudaMemcpy(dx, d->h_x, sizeof(double) * d->n * d->p, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(dyT, yT.data(), sizeof(double) * yT.size(), cudaMemcpyHostToDevice);
@@ -548,7 +619,7 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
   if (e == cudaSuccess) e = cudaMemset(dst, 0, sizeof(int) * v.C);
   if (e == cudaSuccess) e = cudaMemset(dcn, 0, sizeof(unsigned long long) * CNT_N);
   if (e != cudaSuccess) { c->err = std::string("gpf_create: upload: ") + cudaGetErrorString(e); return fail(GPF_ERR_CUDA); }
-  v.x = dx; v.yT = dyT; v.X = dX; v.F = dF; v.hyper = dh; v.Kinv = dK; v.ws = dws;
+  v.x = dx; v.yT = dyT; v.X = dX; v.F = dF; v.hyper = dh; v.Kinv = nullptr; v.LB = dLB; v.Bjit = dBj; v.ws = dws;
   v.sched = dsched;
   v.d2 = dd2; v.G = dG; v.Z = dZ; v.full = dfull;
   v.group_of_fn = dgof; v.group_fns = dgf; v.group_off = dgo; v.status = dst; v.counters = dcn;
@@ -591,7 +662,7 @@ int gpf_set_state(gpf_ctx* c, const double* h_F, const double* h_hyper) {
   if (h_F) CK(c, cudaMemcpyAsync(v.F, h_F, sizeof(double) * v.C * v.f * v.n, cudaMemcpyHostToDevice, c->stream));
   if (h_hyper) {
     CK(c, cudaMemcpyAsync(v.hyper, h_hyper, sizeof(double) * v.C * v.H, cudaMemcpyHostToDevice, c->stream));
-    std::fill(c->kinv_valid.begin(), c->kinv_valid.end(), 0);
+    std::fill(c->lb_valid.begin(), c->lb_valid.end(), 0);
   }
   CK(c, cudaStreamSynchronize(c->stream));
   return GPF_OK;
@@ -640,7 +711,7 @@ double* gpf_device_F(gpf_ctx* c) { return c->dev.F; }
 double* gpf_device_hyper(gpf_ctx* c) { return c->dev.hyper; }
 
 int gpf_invalidate(gpf_ctx* c) {   // call after writing gpf_device_hyper() directly
-  std::fill(c->kinv_valid.begin(), c->kinv_valid.end(), 0);
+  std::fill(c->lb_valid.begin(), c->lb_valid.end(), 0);
   return GPF_OK;
 }
 
@@ -673,14 +744,15 @@ int gpf_group_kinv(gpf_ctx* c, int g, double* d_out) {
   CK(c, cudaSetDevice(c->device));
   const CtxDev& v = c->dev;
   if (g < -1 || g >= v.P || (g < 0 && d_out)) { c->err = "gpf_group_kinv: bad group"; return GPF_ERR_ARG; }
-  for (int q = (g < 0 ? 0 : g); q < (g < 0 ? v.P : g + 1); ++q) {
-    int rc = launch_kinv(c, q);
-    if (rc) return rc;
-  }
+  // the factor of K_g + offset I that the function steps use (the sweep itself never forms the inverse) ...
+  int rc = (g < 0) ? launch_factor(c, 0, v.P) : launch_factor(c, g);
+  if (rc) return rc;
+  // ... and, on request, the inverse itself (Kernel.K_inv as an operator on the chains' current hyper-parameters)
   if (d_out) {
+    rc = launch_kinv(c, g);
+    if (rc) return rc;
     const size_t tstride = (size_t)plt_tiles(v.NT) * TILE;
-    k_tiles_to_dense<<<std::min(v.C, 1024), NTHR, 0, c->stream>>>(v.Kinv + (size_t)g * v.C * tstride, tstride, v.n, v.NT, v.C,
-                                                                d_out, 1);
+    k_tiles_to_dense<<<std::min(v.C, 1024), NTHR, 0, c->stream>>>(c->d_kinv_tmp, tstride, v.n, v.NT, v.C, d_out, 1);
     ++c->launches;
     CK(c, cudaGetLastError());
   }
@@ -688,10 +760,10 @@ int gpf_group_kinv(gpf_ctx* c, int g, double* d_out) {
 }
 
 int gpf_function_step(gpf_ctx* c, int fn, unsigned sampler_id, unsigned sweep, const double* d_z_inject, double* d_mu_out,
-                      double* d_LA_out, double* d_mt_out, double* d_nt_out) {
+                      double* d_LC_out, double* d_mt_out, double* d_nt_out) {
   CK(c, cudaSetDevice(c->device));
   if (fn < 0 || fn >= c->dev.f) { c->err = "gpf_function_step: bad function index"; return GPF_ERR_ARG; }
-  return launch_function(c, fn, sampler_id, sweep, d_z_inject, FnOut{d_mu_out, d_LA_out, d_mt_out, d_nt_out});
+  return launch_function(c, fn, sampler_id, sweep, d_z_inject, FnOut{d_mu_out, d_LC_out, d_mt_out, d_nt_out});
 }
 
 int gpf_obs_loglik(gpf_ctx* c, const double* d_cand, double* d_out) {
@@ -815,7 +887,7 @@ int gpf_set_option(gpf_ctx* c, int option, int value) {
   if (option == 2) { c->share = value; return GPF_OK; }
   if (option == 3) {   // centrosymmetric split of K_inv on uniform grids (on by default where it applies)
     c->dev.centro = (value && c->centro_ok) ? 1 : 0;
-    for (auto& q : c->kinv_valid) q = 0;
+    for (auto& q : c->lb_valid) q = 0;
     return GPF_OK;
   }
   if (option == 4) { c->dev.bhat = value ? c->d_bhat : nullptr; return GPF_OK; }

@@ -13,7 +13,7 @@ constexpr double LOG2PI = 1.8378770664093453;   // log(2 pi)
 constexpr double LN10 = 2.302585092994046;
 
 // counters (gpf_get_counters)
-enum { CNT_CHOL = 0, CNT_LOGP = 1, CNT_JITTER = 2, CNT_DRAW = 3, CNT_INV = 4, CNT_SLICE = 5, CNT_FNCHOL = 6, CNT_N = 8 };
+enum { CNT_CHOL = 0, CNT_LOGP = 1, CNT_JITTER = 2, CNT_DRAW = 3, CNT_INV = 4, CNT_SLICE = 5, CNT_FNCHOL = 6, CNT_BFACT = 7, CNT_N = 8 };
 
 // device view of one sampler context (passed by value to every kernel)
 struct CtxDev {
@@ -29,7 +29,11 @@ struct CtxDev {
   double* hyper;              // C x H
   int* status;                // C
   unsigned long long* counters;
-  double* Kinv;               // P x C x plt_tiles(NT) tiles
+  double* Kinv;               // C x plt_tiles(NT) tiles: scratch of the K_inv operator (gpf_group_kinv with output), else null
+  double* LB;                 // P x C x lb_stride: Cholesky factor(s) of K_g + offset I of every chain (sequential sweeps);
+                              // centro: the factors of the two half-size blocks, one after the other
+  size_t lb_stride;
+  double* Bjit;               // P x C: jitter the ladder of linalg.py:41-54 added to K_g + offset I
   double* ws;                 // per-CTA workspace, ws_stride doubles each
   size_t ws_stride;
   double offset, prior_jitter, prior_lb, prior_ub;
@@ -39,7 +43,8 @@ struct CtxDev {
   const double* Z;            // f x n   X^T y over the observed entries (NaN -> 0)
   const unsigned char* full;  // n       1 if no observation is missing at time t
   int* sched;                 // chain hand-out counter of the running launch (reset to 0 by the host before it)
-  double* fws;                // per-CTA scratch of the class-mode function kernel: 2 x 32 x NT*32 doubles each
+  double* fws;                // per-CTA scratch of the fused function kernel (right-hand-side rows): fws_stride doubles each
+  size_t fws_stride;
   const double* bhat;         // f x n  least-squares functions Z[f,t] / G[f,f] (balanced design, nothing missing), else null
   double rss0;                // sum of squared residuals of y about X bhat (host, extended precision)
 };
@@ -53,10 +58,20 @@ __device__ __forceinline__ int next_chain(int* sched, int* slot) {
   return *slot;
 }
 
+// per-chain status word: a negative code (not PD) wins over everything, the more severe (more negative) first; otherwise
+// the largest number of jitter retries.  Several CTAs (items of the same chain in one launch, concurrent slice kernels of
+// different groups) may report at once: compare-and-swap loop, no update is lost.
 __device__ __forceinline__ void status_merge(int* st, int code) {
-  const int old = *st;
-  if (code < 0) { if (old >= 0 || code < old) *st = code; }
-  else if (old >= 0 && code > old) *st = code;
+  int old = *reinterpret_cast<volatile int*>(st);
+  for (;;) {
+    int want;
+    if (code < 0) want = (old >= 0 || code < old) ? code : old;
+    else want = (old >= 0 && code > old) ? code : old;
+    if (want == old) return;
+    const int seen = atomicCAS(st, old, want);
+    if (seen == old) return;
+    old = seen;
+  }
 }
 
 // scaled inputs of RBF.dist (rbf.pyx:9-11): xs = x / lengthscale, xsq = sum(xs^2, 1)
@@ -175,6 +190,7 @@ struct SrcRbf {
   const double *xs, *xsq;
   int n, p;
   double sigma;
+  __device__ __forceinline__ double at(int R, int Cc) const { return rbf_elem(xs, xsq, n, p, sigma, R, Cc); }
   __device__ __forceinline__ void rows(double (&a)[32], int bi, int bj, int lane) const {
 #pragma unroll
     for (int c = 0; c < 32; ++c) a[c] = rbf_elem(xs, xsq, n, p, sigma, bi * TB + lane, bj * TB + c);

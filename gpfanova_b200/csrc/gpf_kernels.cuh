@@ -307,258 +307,6 @@ __global__ void __launch_bounds__(NTHR, 2) k_group_kinv(CtxDev c, int g_first, i
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Function._sample (sample/function.py:14-40) + base.functionResidual (base.py:180-190), fused:
-//   m_t, n_t  ->  A = K_inv + diag(n_t)/(sigma_y + offset), b = m_t/(sigma_y + offset)  ->  L_A = jitchol(A) with
-//   w = L_A^-1 b riding along  ->  mu = L_A^-T w, beta = L_A^-T (w + z)  (draw contract: beta = mu + L_A^-T z).
-// Residual projection: at time points where nothing is missing, m_t = (X^T y)[f,t] - sum_{q != f} (X^T X)[f,q] F_q(t)
-// and n_t = (X^T X)[f,f] (precomputed Z, G); time points with missing observations take the per-observation loop.
-// ---------------------------------------------------------------------------------------------------------
-struct FnOut { double *mu, *LA, *mt, *nt; };
-
-// fn_list / sid_list (nfn entries; nullptr: the single function fn_single): functions drawn by this launch.  Several
-// functions may share a launch only when their conditionals do not depend on each other (X^T X diagonal and nothing
-// missing -- decided by the host), items = (function, chain) pairs.
-__global__ void __launch_bounds__(NTHR, 2) k_function(CtxDev c, int fn_single, unsigned sid_single, const int* __restrict__ fn_list,
-                                                      const unsigned* __restrict__ sid_list, int nfn, unsigned sweep,
-                                                      const double* __restrict__ z_inject, FnOut out) {
-  const int NT = c.NT, n = c.n, npad = NT * TB;
-  EngineSmem sm(smem_base(), NT, 1);
-  double* xs = smem_base() + engine_smem_doubles(NT, 1);   // 2 x npad: w -> mu, w+z -> beta
-  double* brow = xs + 2 * npad;                            // npad
-  double* red = brow + npad;                               // NW*2*32
-  const size_t tstride = (size_t)plt_tiles(NT) * TILE;
-  double* W = c.ws + (size_t)blockIdx.x * c.ws_stride;
-  double* Wx = W + tstride;
-  const Stream rng{c.k0, c.k1};
-  __shared__ int s_chain;
-  for (int item = next_chain(c.sched, &s_chain); item < c.C * nfn; item = next_chain(c.sched, &s_chain)) {
-    const int ch = item % c.C;
-    const int fn = fn_list ? fn_list[item / c.C] : fn_single;
-    const unsigned sampler_id = sid_list ? sid_list[item / c.C] : sid_single;
-    const int g = c.group_of_fn[fn];
-    const double* Grow = c.G + (size_t)fn * c.f;
-    const double* Fc = c.F + (size_t)ch * c.f * n;
-    const double* A0 = c.Kinv + ((size_t)g * c.C + ch) * tstride;
-    const double yinv = 1.0 / (exp10(c.hyper[(size_t)ch * c.H]) + c.offset);   // white.py:7-9 through kernel.pyx:51-64
-    __syncthreads();
-    for (int t = threadIdx.x; t < npad; t += NTHR) {
-      double mt = 0.0, nt = 0.0;
-      if (t < n) {
-        if (c.full[t]) {
-          mt = c.Z[(size_t)fn * n + t];
-          for (int q = 0; q < c.f; ++q) {
-            const double gq = Grow[q];
-            if (q != fn && gq != 0.0) mt = fma(-gq, Fc[(size_t)q * n + t], mt);
-          }
-          nt = Grow[fn];
-        } else {
-          for (int o = 0; o < c.m; ++o) {
-            const double xf = c.X[o * c.f + fn];
-            if (xf == 0.0) continue;
-            const double yv = c.yT[(size_t)o * n + t];
-            if (isnan(yv)) continue;
-            double pred = 0.0;
-            for (int q = 0; q < c.f; ++q)
-              if (q != fn) pred = fma(c.X[o * c.f + q], Fc[(size_t)q * n + t], pred);
-            mt = fma(xf, yv - pred, mt);
-            nt = fma(xf, xf, nt);
-          }
-        }
-        if (out.mt) out.mt[(size_t)ch * n + t] = mt;
-        if (out.nt) out.nt[(size_t)ch * n + t] = nt;
-      }
-      sm.dvec[t] = (t < n) ? nt * yinv : 0.0;   // function.py:30
-      brow[t] = (t < n) ? yinv * mt : 0.0;      // function.py:32
-      xs[t] = 0.0;
-      xs[npad + t] = 0.0;
-    }
-    int tries = 0, code = 0;
-    double jitter = 0.0;
-    for (;;) {
-      __syncthreads();
-      EngineIO io{W, Wx, RowSrc{brow, nullptr, npad, 1, n}, xs, npad};
-      if (chol_engine<AUG_RHS, true>(SrcTiles{A0}, io, NT, 1, 1, sm)) { code = tries; break; }
-      // jitchol ladder on A (linalg.py:41-54)
-      if (tries == 0) {
-        double s = 0.0, bad = 0.0;
-        for (int t = threadIdx.x; t < n; t += NTHR) {
-          const double d = A0[(size_t)plt(t >> 5, t >> 5) * TILE + (t & 31) * TB + (t & 31)] + sm.dvec[t];
-          s += d;
-          if (d <= 0.0) bad += 1.0;
-        }
-        s = block_sum(s, sm.red());
-        bad = block_sum(bad, sm.red());
-        if (bad > 0.0) { code = GPF_STATUS_NONPOS_DIAG; break; }
-        jitter = s / n * 1e-6;
-        for (int t = threadIdx.x; t < n; t += NTHR) sm.dvec[t] += jitter;
-      } else {
-        for (int t = threadIdx.x; t < n; t += NTHR) sm.dvec[t] += 9.0 * jitter;
-        jitter *= 10.0;
-      }
-      ++tries;
-      if (tries > c.maxtries || !isfinite(jitter)) { code = GPF_STATUS_NOT_PD; break; }
-    }
-    __syncthreads();
-    if (code >= 0) {
-      // ---- z: injected or Philox Box-Muller (counter = (pair, sampler, sweep, chain)) ----
-      if (z_inject) {
-        for (int t = threadIdx.x; t < n; t += NTHR) xs[npad + t] = xs[t] + z_inject[(size_t)ch * n + t];
-      } else {
-        for (int pr = threadIdx.x; 2 * pr < n; pr += NTHR) {
-          double z0, z1;
-          rng.normal_pair((unsigned)(ch + c.chain_offset), sweep, sampler_id, (unsigned)pr, z0, z1);
-          xs[npad + 2 * pr] = xs[2 * pr] + z0;
-          if (2 * pr + 1 < n) xs[npad + 2 * pr + 1] = xs[2 * pr + 1] + z1;
-        }
-      }
-      __syncthreads();
-      back_solve<2>(W, NT, xs, npad, sm, red);
-      for (int t = threadIdx.x; t < n; t += NTHR) {
-        c.F[((size_t)ch * c.f + fn) * n + t] = xs[npad + t];
-        if (out.mu) out.mu[(size_t)ch * n + t] = xs[t];
-      }
-      if (out.LA) tiles_to_dense(W, n, NT, out.LA + (size_t)ch * n * n, 0);
-    }
-    if (threadIdx.x == 0) {
-      status_merge(c.status + ch, code);
-      atomicAdd(c.counters + CNT_CHOL, 1ull + (unsigned long long)tries);
-      atomicAdd(c.counters + CNT_DRAW, 1ull);
-      atomicAdd(c.counters + CNT_FNCHOL, 1ull + (unsigned long long)tries);
-      if (tries) atomicAdd(c.counters + CNT_JITTER, (unsigned long long)tries);
-    }
-  }
-}
-
-// draws of up to R functions of one class in one pass: beta_j = L_A^-T (w_j + z_j), the R right-hand sides solved together
-// (each tile of L_A is read once per R functions instead of once per function; per right-hand side the arithmetic and its
-// order are those of back_solve<2>, so the draws are bit-identical).  The right-hand sides live in the panel slots, which
-// the finished factorisation no longer needs.  Separate function: keeps the register allocation of the engine loops of
-// the calling kernel untouched.
-template <int R>
-__device__ __noinline__ void class_draw_batch(const CtxDev& c, const double* W, int NT, const EngineSmem& sm,
-                                              const double* __restrict__ wrow, const int* __restrict__ fns,
-                                              const unsigned* __restrict__ sids, int j0, int cnt, int ch, unsigned sweep) {
-  const int n = c.n, npad = NT * TB;
-  const Stream rng{c.k0, c.k1};
-  double* xs = sm.P;                                   // R x npad
-  __syncthreads();
-  for (int e = threadIdx.x; e < R * npad; e += NTHR) {
-    const int v = e / npad, t = e % npad;
-    xs[e] = (v < cnt && t < n) ? wrow[(size_t)(j0 + v) * npad + t] : 0.0;
-  }
-  __syncthreads();
-  for (int q = threadIdx.x; q < cnt * ((n + 1) / 2); q += NTHR) {
-    const int v = q / ((n + 1) / 2), pr = q % ((n + 1) / 2);
-    double z0, z1;
-    rng.normal_pair((unsigned)(ch + c.chain_offset), sweep, sids[j0 + v], (unsigned)pr, z0, z1);
-    xs[v * npad + 2 * pr] += z0;
-    if (2 * pr + 1 < n) xs[v * npad + 2 * pr + 1] += z1;
-  }
-  __syncthreads();
-  back_solve<R>(W, NT, xs, npad, sm, nullptr);
-  for (int e = threadIdx.x; e < cnt * n; e += NTHR) {
-    const int v = e / n, t = e % n;
-    c.F[((size_t)ch * c.f + fns[j0 + v]) * n + t] = xs[v * npad + t];
-  }
-  __syncthreads();
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// Function._sample for a CLASS of functions that share their conditional precision matrix.
-// In a balanced design with nothing missing, n_t = (X^T X)[f,f] for every t, so functions of one prior group with equal
-// (X^T X)[f,f] have the SAME  A = K_inv + n_f/(sigma_y + offset) I  (with helmertConvert=True: every function of a group,
-// e.g. 361 interaction functions of a 20 x 20 design).  One factorisation then serves the whole class: the functions'
-// right-hand sides b_f ride along as rows of one augmented tile row, and each function gets its own two back
-// substitutions (mu_f, beta_f = L_A^-T (w_f + z_f)).  Results are identical to the one-function kernel (same A, same
-// L_A, every row of the augmented block is solved independently of the others).
-// Items = (class, chain); cls_off / cls_fn / cls_sid: CSR list of the functions (and sampler ids) of every class.
-// ---------------------------------------------------------------------------------------------------------
-template <bool BATCH>   // BATCH: classes of three or more functions draw in batches of 8 right-hand sides (own instantiation:
-                        // the call must not perturb the register allocation of the few-functions kernel)
-__global__ void __launch_bounds__(NTHR, 2) k_function_class(CtxDev c, const int* __restrict__ cls_off, const int* __restrict__ cls_fn,
-                                                            const unsigned* __restrict__ cls_sid, int ncls, unsigned sweep) {
-  const int NT = c.NT, n = c.n, npad = NT * TB;
-  EngineSmem sm(smem_base(), NT, 1);
-  double* xs = smem_base() + engine_smem_doubles(NT, 1);   // 2 x npad: w -> mu, w+z -> beta
-  double* red = xs + 3 * npad;                             // NW*2*32  (same carve-up as k_function)
-  const size_t tstride = (size_t)plt_tiles(NT) * TILE;
-  double* W = c.ws + (size_t)blockIdx.x * c.ws_stride;
-  double* Wx = W + tstride;
-  double* brow = c.fws + (size_t)blockIdx.x * 2 * TB * npad;   // right-hand sides of the class, 32 x npad
-  double* wrow = brow + (size_t)TB * npad;                     // forward-solved rows
-  const Stream rng{c.k0, c.k1};
-  __shared__ int s_chain;
-  for (int item = next_chain(c.sched, &s_chain); item < c.C * ncls; item = next_chain(c.sched, &s_chain)) {
-    const int ch = item % c.C, cls = item / c.C;
-    const int* fns = cls_fn + cls_off[cls];
-    const unsigned* sids = cls_sid + cls_off[cls];
-    const int nf = cls_off[cls + 1] - cls_off[cls];
-    const int f0 = fns[0], g = c.group_of_fn[f0];
-    const double* A0 = c.Kinv + ((size_t)g * c.C + ch) * tstride;
-    const double yinv = 1.0 / (exp10(c.hyper[(size_t)ch * c.H]) + c.offset);
-    const double nt = c.G[(size_t)f0 * c.f + f0];
-    __syncthreads();
-    for (int t = threadIdx.x; t < npad; t += NTHR) sm.dvec[t] = (t < n) ? nt * yinv : 0.0;
-    for (int e = threadIdx.x; e < nf * npad; e += NTHR) {
-      const int j = e / npad, t = e % npad;
-      brow[e] = (t < n) ? yinv * c.Z[(size_t)fns[j] * n + t] : 0.0;      // function.py:32 with m_t = (X^T y)[f,t]
-    }
-    int tries = 0, code = 0;
-    double jitter = 0.0;
-    for (;;) {
-      __syncthreads();
-      EngineIO io{W, Wx, RowSrc{brow, nullptr, npad, nf, n}, wrow, npad};
-      if (chol_engine<AUG_RHS, true>(SrcTiles{A0}, io, NT, 1, (nf + 7) / 8, sm)) { code = tries; break; }
-      if (tries == 0) {   // jitchol ladder on A (linalg.py:41-54)
-        double s = 0.0, bad = 0.0;
-        for (int t = threadIdx.x; t < n; t += NTHR) {
-          const double d = A0[(size_t)plt(t >> 5, t >> 5) * TILE + (t & 31) * TB + (t & 31)] + sm.dvec[t];
-          s += d;
-          if (d <= 0.0) bad += 1.0;
-        }
-        s = block_sum(s, sm.red());
-        bad = block_sum(bad, sm.red());
-        if (bad > 0.0) { code = GPF_STATUS_NONPOS_DIAG; break; }
-        jitter = s / n * 1e-6;
-        for (int t = threadIdx.x; t < n; t += NTHR) sm.dvec[t] += jitter;
-      } else {
-        for (int t = threadIdx.x; t < n; t += NTHR) sm.dvec[t] += 9.0 * jitter;
-        jitter *= 10.0;
-      }
-      ++tries;
-      if (tries > c.maxtries || !isfinite(jitter)) { code = GPF_STATUS_NOT_PD; break; }
-    }
-    __syncthreads();
-    if (BATCH && code >= 0 && nf >= 3) {
-      // many functions per class (helmertConvert designs): draws in batches of 8 right-hand sides
-      for (int j0 = 0; j0 < nf; j0 += 8) class_draw_batch<8>(c, W, NT, sm, wrow, fns, sids, j0, (nf - j0 < 8) ? nf - j0 : 8, ch, sweep);
-    } else if (code >= 0) {
-      for (int j = 0; j < nf; ++j) {
-        const int fn = fns[j];
-        const double* wj = wrow + (size_t)j * npad;
-        for (int pr = threadIdx.x; 2 * pr < npad; pr += NTHR) {
-          double z0 = 0.0, z1 = 0.0;
-          if (2 * pr < n) rng.normal_pair((unsigned)(ch + c.chain_offset), sweep, sids[j], (unsigned)pr, z0, z1);
-          xs[npad + 2 * pr] = (2 * pr < n) ? wj[2 * pr] + z0 : 0.0;
-          xs[npad + 2 * pr + 1] = (2 * pr + 1 < n) ? wj[2 * pr + 1] + z1 : 0.0;
-        }
-        __syncthreads();
-        back_solve<1>(W, NT, xs + npad, npad, sm, red);   // only the draw is kept in a sweep (mu is not an output here)
-        for (int t = threadIdx.x; t < n; t += NTHR) c.F[((size_t)ch * c.f + fn) * n + t] = xs[npad + t];
-        __syncthreads();
-      }
-    }
-    if (threadIdx.x == 0) {
-      status_merge(c.status + ch, code);
-      atomicAdd(c.counters + CNT_CHOL, 1ull + (unsigned long long)tries);
-      atomicAdd(c.counters + CNT_FNCHOL, 1ull + (unsigned long long)tries);
-      atomicAdd(c.counters + CNT_DRAW, (unsigned long long)nf);
-      if (tries) atomicAdd(c.counters + CNT_JITTER, (unsigned long long)tries);
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------
 // Base.observationLikelihood (base.py:196-214): the sum of squared residuals is computed once per chain, after
 // which every candidate is O(1):  -N (log sd + log(2 pi)/2) - SSE / (2 sd^2) + log U(lb,ub)(sd),  sd = sqrt(10^x).
 // mode 0: evaluate at cand[ch] -> out[ch].   mode 1: slice step on y_sigma (sample/slice.pyx:24-62).

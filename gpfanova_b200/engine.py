@@ -252,7 +252,8 @@ class ChainEngine(object):
     def counters(self, clear=False):
         c = np.zeros(8, dtype=np.uint64)
         self._ck(self._lib.gpf_get_counters(self._h, c.ctypes.data_as(C.c_void_p), int(clear)))
-        return dict(zip(["chol", "logp", "jitter", "draws", "inverses", "slice_steps", "function_chol"], [int(v) for v in c[:7]]))
+        return dict(zip(["chol", "logp", "jitter", "draws", "inverses", "slice_steps", "function_chol", "ko_factor"],
+                        [int(v) for v in c[:8]]))
 
     # -- pieces of the sweep -------------------------------------------------------------------
     def group_kinv(self, g, want=True):
@@ -261,14 +262,16 @@ class ChainEngine(object):
         self.sync()
         return out
 
-    def function_step(self, fn, sweep=0, z=None, want=("mu", "LA", "mt", "nt")):
-        """Function._sample for function fn of every chain; returns dict of requested intermediates (CUDA tensors)"""
-        zt = self._dev_in(z, (self.C, self.n))
-        o = {k: None for k in ("mu", "LA", "mt", "nt")}
+    def function_step(self, fn, sweep=0, z=None, want=("mu", "LC", "mt", "nt")):
+        """Function._sample for function fn of every chain; returns dict of requested intermediates (CUDA tensors).
+        z: (C, 2n) injected standard normals [z1 | z2] or None (Philox).  "LC": Cholesky factor of
+        C = I + S K_o S (Sigma = K_o - K_o S C^-1 S K_o, S = sqrt(n_t / (sigma_y + 1e-9)))."""
+        zt = self._dev_in(z, (self.C, 2 * self.n))
+        o = {k: None for k in ("mu", "LC", "mt", "nt")}
         for k in want:
-            o[k] = self._new(self.C, self.n, self.n) if k == "LA" else self._new(self.C, self.n)
+            o[k] = self._new(self.C, self.n, self.n) if k == "LC" else self._new(self.C, self.n)
         sid = self.sampler_id[("function", fn)]
-        self._ck(self._lib.gpf_function_step(self._h, int(fn), sid, int(sweep), _ptr(zt), _ptr(o["mu"]), _ptr(o["LA"]),
+        self._ck(self._lib.gpf_function_step(self._h, int(fn), sid, int(sweep), _ptr(zt), _ptr(o["mu"]), _ptr(o["LC"]),
                                              _ptr(o["mt"]), _ptr(o["nt"])))
         self.sync()
         return {k: v for k, v in o.items() if v is not None}
@@ -326,8 +329,9 @@ class ChainEngine(object):
 
     def set_option(self, option, value):
         """option 0: Toeplitz/Schur slice log-likelihood on uniform grids (1, default) or dense tile engine (0);
-        1: batched launches; 2: shared factorisation for functions with identical conditional precision;
-        3: centrosymmetric split of K_inv on uniform grids (even n >= 64); 4: observation likelihood about the
+        1: batched launches (balanced designs: one fused kernel per sweep for all function draws); 2: shared factorisation
+        for functions with identical conditional precision; 3: centrosymmetric split on uniform grids (even n >= 64): all
+        n^3 work of the function step on the two half-size blocks; 4: observation likelihood about the
         least-squares fit (balanced designs, nothing missing)"""
         self._ck(self._lib.gpf_set_option(self._h, int(option), int(value)))
 
@@ -523,7 +527,7 @@ class EngineGroup(object):
         return 0
 
     # per-sampler entry points: run on every device, report the engine holding chain 0 / concatenated per-chain values
-    def function_step(self, fn, sweep=0, z=None, want=("mu", "LA", "mt", "nt")):
+    def function_step(self, fn, sweep=0, z=None, want=("mu", "LC", "mt", "nt")):
         outs = []
         for e, s in zip(self.engines, self._slices()):
             outs.append(e.function_step(fn, sweep=sweep, z=None if z is None else np.asarray(z)[s], want=want))

@@ -1,7 +1,8 @@
 """Function sampler (gpfanova/sample/function.py:6-40): conditional posterior draw of one latent function.
 
-The numerical work -- residual projection, A = diag(n_t)/sigma_y + K^-1, jitchol(A), mu = A^-1 b and the Gaussian
-draw -- is the fused CUDA kernel behind gpf_function_step; this class is the reference-shaped handle on it."""
+The numerical work -- residual projection and a draw from N(A^-1 b, A^-1), A = diag(n_t)/sigma_y + K^-1, evaluated in
+observation form without inverting K -- is the fused CUDA kernel behind gpf_function_step; this class is the
+reference-shaped handle on it."""
 from .sampler import Sampler
 
 
@@ -18,6 +19,7 @@ class Function(Sampler):
         return self.base._device_function_step(self.f)
 
     def conditional(self, z=None):
-        """(mu, L_A) of the conditional N(mu, (L_A L_A^T)^-1) for chain 0 -- the quantities function.py:34-38 builds;
-        z: optional injected standard normals (n,) used for the draw (beta = mu + L_A^-T z)."""
+        """(mu, Sigma) of the conditional N(mu, Sigma) for chain 0 -- the mean and covariance function.py:34-38 builds
+        (A^-1 b, A^-1); z: optional injected standard normals (2n,) [z1 | z2] used for the draw that is written
+        into the state."""
         return self.base._device_function_step(self.f, z=z, want_conditional=True)

@@ -110,7 +110,7 @@ int gpf_wait_event(gpf_ctx* ctx, int idx);
 int gpf_memcpy_d2h_event(gpf_ctx* ctx, void* h_dst, const void* d_src, size_t bytes, int idx);
 double* gpf_device_F(gpf_ctx* ctx);       /* device pointers to the live state (chains x f x n) */
 double* gpf_device_hyper(gpf_ctx* ctx);   /* chains x H */
-int gpf_invalidate(gpf_ctx* ctx);         /* call after writing through gpf_device_hyper(): cached K_inv are stale */
+int gpf_invalidate(gpf_ctx* ctx);         /* call after writing through gpf_device_hyper(): cached factors are stale */
 int gpf_n_samplers(gpf_ctx* ctx);         /* 1 + f + 2P: length of the non-Transform sampler list (base.py:57-84) */
 
 /* per-chain status of the last factorisations (max |code| since last clear); h_status: chains ints.
@@ -118,24 +118,33 @@ int gpf_n_samplers(gpf_ctx* ctx);         /* 1 + f + 2P: length of the non-Trans
 int gpf_get_status(gpf_ctx* ctx, int* h_status, int clear);
 
 /* counters since creation/clear: [0] factorisations, [1] log-density evaluations in slice steps,
- * [2] jitter retries, [3] function draws, [4] inverse (potri) count, [5] slice steps, [6] factorisations executed for
- * function draws (fewer than [3] when functions share their conditional precision), [7] reserved. */
+ * [2] jitter retries, [3] function draws, [4] inverse (potri) count, [5] slice steps, [6] factorisations of C executed
+ * for function draws (fewer than [3] when functions share their conditional precision), [7] factorisations of
+ * K_g + offset I (one per prior group, chain and sweep). */
 int gpf_get_counters(gpf_ctx* ctx, unsigned long long* h_counters8, int clear);
 
-/* Kernel.K_inv for prior group g of every chain at the current hyper-parameters (kernel.pyx:51-64
- * with rbf.pyx:16-19); result kept inside the ctx for gpf_function_step.  g = -1: all groups.
- * d_out (may be NULL): chains x n x n full copy for inspection (only for g >= 0). */
+/* Kernel.K_inv for prior group g of every chain at the current hyper-parameters (kernel.pyx:51-64 with
+ * rbf.pyx:16-19 generated on chip).  The call always leaves L_B = jitchol(K_g + offset I) (kernel.pyx:53-56) inside
+ * the ctx for gpf_function_step;  g = -1: all groups.
+ * d_out (may be NULL; only for g >= 0): chains x n x n, the inverse itself (L_B^-T L_B^-1, kernel.pyx:62-64) -- an
+ * inspection operator: the sampling path never forms K_inv (see gpf_function_step). */
 int gpf_group_kinv(gpf_ctx* ctx, int g, double* d_out);
 
-/* Function._sample, sample/function.py:14-40 (+ base.functionResidual, base.py:180-190) for function
- * fn of every chain: m_t, n_t, A = diag(n_t)/(sigma_y+offset) + K_inv, b, L_A = jitchol(A),
- * mu = A^-1 b, draw beta = mu + L_A^-T z, written into the state.
+/* Function._sample, sample/function.py:14-40 (+ base.functionResidual, base.py:180-190) for function fn of every chain:
+ * m_t, n_t, then a draw from N(A^-1 b, A^-1) with A = diag(n_t)/(sigma_y+offset) + K_o^-1, b = m_t/(sigma_y+offset),
+ * K_o = K_g + offset I, written into the state.  The conditional is evaluated in observation form, which is the same
+ * Gaussian without the inverse of the cond-1e11 matrix K_o (S = diag(n_t/(sigma_y+offset))^1/2, C = I + S K_o S):
+ *     mu = A^-1 b = K_o S C^-1 q0 (q0 = S^-1 b),   Sigma = A^-1 = K_o - K_o S C^-1 S K_o,
+ *     draw: f = L_B z1,  q = q0 - S f - z2,  beta = L_B (z1 + L_B^T S C^-1 q)       (z1, z2 standard normal).
+ * On a uniform grid with an even number (>= 64) of time points L_B is the block factor of the centrosymmetric split
+ * (option 3) and z1 lives in the split domain.
  *   sampler_id, sweep : Philox counter words (position in the reference's sampler list; sweep number)
- *   d_z_inject (may be NULL): chains x n standard normals used instead of Philox
- *   d_mu_out, d_LA_out, d_mt_out, d_nt_out (may be NULL): chains x n, chains x n x n, chains x n (x2).
- * Requires gpf_group_kinv for the function's group at the current hyper-parameters. */
+ *   d_z_inject (may be NULL): chains x 2n standard normals [z1 | z2] used instead of Philox
+ *   d_mu_out (chains x n), d_LC_out (chains x n x n: lower Cholesky factor of C), d_mt_out, d_nt_out (chains x n):
+ *   inspection outputs, each may be NULL.
+ * Factors K_o first if the ctx does not hold L_B at the current hyper-parameters. */
 int gpf_function_step(gpf_ctx* ctx, int fn, unsigned sampler_id, unsigned sweep, const double* d_z_inject,
-                      double* d_mu_out, double* d_LA_out, double* d_mt_out, double* d_nt_out);
+                      double* d_mu_out, double* d_LC_out, double* d_mt_out, double* d_nt_out);
 
 /* Base.observationLikelihood, base.py:196-214, at candidate log10 y_sigma per chain. d_cand,d_out: chains */
 int gpf_obs_loglik(gpf_ctx* ctx, const double* d_cand, double* d_out);
@@ -160,19 +169,21 @@ int gpf_sweep(gpf_ctx* ctx, int n_sweeps, int thin, unsigned sweep0, const int* 
               long long history_capacity_rows, long long* rows_out);
 
 /* timing/accounting of the last gpf_sweep call, measured with CUDA events on the ctx stream:
- * h_ms[0] total, [1] kinv kernels, [2] function kernels, [3] slice kernels, [4] y_sigma kernel, [5] store.
+ * h_ms[0] total, [1] K_o factor / K_inv kernels, [2] function kernels, [3] slice kernels, [4] y_sigma kernel, [5] store.
  * gpf_set_profile(ctx, 1): total + per-kernel brackets (adds event overhead, serialises the groups' slice kernels);
  * gpf_set_profile(ctx, 2): total only (one event pair around the whole call); 0: off. */
 /* options: 0 = use the O(n^2) Toeplitz (Schur algorithm) slice log-likelihood when the time grid is uniform
  * (default 1; 0 forces the dense tile engine, which is always used for non-uniform inputs);
- * 1 = batch the independent function draws (balanced design, nothing missing) and the K_inv of all groups of a sweep
- * into single launches (default 1; results are identical either way);
+ * 1 = balanced design with nothing missing (X^T X diagonal): the function draws of a sweep do not depend on each other
+ * and run as ONE fused launch per sweep, one (prior group, chain) item per CTA: factor of K_o, then the group's
+ * functions, all in the CTA's L2-resident workspace (default 1; 0 = one launch per sampler in the reference's order;
+ * the draws agree to rounding);
  * 2 = let functions of a group with identical conditional precision (balanced design, equal (X^T X)[f,f]) share one
- * factorisation (default 1; results are identical either way);
- * 3 = uniform grid with an even number (>= 64) of time points: K + offset I is symmetric Toeplitz, hence
- * centrosymmetric, and K_inv is assembled from the inverses of the two n/2 x n/2 blocks K11 +- K12 J of its
- * orthogonal block diagonalisation -- a quarter of the flops of base.py:133's n x n inverse, same backward-stable
- * Cholesky inverse on each block (default 1; 0 = invert the n x n matrix directly);
+ * factorisation of C (default 1; results agree to rounding);
+ * 3 = uniform grid with an even number (>= 64) of time points: K_o is symmetric Toeplitz, hence centrosymmetric,
+ * K_o = Q^T diag(B+, B-) Q with B+- = K11 +- K12 J and Q = [[I, J], [I, -J]]/sqrt 2: every n^3 operation of the function
+ * step (and gpf_group_kinv's inverse) runs on the two n/2 x n/2 blocks -- a quarter of the flops (default 1;
+ * 0 = full-size matrices; changes the square root of K_o the prior draw uses, i.e. the map from z1 to the draw);
  * 4 = balanced design with nothing missing: the residual sum of squares of base.py:196-214 is evaluated about the
  * least-squares fit, ||y - X F||^2 = ||y - X bhat||^2 + sum_f (X^T X)[f,f] ||F_f - bhat_f||^2 (O(f n) per chain instead
  * of O(n m f), all terms non-negative; default 1; 0 = per-observation loop, always used otherwise). */

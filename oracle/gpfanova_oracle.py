@@ -13,15 +13,20 @@ reference into ``oracle/_ref`` and ``oracle/make_golden.py`` runs it to mint
 those vectors (and, when ``oracle/_ref`` is importable, against the live
 reference).
 
-Two deliberate, documented departures, both *injection points* and not
-arithmetic changes:
+Two deliberate, documented departures, both *injection points* and not changes of
+the sampled distribution:
 
   * Gaussian draw map.  The reference draws through numpy's SVD map
-    (function.py:40).  No factorisation-based sampler can reproduce that map for
-    the same z, so the contract here (oracle AND device) is
-    ``beta = mu + L_A^{-T} z`` with ``L_A = jitchol(A)`` -- the very factor the
-    reference builds at function.py:34.  Equality with the reference is in
-    distribution (same mu, same covariance A^{-1}).
+    (function.py:40), which no factorisation-based sampler can reproduce for the same
+    z.  The contract here (oracle AND device) is the observation form of the same
+    conditional N(A^-1 b, A^-1), A = K_o^-1 + D (function.py:27-38):
+        f = S_B z1,  q = q0 - S f - z2,  v = C^-1 q,  beta = f + S_B S_B^T S v
+    with S = D^1/2, C = I + S K_o S, q0 = S^-1 b and S_B a square root of K_o = K + 1e-9 I
+    (``prior_sqrt``: the Cholesky factor kernel.pyx:56 builds; on a uniform grid with an
+    even number >= 64 of time points the block factor of the centrosymmetric split).
+    mu = K_o S C^-1 q0 and Sigma = K_o - K_o S C^-1 S K_o are the reference's A^-1 b and
+    A^-1 (``function_conditional`` keeps the reference's own arithmetic for comparison);
+    equality of the draws with the reference is in distribution.
   * Random streams.  The reference uses the global numpy/scipy stream.  Here all
     randomness comes from Philox4x32-10 keyed (seed; chain, sweep, sampler, draw)
     so the device can replay the identical stream.
@@ -318,9 +323,90 @@ def function_conditional(m_t, n_t, y_sigma_log10, Kinv_f):
 
 
 def function_draw(mu, L_A, z):
-    """injection contract replacing function.py:40:  beta = mu + L_A^{-T} z."""
+    """a draw from N(mu, (L_A L_A^T)^-1) in the reference's own parametrisation: beta = mu + L_A^{-T} z
+    (kept for the statistical checks; the device contract is function_draw_obs)."""
     import scipy.linalg
     return mu + scipy.linalg.solve_triangular(L_A, z, lower=True, trans='T')
+
+
+def uniform_even_grid(x):
+    """the grids on which K is symmetric Toeplitz and the centrosymmetric split is used: one input dimension, evenly
+    spaced (to 1e-14 of the range), an even number >= 64 of points"""
+    x = np.asarray(x, dtype=float)
+    if x.ndim == 2:
+        if x.shape[1] != 1:
+            return False
+        x = x[:, 0]
+    n = x.shape[0]
+    if n % 2 or n < 64:
+        return False
+    h = (np.longdouble(x[-1]) - np.longdouble(x[0])) / (n - 1)
+    tol = 1e-14 * (abs(x[0]) + abs(x[-1]))
+    return bool(np.all(np.abs((np.longdouble(x[0]) + np.arange(n) * h - x).astype(float)) <= tol))
+
+
+def prior_sqrt(K, centro=False):
+    """S_B with S_B S_B^T = K_o + jitter I,  K_o = K + OFFSET I  (kernel.pyx:53-56: jitchol of K + 1e-9 I, ladder of
+    linalg.py:41-54 included).  centro: K_o = Q^T diag(B+, B-) Q with B+- = K11 +- K12 J, Q = [[I, J], [I, -J]]/sqrt 2, and
+    S_B = Q^T diag(chol B+, chol B-) (the ladder adds the same jitter to both blocks).  Returns (S_B, jitter, tries)."""
+    n = K.shape[0]
+    Ko = K + np.eye(n) * OFFSET
+    if not centro:
+        L, tries = jitchol(Ko)
+        jit = 0.0 if tries == 0 else Ko.diagonal().mean() * 1e-6 * 10.0 ** (tries - 1)
+        return L, jit, tries
+    h = n // 2
+    K11, K12J = Ko[:h, :h], Ko[:h, h:][:, ::-1]
+    jit, tries = 0.0, 0
+    while True:
+        try:
+            Lp = np.linalg.cholesky(K11 + K12J + jit * np.eye(h))
+            Lm = np.linalg.cholesky(K11 - K12J + jit * np.eye(h))
+            break
+        except np.linalg.LinAlgError:
+            jit = Ko.diagonal().mean() * 1e-6 if tries == 0 else jit * 10.0
+            tries += 1
+            if tries > 5:
+                raise np.linalg.LinAlgError("not positive definite, even with jitter.")
+    r = math.sqrt(0.5)
+    SB = np.zeros((n, n))
+    SB[:h, :h] = r * Lp
+    SB[:h, h:] = r * Lm
+    SB[h:, :h] = r * Lp[::-1, :]
+    SB[h:, h:] = -r * Lm[::-1, :]
+    return SB, jit, tries
+
+
+def function_conditional_obs(m_t, n_t, y_sigma_log10, K, jitter=0.0):
+    """the conditional of sample/function.py:27-38 in observation form (no inverse of K):
+       D = diag(n_t) y_inv, S = D^1/2, C = I + S K_o S, q0 = S^-1 (y_inv m_t) (0 where n_t = 0),
+       mu = K_o S C^-1 q0 (= A^-1 b),  cov = K_o - K_o S C^-1 S K_o (= A^-1),  K_o = K + (OFFSET + jitter) I."""
+    n = m_t.shape[0]
+    yinv_s = 1.0 / (10.0 ** y_sigma_log10 + OFFSET)
+    Ko = K + np.eye(n) * (OFFSET + jitter)
+    d = n_t * yinv_s
+    sd = np.sqrt(d)
+    q0 = np.where(d > 0, yinv_s * m_t / np.where(sd > 0, sd, 1.0), 0.0)
+    C = np.eye(n) + sd[:, None] * Ko * sd[None, :]
+    L_C = np.linalg.cholesky(C)
+    import scipy.linalg
+    v0 = scipy.linalg.cho_solve((L_C, True), q0)
+    mu = Ko.dot(sd * v0)
+    Wm = scipy.linalg.solve_triangular(L_C, sd[:, None] * Ko, lower=True)
+    cov = Ko - Wm.T.dot(Wm)
+    return dict(C=C, L_C=L_C, q0=q0, sd=sd, mu=mu, cov=cov, Ko=Ko)
+
+
+def function_draw_obs(st, SB, z):
+    """the draw contract: z = [z1 | z2] (2n standard normals),
+       f = S_B z1,  q = q0 - S f - z2,  v = C^-1 q,  beta = S_B (z1 + S_B^T S v)."""
+    import scipy.linalg
+    n = st['q0'].shape[0]
+    z1, z2 = z[:n], z[n:2 * n]
+    f = SB.dot(z1)
+    q = st['q0'] - st['sd'] * f - z2
+    v = scipy.linalg.cho_solve((st['L_C'], True), q)
+    return SB.dot(z1 + SB.T.dot(st['sd'] * v))
 
 
 # --------------------------------------------------------------------------
@@ -488,15 +574,16 @@ class Model(object):
         return prior_loglik(self.x, Fg, self.hyper[1 + 2 * g], self.hyper[2 + 2 * g], cand, which)
 
     def function_step(self, f, z):
+        """z: 2n standard normals [z1 | z2] (function_draw_obs)"""
         g = [i for i, grp in enumerate(self.groups) if f in grp][0]
         K = rbf_K(self.x, 10.0 ** self.hyper[1 + 2 * g], 10.0 ** self.hyper[2 + 2 * g])
-        Kinv, _, nt = K_inv(K)
+        SB, jit, nt = prior_sqrt(K, uniform_even_grid(self.x))
         m_t, n_t = function_moments(self.y, self.X, self.F, f)
-        st = function_conditional(m_t, n_t, self.hyper[0], Kinv)
-        self.counters['jitter'] += nt + st['ntries']
-        beta = function_draw(st['mu'], st['L_A'], z)
+        st = function_conditional_obs(m_t, n_t, self.hyper[0], K, jit)
+        self.counters['jitter'] += nt
+        beta = function_draw_obs(st, SB, z)
         self.F[:, f] = beta
-        st.update(m_t=m_t, n_t=n_t, Kinv=Kinv, beta=beta)
+        st.update(m_t=m_t, n_t=n_t, SB=SB, beta=beta)
         return st
 
     def sweep(self, stream, chain, sweep_idx, order=None):
@@ -507,7 +594,7 @@ class Model(object):
         for sid in ids:
             kind, arg = self.order[sid]
             if kind == 'function':
-                z = stream.normals(chain, sweep_idx, sid, self.n)
+                z = stream.normals(chain, sweep_idx, sid, 2 * self.n)
                 self.function_step(arg, z)
             else:
                 h = arg

@@ -161,6 +161,14 @@ def main():
     gp = build_ref.import_ref()
     os.makedirs(GOLD, exist_ok=True)
     cands = [-2.5, -2.0, -1.3, -0.5, 0.0, 0.25, 0.5, 0.7, 1.9, 2.0, 2.5]
+    only = set(sys.argv[1:])          # optional: names of the cases to (re)mint; default all
+    global stage_case
+    stage_all = stage_case
+
+    def stage_case(gp_, name, *a, **k):
+        if only and name not in only:
+            return None
+        return stage_all(gp_, name, *a, **k)
 
     # KAT-0: n=5 one-way, closed-form data
     n = 5
@@ -213,6 +221,27 @@ def main():
     hyper = [-1.0, 0.1, 0.2, -0.3, 0.3, 0.2, -0.1]
     stage_case(gp, 'unbalanced_p2_n12', x, y, effect, F, hyper, cands)
 
+    # cfg-4 shape (small): 5x5 levels + interaction, one replicate, helmertConvert=True as analysis/cokol/cokol.py:74
+    # (f = 25 functions, interaction group of 16 functions sharing one conditional precision), n = 20
+    n = 20
+    x = np.linspace(-1, 1, n)[:, None]
+    effect = np.array(list(itertools.product(range(5), range(5))))
+    hyper_true = [-2] + [0] * 8
+    y, fs = prior_data(gp, x, effect, 321, hyper_true, interactions=True, helmertConvert=True)
+    F = fs + 0.05 * np.random.default_rng(12).standard_normal(fs.shape)
+    hyper = [-1.8, 0.1, -0.2, 0.3, 0.2, -0.2, -0.4, -0.3, 0.1]
+    stage_case(gp, 'cokol5x5_hc_n20', x, y, effect, F, hyper, cands, interactions=True, helmertConvert=True)
+
+    # cfg-1 shape on a uniform grid with an even number >= 64 of time points: the centrosymmetric split is active
+    n = 64
+    x = np.linspace(-1, 1, n)[:, None]
+    effect = np.array(list(range(3)) * 5)[:, None]
+    y, fs = prior_data(gp, x, effect, 77, [-2, 0, 0, 0, 0])
+    F = fs + 0.05 * np.random.default_rng(13).standard_normal(fs.shape)
+    stage_case(gp, 'oneway_n64', x, y, effect, F, [-1.6, 0.2, -0.1, -0.3, 0.15], cands)
+
+    if only and 'jitchol' not in only:
+        return
     # jitchol (linalg.py:35-54): PD, PSD-needs-jitter, and failing inputs
     rng = np.random.default_rng(3)
     B = rng.standard_normal((16, 16))

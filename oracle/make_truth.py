@@ -21,8 +21,10 @@ from helpers import load_case, oracle_model  # noqa: E402
 
 mp.mp.dps = 60
 SEL_FUNCS = [("oneway_n50", [0, 1, 2]), ("oneway_n50_missing", [0, 1]), ("twoway_n24", [0, 3, 5]),
-             ("twoway_n24_hc", [0, 3, 5, 8]), ("unbalanced_p2_n12", [1])]
-SEL_LL = [("oneway_n50", [0, 1]), ("twoway_n24", [0, 2, 3]), ("unbalanced_p2_n12", [1])]
+             ("twoway_n24_hc", [0, 3, 5, 8]), ("unbalanced_p2_n12", [1]), ("oneway_n64", [0, 2]),
+             ("cokol5x5_hc_n20", [0, 2, 9, 24])]
+SEL_LL = [("oneway_n50", [0, 1]), ("twoway_n24", [0, 2, 3]), ("unbalanced_p2_n12", [1]), ("oneway_n64", [1]),
+          ("cokol5x5_hc_n20", [3])]
 
 
 def mpf(v):
@@ -46,8 +48,15 @@ def tonp(M):
 
 
 def main():
+    """python oracle/make_truth.py [case ...]: with case names, only those are (re)computed and merged into the file"""
     out = {}
+    only = set(sys.argv[1:])
+    path = os.path.join(os.path.dirname(HERE), "tests", "golden", "truth.npz")
+    if only and os.path.exists(path):
+        out = dict(np.load(path))
     for name, fs in SEL_FUNCS:
+        if only and name not in only:
+            continue
         c = load_case(name)
         m = oracle_model(c)
         kinv_cache = {}
@@ -70,6 +79,8 @@ def main():
             out["%s/cov_%d" % (name, f)] = tonp(cov)
             print(name, "f", f, "done", flush=True)
     for name, gs in SEL_LL:
+        if only and name not in only:
+            continue
         c = load_case(name)
         m = oracle_model(c)
         cands = c["cands"]
@@ -100,7 +111,7 @@ def main():
                     vals.append(float(ll))
                 out["%s/prior_ll_%s_%d" % (name, which, g)] = np.array(vals)
                 print(name, "ll", g, which, "done", flush=True)
-    np.savez_compressed(os.path.join(os.path.dirname(HERE), "tests", "golden", "truth.npz"), **out)
+    np.savez_compressed(path, **out)
 
 
 if __name__ == "__main__":

@@ -7,7 +7,7 @@ import gpfanova_oracle as orc
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = ["kat0_zeroF", "kat0_sinF", "oneway_n50", "oneway_n50_missing", "twoway_n24", "twoway_n24_hc",
-         "unbalanced_p2_n12"]
+         "unbalanced_p2_n12", "cokol5x5_hc_n20", "oneway_n64"]
 
 
 def load_case(name):

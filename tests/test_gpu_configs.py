@@ -1,0 +1,171 @@
+"""GPU parity at the shapes of BASELINE.json's configs, through the kernels those shapes launch: whole Gibbs sweeps
+against the oracle driven by the same Philox stream, at n = 100 / 200 / 256 (several tile rows, both halves of the
+centrosymmetric split), with classes of 1, 2, 4, 11 and 64 functions sharing one factorisation, on odd and non-uniform
+grids (the non-split variants of the fused kernel), and the fused launch against the sequential sampler order."""
+import itertools
+
+import numpy as np
+import pytest
+
+import gpfanova_oracle as orc
+from helpers import load_case, oracle_model, relerr
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def eng():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from gpfanova_b200 import engine
+    return engine
+
+
+def make_problem(levels, reps, n, hc, seed, grid="uniform"):
+    """synthetic FANOVA data drawn from the model's own prior (test_convergence.py:56-62 style)"""
+    rng = np.random.default_rng(seed)
+    if grid == "uniform":
+        x = np.linspace(-1, 1, n)[:, None]
+    else:
+        x = np.sort(rng.uniform(-1, 1, size=(n, 1)), axis=0)
+    if len(levels) == 1:
+        effect = np.array(list(range(levels[0])) * reps)[:, None]
+    else:
+        effect = np.array(list(itertools.product(*[range(k) for k in levels])) * reps)
+    d = orc.Design(effect, interactions=len(levels) > 1, helmertConvert=hc)
+    groups = d.prior_groups()
+    F = np.zeros((n, d.f))
+    L = np.linalg.cholesky(orc.rbf_K(x, 1.0, 0.7) + 1e-8 * np.eye(n))
+    for i in range(d.f):
+        F[:, i] = L @ rng.standard_normal(n)
+    y = F @ d.X.T + rng.normal(0, 0.1, size=(n, d.m))
+    return x, y, d, groups, F
+
+
+#        name                 levels   reps  n    hc     grid          chains  sweeps  oracle chains
+SHAPES = [
+    ("cfg5_n256",            (3, 3),  5,    256, False, "uniform",    4,      2,      (0, 3)),      # h = 128: 4 + 4 tile rows
+    ("cfg2_n100_64chains",   (3, 3),  5,    100, False, "uniform",    64,     2,      (0, 31, 63)),  # h = 50: 2 tile rows
+    ("hc3x3_n200",           (3, 3),  2,    200, True,  "uniform",    3,      2,      (0, 2)),      # classes of 2, 2, 4; h = 100
+    ("oneway12_hc_n100",     (12,),   2,    100, True,  "uniform",    3,      2,      (1,)),        # class of 11: 32-row passes
+    ("odd_n101",             (3, 3),  2,    101, False, "uniform",    3,      2,      (0,)),        # no split: full-size fused kernel
+    ("nonuniform_n72",       (3, 3),  2,    72,  False, "random",     3,      2,      (2,)),        # element-wise RBF source
+    ("cokol9x9_hc_n200",     (9, 9),  1,    200, True,  "uniform",    2,      1,      (1,)),        # cfg4 shape: 64-function class
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=[s[0] for s in SHAPES])
+def test_sweeps_at_config_shapes_follow_oracle(eng, shape):
+    name, levels, reps, n, hc, grid, C, S, och = shape
+    x, y, d, groups, F = make_problem(levels, reps, n, hc, seed=len(name) + n, grid=grid)
+    seed = 4242
+    e = eng.ChainEngine(x, y, d.X, groups, chains=C, seed=seed, chain_offset=5)
+    rng = np.random.default_rng(3)
+    hyper = np.concatenate([np.full((C, 1), -2.0), rng.uniform(-0.7, 0.7, size=(C, e.H - 1))], axis=1)
+    e.set_state(F=np.zeros((C, e.f, n)), hyper=hyper)
+    hist = torch.zeros((S, C, e.H + e.f * n), dtype=torch.float64, device="cuda")
+    assert e.sweep(S, thin=0, history=hist) == S
+    e.sync()
+    e.status()
+    hist = hist.cpu().numpy()
+    assert np.all(np.isfinite(hist))
+    cnt = e.counters()
+    assert cnt["draws"] == C * S * e.f and cnt["slice_steps"] == C * S * e.H
+    st = orc.Stream(seed)
+    for ch in och:
+        m = orc.Model(x, y, d.X, groups)
+        m.hyper = hyper[ch].copy()
+        for s in range(S):
+            m.sweep(st, ch + 5, s)
+            assert np.allclose(hist[s, ch, :e.H], m.hyper, rtol=0, atol=1e-6), (name, ch, s, hist[s, ch, :e.H], m.hyper)
+            assert relerr(hist[s, ch, e.H:].reshape(e.f, n), m.F.T) < 1e-6, (name, ch, s)
+    e.close()
+
+
+@pytest.mark.parametrize("shape", [s for s in SHAPES if s[0] in ("cfg5_n256", "hc3x3_n200", "oneway12_hc_n100", "odd_n101",
+                                                               "nonuniform_n72", "cokol9x9_hc_n200")],
+                         ids=lambda s: s[0])
+def test_fused_launch_equals_sequential_order_at_size(eng, shape):
+    """gpf_set_option(1, 0): one launch per sampler with the general kernel (own factorisation of C per function, factor of
+    K_o from HBM); default: one fused launch per sweep.  Same Philox stream, same draws to rounding."""
+    name, levels, reps, n, hc, grid, C, S, och = shape
+    x, y, d, groups, F = make_problem(levels, reps, n, hc, seed=7 + n, grid=grid)
+    C = min(C, 3)
+    rng = np.random.default_rng(8)
+    outs, fchol = [], []
+    for batch, share in ((1, 1), (1, 0), (0, 0)):
+        e = eng.ChainEngine(x, y, d.X, groups, chains=C, seed=99)
+        e.set_option(1, batch)
+        e.set_option(2, share)
+        hyper = np.concatenate([np.full((C, 1), -2.0), np.random.default_rng(8).uniform(-0.7, 0.7, size=(C, e.H - 1))], axis=1)
+        e.set_state(F=F.T, hyper=hyper)
+        hist = torch.zeros((1, C, e.H + e.f * n), dtype=torch.float64, device="cuda")
+        e.sweep(1, history=hist)
+        e.sync()
+        e.status()
+        outs.append(hist.cpu().numpy())
+        fchol.append(e.counters()["function_chol"])
+        e.close()
+    scale = np.max(np.abs(outs[2]))
+    for o in outs[:2]:
+        assert np.max(np.abs(o[..., :1 + 2 * len(groups)] - outs[2][..., :1 + 2 * len(groups)])) < 1e-7
+        assert np.max(np.abs(o - outs[2])) < 1e-7 * scale, (name, np.max(np.abs(o - outs[2])))
+    assert fchol[2] == C * d.f and fchol[1] == C * d.f and fchol[0] <= fchol[1]
+    if hc:
+        rbs = 32 if max(len(g) for g in groups) > 8 else 8
+        assert fchol[0] == C * sum(-(-len(g) // rbs) for g in groups)      # one factorisation of C per class (and pass)
+
+
+@pytest.mark.parametrize("name", ["cokol5x5_hc_n20", "oneway_n64"])
+def test_new_goldens_whole_sweeps(eng, name):
+    """the cfg4-shaped (5 x 5 levels, helmertConvert) and the n = 64 (split active) reference goldens: sweeps from the golden
+    state follow the oracle"""
+    c = load_case(name)
+    C, S, seed = 3, 3, 77
+    e = eng.ChainEngine(c["x"], c["y"], c["design_matrix"], c["groups"], chains=C, seed=seed)
+    e.set_state(F=c["F"].T, hyper=c["hyper"])
+    hist = torch.zeros((S, C, e.H + e.f * e.n), dtype=torch.float64, device="cuda")
+    e.sweep(S, history=hist)
+    e.sync()
+    e.status()
+    hist = hist.cpu().numpy()
+    stream = orc.Stream(seed)
+    for ch in range(C):
+        m = oracle_model(c)
+        for s in range(S):
+            m.sweep(stream, ch, s)
+            assert np.allclose(hist[s, ch, :e.H], m.hyper, rtol=0, atol=1e-6), (name, ch, s)
+            assert relerr(hist[s, ch, e.H:].reshape(e.f, e.n), m.F.T) < 1e-6, (name, ch, s)
+    e.close()
+
+
+def test_dense_slice_path_with_many_functions(eng):
+    """cfg4 shape: the 64-function interaction group rides along the dense slice factorisation as two right-hand-side tile
+    rows (gpf_set_option(0, 0): dense engine instead of the Toeplitz/Schur path) -- log-likelihoods and a sweep"""
+    x, y, d, groups, F = make_problem((9, 9), 1, 200, True, seed=21)
+    C = 4
+    rng = np.random.default_rng(4)
+    hyper = np.concatenate([np.full((C, 1), -2.0), rng.uniform(-0.6, 0.6, size=(C, 1 + 2 * len(groups) - 1))], axis=1)
+    cand = rng.uniform(-1.0, 1.0, size=C)
+    res = {}
+    for opt in (1, 0):
+        e = eng.ChainEngine(x, y, d.X, groups, chains=C, seed=6)
+        e.set_option(0, opt)
+        e.set_state(F=F.T, hyper=hyper)
+        vals = {}
+        for g in (1, 3):
+            for which in ("sigma", "lengthscale"):
+                got = e.prior_loglik(g, which, cand)
+                for ch in range(C):
+                    o = orc.prior_loglik(x, F[:, groups[g]].T, hyper[ch, 1 + 2 * g], hyper[ch, 2 + 2 * g], cand[ch], which)
+                    assert abs(got[ch] - o) <= 5e-9 * max(1.0, abs(o)), (opt, g, which, ch, got[ch], o)
+                vals[(g, which)] = got
+        hist = torch.zeros((1, C, e.H + e.f * 200), dtype=torch.float64, device="cuda")
+        e.sweep(1, history=hist)
+        e.sync()
+        e.status()
+        res[opt] = hist.cpu().numpy()
+        e.close()
+    # same Philox stream, two evaluations of the same log densities: the slice decisions and hence the states agree
+    assert np.max(np.abs(res[0][..., :9] - res[1][..., :9])) < 1e-6

@@ -168,6 +168,51 @@ def test_draw_contract_covariance():
     assert relerr(T @ T.T, st["cov"]) < 1e-9
 
 
+@pytest.mark.parametrize("name", CASES)
+def test_observation_form_is_the_reference_conditional(name):
+    """function_conditional_obs (the device contract: no inverse of K) against the reference's mu / cov goldens: the
+    difference is bounded by the reference's own K_inv rounding (4e-11..1e-9), and against the 60-digit
+    arbiter it is 1e-10 or better where the reference's own path is not."""
+    c = load_case(name)
+    m = oracle_model(c)
+    T = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "truth.npz")))
+    for f in range(m.f):
+        g = [i for i, grp in enumerate(m.groups) if f in grp][0]
+        m_t, n_t = orc.function_moments(m.y, m.X, m.F, f)
+        st = orc.function_conditional_obs(m_t, n_t, m.hyper[0], c["K_%d" % g])
+        assert relerr(st["mu"], c["mu_%d" % f]) < 5e-9
+        assert relerr(st["cov"], c["cov_%d" % f]) < 5e-9
+        k = "%s/mu_%d" % (name, f)
+        if k in T:
+            assert relerr(st["mu"], T[k]) < 1e-11 and relerr(st["cov"], T["%s/cov_%d" % (name, f)]) < 1e-10
+
+
+@pytest.mark.parametrize("name,centro", [("oneway_n50", False), ("oneway_n50_missing", False), ("oneway_n64", True),
+                                         ("unbalanced_p2_n12", False)])
+def test_observation_draw_map_has_the_conditional_moments(name, centro):
+    """function_draw_obs is affine in z = [z1 | z2]: its value at z = 0 is mu and its Jacobian M satisfies
+    M M^T = Sigma -- so a draw has exactly the distribution N(A^-1 b, A^-1) of function.py:38-40."""
+    c = load_case(name)
+    m = oracle_model(c)
+    assert orc.uniform_even_grid(m.x) == centro
+    f = 1
+    g = [i for i, grp in enumerate(m.groups) if f in grp][0]
+    K = c["K_%d" % g]
+    m_t, n_t = orc.function_moments(m.y, m.X, m.F, f)
+    st = orc.function_conditional_obs(m_t, n_t, m.hyper[0], K)
+    SB, jit, tries = orc.prior_sqrt(K, centro)
+    assert tries == 0 and relerr(SB @ SB.T, st["Ko"]) < 1e-13
+    n = m.n
+    mu0 = orc.function_draw_obs(st, SB, np.zeros(2 * n))
+    assert relerr(mu0, st["mu"]) < 1e-10
+    M = np.stack([orc.function_draw_obs(st, SB, e) - mu0 for e in np.eye(2 * n)], axis=1)
+    assert relerr(M @ M.T, st["cov"]) < 1e-9
+    if centro:      # the two square roots of K_o give the same law
+        L = np.linalg.cholesky(st["Ko"])
+        M2 = np.stack([orc.function_draw_obs(st, L, e) - mu0 for e in np.eye(2 * n)], axis=1)
+        assert relerr(M2 @ M2.T, M @ M.T) < 1e-9
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="live reference only in the build container")
 def test_oracle_vs_live_reference_sweep_pieces():
     """run the live reference on a fresh random state and compare every stage"""
