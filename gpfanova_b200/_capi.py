@@ -60,6 +60,7 @@ SIGNATURES = {
     "gpf_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "gpf_set_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "gpf_get_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "gpf_debug_trace": (C.c_int, [C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

@@ -897,6 +897,19 @@ int gpf_set_option(gpf_ctx* c, int option, int value) {
 
 int gpf_set_profile(gpf_ctx* c, int on) { c->profile = on; return GPF_OK; }
 
+// phase cycle counters of the fused function kernel (builds with -DGPF_FTRACE only; zeros otherwise): read and clear
+int gpf_debug_trace(gpf_ctx* c, unsigned long long* h8) {
+  CK(c, cudaSetDevice(c->device));
+  for (int i = 0; i < 8; ++i) h8[i] = 0;
+#ifdef GPF_FTRACE
+  CK(c, cudaStreamSynchronize(c->stream));
+  CK(c, cudaMemcpyFromSymbol(h8, gpf::gpf_ftrace, 8 * sizeof(unsigned long long)));
+  unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  CK(c, cudaMemcpyToSymbol(gpf::gpf_ftrace, z, sizeof z));
+#endif
+  return GPF_OK;
+}
+
 int gpf_get_profile(gpf_ctx* c, double* h_ms6, unsigned long long* h_launches) {
   if (h_ms6) for (int i = 0; i < 6; ++i) h_ms6[i] = c->ms[i];
   if (h_launches) *h_launches = c->launches;

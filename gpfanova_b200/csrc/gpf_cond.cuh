@@ -26,6 +26,26 @@ namespace gpf {
 
 constexpr double RSQRT2 = 0.70710678118654752440;
 
+#ifdef GPF_FTRACE
+// phase timers of the fused kernel (thread 0 of every 16th CTA), cycles: [0] table, [1] factor of K_o, [2] right-hand sides,
+// [3] factor of C, [4] back substitution, [5] triangular products, [6] write-out, [7] items
+__device__ unsigned long long gpf_ftrace[8];
+#define FT_INIT long long ft_prev = clock64();
+#define FT(s)                                                                 \
+  do {                                                                        \
+    if (threadIdx.x == 0 && (blockIdx.x & 15) == 0) {                         \
+      const long long now_ = clock64();                                       \
+      atomicAdd(gpf_ftrace + (s), (unsigned long long)(now_ - ft_prev));      \
+      ft_prev = now_;                                                         \
+    }                                                                         \
+  } while (0)
+#define FT_COUNT if (threadIdx.x == 0 && (blockIdx.x & 15) == 0) atomicAdd(gpf_ftrace + 7, 1ull);
+#else
+#define FT_INIT
+#define FT(s)
+#define FT_COUNT
+#endif
+
 // element e of the 2n standard normals of one function draw (z1 = elements [0, n), z2 = [n, 2n)): Box-Muller pair e >> 1
 __device__ __forceinline__ double normal_elem(const Stream& rng, unsigned gch, unsigned sweep, unsigned sid, int e) {
   double z0, z1;
@@ -334,8 +354,11 @@ __global__ void __launch_bounds__(NTHR, 2) k_group_fused(CtxDev c, FusedArgs a) 
     const double ls = exp10(c.hyper[(size_t)ch * c.H + 2 + 2 * g]);
     const double yinv = 1.0 / (exp10(c.hyper[(size_t)ch * c.H]) + c.offset);
     __syncthreads();
+    FT_INIT
+    FT_COUNT
     if constexpr (MODE >= 1) toeplitz_table(c.d2, n, sigma, ls, tab, sm0.red());
     else rbf_scale_inputs(c.x, n, c.p, ls, tab, xsq);
+    FT(0);
     // ---------------- 1. jitchol(K_o) ----------------
     int tries = 0, code = 0;
     double jitter = 0.0;
@@ -359,6 +382,7 @@ __global__ void __launch_bounds__(NTHR, 2) k_group_fused(CtxDev c, FusedArgs a) 
       if (tries > c.maxtries || !isfinite(jitter)) { code = GPF_STATUS_NOT_PD; break; }
     }
     int nfact = 0, ndraw = 0;
+    FT(1);
     // ---------------- 2. the classes of this group ----------------
     if (code >= 0)
       for (int cls = a.gcls_off[g]; cls < a.gcls_off[g + 1]; ++cls) {
@@ -398,6 +422,7 @@ __global__ void __launch_bounds__(NTHR, 2) k_group_fused(CtxDev c, FusedArgs a) 
           }
           // ---- C = I + c K_o with the q riding along ----
           gsync();
+          FT(2);
           for (int t = tid; t < hpad; t += NTE) sm.dvec[t] = (t < hh) ? 1.0 + cc * (c.offset + jitter) : 0.0;
           gsync();
           EngineIO io{WC, Wx, RowSrc{qrow, nullptr, rowlen, cnt, hh}, wrow, rowlen};
@@ -409,6 +434,7 @@ __global__ void __launch_bounds__(NTHR, 2) k_group_fused(CtxDev c, FusedArgs a) 
             okh = chol_engine<AUG_RHS, true>(SrcScaled<SrcToeplitz>{SrcToeplitz{tab, n}, cc, n}, io, NTm, 1, ntl, sm);
           else okh = chol_engine<AUG_RHS, true>(SrcScaled<SrcRbf>{SrcRbf{tab, xsq, n, c.p, sigma}, cc, n}, io, NTm, 1, ntl, sm);
           const bool okc = !__syncthreads_or(okh ? 0 : 1);
+          FT(3);
           ++nfact;
           if (!okc) { code = GPF_STATUS_NOT_PD; break; }
           // ---- v = L_C^-T w;  beta = L_B (z1 + sqrt(c) L_B^T v) ----
@@ -421,6 +447,7 @@ __global__ void __launch_bounds__(NTHR, 2) k_group_fused(CtxDev c, FusedArgs a) 
             }
             if (R <= 2) back_solve_g<2, NWE>(WC, NTm, xa, ldv, sm.rinv, sub);
             else back_solve_g<8, NWE>(WC, NTm, xa, ldv, sm.rinv, sub);
+            FT(4);
             for (int e = tid; e < R * hh; e += NTE) xa[(e / hh) * ldv + e % hh] *= sc;
             gsync();
             trimv_dmma<true, NWE>(LBt, NTm, xa, xb, ldv, R, warp, lane);
@@ -432,6 +459,7 @@ __global__ void __launch_bounds__(NTHR, 2) k_group_fused(CtxDev c, FusedArgs a) 
             gsync();
             trimv_dmma<false, NWE>(LBt, NTm, xb, xa, ldv, R, warp, lane);
             __syncthreads();
+            FT(5);
             const double* p0 = sm0.P;
             const double* p1 = sm1.P;
             for (int e = threadIdx.x; e < R * hh; e += NTHR) {
@@ -444,6 +472,7 @@ __global__ void __launch_bounds__(NTHR, 2) k_group_fused(CtxDev c, FusedArgs a) 
               } else Fo[i] = p0[v * ldv + i];
             }
             __syncthreads();
+            FT(6);
           }
           ndraw += cnt;
         }

@@ -190,6 +190,9 @@ int gpf_sweep(gpf_ctx* ctx, int n_sweeps, int thin, unsigned sweep0, const int* 
 int gpf_set_option(gpf_ctx* ctx, int option, int value);
 int gpf_set_profile(gpf_ctx* ctx, int on);
 int gpf_get_profile(gpf_ctx* ctx, double* h_ms6, unsigned long long* h_launches);
+/* development aid: cycle counters of the phases of the fused function kernel, read and cleared (all zero unless the
+ * library was built with -DGPF_FTRACE; tools/fused_trace.py) */
+int gpf_debug_trace(gpf_ctx* ctx, unsigned long long* h_cycles8);
 
 #ifdef __cplusplus
 }
