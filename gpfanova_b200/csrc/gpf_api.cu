@@ -52,7 +52,6 @@ struct gpf_ctx {
   int* d_fn_all = nullptr;            // all functions in sampler order / their sampler ids (device)
   unsigned* d_sid_all = nullptr;
   int ncls = 0;                       // classes of functions sharing their conditional precision (indep designs)
-  int rb = 8;                         // right-hand-side rows per factorisation pass of the fused kernel (8 or 32)
   int *d_cls_off = nullptr, *d_cls_fn = nullptr, *d_gcls_off = nullptr, *d_gorder = nullptr;
   int *d_cls1_off = nullptr, *d_gcls1_off = nullptr;   // option 2 = 0: every function its own class
   unsigned* d_cls_sid = nullptr;
@@ -212,11 +211,12 @@ int launch_all_functions(gpf_ctx* c, unsigned sweep) {
   CK(c, cudaMemsetAsync(c->dev.sched, 0, sizeof(int), c->stream));
   const int grid = std::min(c->dev.C * c->dev.P, 2 * c->sms);
   FusedArgs a{c->d_gorder, c->share ? c->d_gcls_off : c->d_gcls1_off, c->share ? c->d_cls_off : c->d_cls1_off, c->d_cls_fn,
-              c->d_cls_sid, sweep, c->rb};
+              c->d_cls_sid, sweep};
   const int mode = mode_of(c);
-  if (mode == 2) k_group_fused<2><<<grid, NTHR, c->smem_fused[2], c->stream>>>(c->dev, a);
-  else if (mode == 1) k_group_fused<1><<<grid, NTHR, c->smem_fused[1], c->stream>>>(c->dev, a);
-  else k_group_fused<0><<<grid, NTHR, c->smem_fused[0], c->stream>>>(c->dev, a);
+  const size_t sm = c->smem_fused[mode];
+  if (mode == 2) k_group_fused<2><<<grid, NTHR, sm, c->stream>>>(c->dev, a);
+  else if (mode == 1) k_group_fused<1><<<grid, NTHR, sm, c->stream>>>(c->dev, a);
+  else k_group_fused<0><<<grid, NTHR, sm, c->stream>>>(c->dev, a);
   ++c->launches;
   CK(c, cudaGetLastError());
   return GPF_OK;
@@ -465,7 +465,7 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
     gcoff1.push_back((int)coff1.size() - 1);
   }
   c->ncls = (int)coff.size() - 1;
-  c->rb = maxcls > 8 ? 32 : 8;
+  (void)maxcls;
   // shared-memory budgets
   const size_t xsd = (size_t)d->n * d->p + d->n;
   c->smem_kinv = (engine_smem_doubles(v.NT, 0) + xsd) * sizeof(double);
@@ -478,7 +478,7 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
     const int nsub = mode == 2 ? 2 : 1, NTm = ((mode == 2 ? d->n / 2 : d->n) + TB - 1) / TB;
     c->smem_fn[mode] = function_smem_doubles(d->n, d->p, v.NT, mode) * sizeof(double);
     c->smem_fact[mode] = ((size_t)nsub * engine_smem_doubles(NTm, 0) + xsd) * sizeof(double);
-    c->smem_fused[mode] = fused_smem_doubles(d->n, d->p, mode, c->rb) * sizeof(double);
+    c->smem_fused[mode] = fused_smem_doubles(d->n, d->p, mode) * sizeof(double);
     smax = std::max(smax, std::max(c->smem_fn[mode], std::max(c->smem_fact[mode], c->indep ? c->smem_fused[mode] : (size_t)0)));
   }
   for (int g = 0; g < d->P; ++g) {
@@ -527,7 +527,7 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
   v.ws_stride = tstride + (size_t)std::max(v.NEmax, 1) * v.NT * TILE;
   v.ws_stride = std::max(v.ws_stride, 2 * tstride + (size_t)v.NT * TILE);
   if (c->centro_ok) v.ws_stride = std::max(v.ws_stride, 2 * hstride2 + 2 * (size_t)NTh * TILE);
-  v.fws_stride = 2 * (size_t)c->rb * std::max((size_t)v.NT * TB, (size_t)2 * NTh * TB);
+  v.fws_stride = std::max(fused_scratch_doubles(d->n, 1), c->centro_ok ? fused_scratch_doubles(d->n, 2) : (size_t)0);
   double *dx, *dyT, *dX, *dF, *dh, *dLB, *dBj, *dws, *dd2, *dG, *dZ, *dfws;
   unsigned char* dfull;
   int *dgof, *dgf, *dgo, *dst, *dsched;
@@ -898,14 +898,14 @@ int gpf_set_option(gpf_ctx* c, int option, int value) {
 int gpf_set_profile(gpf_ctx* c, int on) { c->profile = on; return GPF_OK; }
 
 // phase cycle counters of the fused function kernel (builds with -DGPF_FTRACE only; zeros otherwise): read and clear
-int gpf_debug_trace(gpf_ctx* c, unsigned long long* h8) {
+int gpf_debug_trace(gpf_ctx* c, unsigned long long* h24) {
   CK(c, cudaSetDevice(c->device));
-  for (int i = 0; i < 8; ++i) h8[i] = 0;
+  for (int i = 0; i < 24; ++i) h24[i] = 0;
 #ifdef GPF_FTRACE
   CK(c, cudaStreamSynchronize(c->stream));
-  CK(c, cudaMemcpyFromSymbol(h8, gpf::gpf_ftrace, 8 * sizeof(unsigned long long)));
-  unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  CK(c, cudaMemcpyToSymbol(gpf::gpf_ftrace, z, sizeof z));
+  CK(c, cudaMemcpyFromSymbol(h24, gpf::gpf_ftrace, 8 * sizeof(unsigned long long)));
+  unsigned long long z[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  CK(c, cudaMemcpyToSymbol(gpf::gpf_ftrace, z, 8 * sizeof(unsigned long long)));
 #endif
   return GPF_OK;
 }

@@ -295,12 +295,13 @@ __global__ void __launch_bounds__(NTHR, 2) k_function(CtxDev c, int fn_single, u
 // Balanced design with nothing missing (X^T X diagonal): the function draws of a sweep do not depend on each other and
 // n_t = (X^T X)[f,f] =: n_f for every t, so D = c I with c = n_f / (sigma_y + offset), and functions of one prior group with
 // equal n_f (a CLASS; with helmertConvert=True every function of a group) share C = I + c K_o.
-// One item = (prior group, chain), everything stays in the CTA's L2-resident workspace -- neither K^-1 nor any factor
-// ever goes to HBM:
+// One item = (prior group, chain), everything stays on the SM or in the CTA's L2-resident workspace -- neither K^-1 nor
+// any factor ever goes to HBM:
 //   1. jitchol(K_o) (centro: of B+ and B-, side by side on two sub-engines)
-//   2. per class: q of its functions (prior draws through L_B), one factorisation of C with the q riding along as rows of
-//      an augmented tile row (at most rb functions per pass), back substitution, beta = L_B (z1 + sqrt(c) L_B^T v).
-// The right-hand side is q0 = sqrt(c) ybar with ybar = (X^T y)[f] / n_f (c.bhat).
+//   2. per class, eight functions per pass: prior draws f = L_B z1 (one tensor-pipe pass over L_B), right-hand sides
+//      q = sqrt(c) (ybar - f) - z2, ONE factorisation of C with the q riding along as rows, back substitution,
+//      beta = f + sqrt(c) K_o v  (uniform grids: K_o v straight from the lag table; else L_B (L_B^T v)).
+// ybar = (X^T y)[f] / n_f (c.bhat).
 // ---------------------------------------------------------------------------------------------------------
 struct FusedArgs {
   const int* gorder;      // P groups, largest work first
@@ -309,14 +310,45 @@ struct FusedArgs {
   const int* cls_fn;
   const unsigned* cls_sid;
   unsigned sweep;
-  int rb;                 // right-hand-side rows per factorisation pass (8: compact slot, or 32)
 };
 
-__host__ __device__ inline size_t fused_smem_doubles(int n, int p, int mode, int rb) {
+constexpr int FUSED_RB = 8;   // functions per factorisation pass (right-hand-side rows riding along)
+
+__host__ __device__ inline size_t fused_smem_doubles(int n, int p, int mode) {
   const int nsub = mode == 2 ? 2 : 1;
   const int hh = mode == 2 ? n / 2 : n, NTm = (hh + TB - 1) / TB;
   const size_t tab = ((mode >= 1 ? (size_t)n : (size_t)n * p + n) + 3) & ~(size_t)3;
-  return (size_t)nsub * engine_smem_doubles(NTm, 1, rb) + tab;
+  return (size_t)nsub * engine_smem_doubles(NTm, 1, FUSED_RB) + tab;
+}
+// per-CTA global scratch (doubles): q rows, solved rows, prior draws -- FUSED_RB rows of nsub * hpad each
+__host__ __device__ inline size_t fused_scratch_doubles(int n, int mode) {
+  const int nsub = mode == 2 ? 2 : 1;
+  const int hh = mode == 2 ? n / 2 : n, NTm = (hh + TB - 1) / TB;
+  return (size_t)3 * FUSED_RB * nsub * NTm * TB;
+}
+
+// y[v][i] = sum_j M[i][j] x[v][j],  i < hh,  for the R vectors x + v*ld, with M = K_o (Toeplitz: tab[|i-j|]) or one of its
+// centrosymmetric blocks B+- (tab[|i-j|] +- tab[n-1-i-j]) generated from the lag table, plus dg * x (offset + jitter on the
+// diagonal).  Threads tid, tid + nthr, ... of the calling group each own rows; x is read as shared-memory broadcasts.
+template <bool CENTRO, int RMAX>
+__device__ __forceinline__ void table_matvec(const double* tab, int n, int hh, double sgn, double dg, const double* x, double* y,
+                                             int ld, int R, int tid, int nthr) {
+  for (int i = tid; i < hh; i += nthr) {
+    double acc[RMAX];
+#pragma unroll
+    for (int v = 0; v < RMAX; ++v) acc[v] = 0.0;
+    for (int j = 0; j < hh; ++j) {
+      const int d = i - j;
+      double t = tab[d < 0 ? -d : d];
+      if constexpr (CENTRO) t = fma(sgn, tab[n - 1 - i - j], t);
+#pragma unroll
+      for (int v = 0; v < RMAX; ++v)
+        if (v < R) acc[v] = fma(t, x[v * ld + j], acc[v]);
+    }
+#pragma unroll
+    for (int v = 0; v < RMAX; ++v)
+      if (v < R) y[v * ld + i] = fma(dg, x[v * ld + i], acc[v]);
+  }
 }
 
 template <int MODE>
@@ -324,27 +356,46 @@ __global__ void __launch_bounds__(NTHR, 2) k_group_fused(CtxDev c, FusedArgs a) 
   constexpr bool centro = (MODE == 2);
   constexpr int NSUB = centro ? 2 : 1, NWE = NW / NSUB, NTE = NWE * 32;
   const int n = c.n, hh = centro ? n / 2 : n, NTm = (hh + TB - 1) / TB, hpad = NTm * TB, ldv = hpad + 4;
-  const size_t esz = engine_smem_doubles(NTm, 1, a.rb), pltsz = (size_t)plt_tiles(NTm) * TILE;
+  const size_t esz = engine_smem_doubles(NTm, 1, FUSED_RB);
+  const size_t pltsz = (size_t)plt_tiles(NTm) * TILE;
   const int sub = threadIdx.x / NTE, tid = threadIdx.x - sub * NTE, warp = tid >> 5, lane = tid & 31;
-  const EngineSmem sm(smem_base() + (size_t)sub * esz, NTm, 1, a.rb);
-  const EngineSmem sm0(smem_base(), NTm, 1, a.rb);
-  const EngineSmem sm1(smem_base() + (size_t)(NSUB - 1) * esz, NTm, 1, a.rb);
+  double* ebase = smem_base() + (size_t)sub * esz;
+  const EngineSmem sg(ebase, NTm, 1, FUSED_RB);
+  double* dvec = sg.dvec;
+  double* rinv = sg.rinv;
+  double* scratch = sg.P;                             // panel slots, idle between factorisations: 8 + 8 vectors, then z2
+  double* scratch1 = smem_base() + (size_t)(NSUB - 1) * esz + (scratch - ebase);   // the other half's (sub 1) scratch
+  double* scratch0 = smem_base() + (scratch - ebase);
+  double* red0 = EngineSmem(smem_base(), NTm, 1, FUSED_RB).red();
   double* tab = smem_base() + (size_t)NSUB * esz;   // MODE >= 1: lag table (n); else scaled inputs (n*p) + xsq (n)
   double* xsq = tab + (size_t)n * c.p;
-  double* xa = sm.P;                                // 8 + 8 vectors (the panel slots are idle between factorisations)
-  double* xb = sm.P + 8 * ldv;
+  double* xa = scratch;
+  double* xb = scratch + FUSED_RB * ldv;
+  double* z2b = xb + FUSED_RB * ldv;                  // centro: FUSED_RB x n full-domain z2 (fits: see fused_smem check)
   double* Wb = c.ws + (size_t)blockIdx.x * c.ws_stride;
   double* LBt = Wb + (size_t)sub * pltsz;                      // factor(s) of K_o
   double* WC = Wb + (size_t)(NSUB + sub) * pltsz;              // factor(s) of C
   double* Wx = Wb + (size_t)2 * NSUB * pltsz + (size_t)sub * NTm * TILE;
   const int rowlen = NSUB * hpad;
-  double* qrow = c.fws + (size_t)blockIdx.x * c.fws_stride + (size_t)sub * hpad;   // rb rows of q, then rb solved rows
-  double* wrow = qrow + (size_t)a.rb * rowlen;
+  double* qrow = c.fws + (size_t)blockIdx.x * c.fws_stride + (size_t)sub * hpad;   // FUSED_RB rows of q, solved rows, prior draws
+  double* wrow = qrow + (size_t)FUSED_RB * rowlen;
+  double* frow = wrow + (size_t)FUSED_RB * rowlen;
   const double sgn = sub ? -1.0 : 1.0;
   const Stream rng{c.k0, c.k1};
   auto gsync = [&]() {
     if constexpr (NSUB == 1) __syncthreads();
     else bar_sync<NTE>(1 + 3 * sub);
+  };
+  // one factorisation on this half's engine; RHSROWS: q rows ride along.  All threads of the CTA get the combined verdict.
+  auto factor = [&](auto src, bool with_rhs, double* Wout, int cnt) -> bool {
+    bool okh;
+    if (with_rhs)
+      okh = chol_engine<AUG_RHS, true, decltype(src), NWE>(src, EngineIO{Wout, Wx, RowSrc{qrow, nullptr, rowlen, cnt, hh}, wrow, rowlen},
+                                                         NTm, 1, (cnt + 7) / 8, sg, sub);
+    else
+      okh = chol_engine<AUG_NONE, true, decltype(src), NWE>(src, EngineIO{Wout, nullptr, RowSrc{nullptr, nullptr, 0, 0, 0}, nullptr, 0},
+                                                          NTm, 0, 0, sg, sub);
+    return !__syncthreads_or(okh ? 0 : 1);
   };
   __shared__ int s_chain;
   for (int item = next_chain(c.sched, &s_chain); item < c.C * c.P; item = next_chain(c.sched, &s_chain)) {
@@ -356,7 +407,7 @@ __global__ void __launch_bounds__(NTHR, 2) k_group_fused(CtxDev c, FusedArgs a) 
     __syncthreads();
     FT_INIT
     FT_COUNT
-    if constexpr (MODE >= 1) toeplitz_table(c.d2, n, sigma, ls, tab, sm0.red());
+    if constexpr (MODE >= 1) toeplitz_table(c.d2, n, sigma, ls, tab, red0);
     else rbf_scale_inputs(c.x, n, c.p, ls, tab, xsq);
     FT(0);
     // ---------------- 1. jitchol(K_o) ----------------
@@ -364,14 +415,12 @@ __global__ void __launch_bounds__(NTHR, 2) k_group_fused(CtxDev c, FusedArgs a) 
     double jitter = 0.0;
     for (;;) {
       __syncthreads();
-      for (int t = tid; t < hpad; t += NTE) sm.dvec[t] = (t < hh) ? c.offset + jitter : 0.0;
+      for (int t = tid; t < hpad; t += NTE) dvec[t] = (t < hh) ? c.offset + jitter : 0.0;
       __syncthreads();
-      EngineIO io{LBt, nullptr, RowSrc{nullptr, nullptr, 0, 0, 0}, nullptr, 0};
-      bool okh;
-      if constexpr (MODE == 2) okh = chol_engine<AUG_NONE, true, SrcCentro, NWE>(SrcCentro{tab, n, hh, sgn}, io, NTm, 0, 0, sm, sub);
-      else if constexpr (MODE == 1) okh = chol_engine<AUG_NONE, true>(SrcToeplitz{tab, n}, io, NTm, 0, 0, sm);
-      else okh = chol_engine<AUG_NONE, true>(SrcRbf{tab, xsq, n, c.p, sigma}, io, NTm, 0, 0, sm);
-      const bool ok = !__syncthreads_or(okh ? 0 : 1);
+      bool ok;
+      if constexpr (MODE == 2) ok = factor(SrcCentro{tab, n, hh, sgn}, false, LBt, 0);
+      else if constexpr (MODE == 1) ok = factor(SrcToeplitz{tab, n}, false, LBt, 0);
+      else ok = factor(SrcRbf{tab, xsq, n, c.p, sigma}, false, LBt, 0);
       if (ok) { code = tries; break; }
       const double dm = sigma + c.offset;                 // jitchol ladder (linalg.py:41-54)
       if (tries == 0) {
@@ -391,90 +440,105 @@ __global__ void __launch_bounds__(NTHR, 2) k_group_fused(CtxDev c, FusedArgs a) 
         const int nf = a.cls_off[cls + 1] - a.cls_off[cls];
         const double cc = c.G[(size_t)fns[0] * c.f + fns[0]] * yinv;     // function.py:30 with n_t = (X^T X)[f,f]
         const double sc = sqrt(cc);
-        for (int j0 = 0; j0 < nf; j0 += a.rb) {
-          const int cnt = (nf - j0 < a.rb) ? nf - j0 : a.rb;
-          // ---- right-hand sides  q = sqrt(c) (ybar - f) - z2,  f = L_B z1, eight functions per pass ----
-          for (int v0 = 0; v0 < cnt; v0 += 8) {
-            const int R = (cnt - v0 < 8) ? cnt - v0 : 8;
-            gsync();
-            for (int e = tid; e < 8 * hpad; e += NTE) {
-              const int v = e / hpad, i = e % hpad;
-              xa[v * ldv + i] = (v < R && i < hh) ? normal_elem(rng, gch, a.sweep, sids[j0 + v0 + v], sub * hh + i) : 0.0;
+        for (int j0 = 0; j0 < nf; j0 += FUSED_RB) {
+          const int R = (nf - j0 < FUSED_RB) ? nf - j0 : FUSED_RB;
+          // ---- normals: z1 in the split domain (this half's block), z2 in the time domain ----
+          gsync();
+          for (int e = tid; e < FUSED_RB * ldv; e += NTE) xa[e] = 0.0;
+          gsync();
+          {
+            const int e0 = sub * hh, p0 = e0 >> 1, p1 = (e0 + hh - 1) >> 1, np1 = p1 - p0 + 1;
+            for (int q = tid; q < R * np1; q += NTE) {
+              const int v = q / np1, pr = p0 + q % np1;
+              double za, zb;
+              rng.normal_pair(gch, a.sweep, sids[j0 + v], (unsigned)pr, za, zb);
+              const int ea = 2 * pr - e0, eb = ea + 1;
+              if (ea >= 0 && ea < hh) xa[v * ldv + ea] = za;
+              if (eb >= 0 && eb < hh) xa[v * ldv + eb] = zb;
             }
-            gsync();
-            trimv_dmma<false, NWE>(LBt, NTm, xa, xb, ldv, R, warp, lane);
-            gsync();
-            for (int e = tid; e < R * hh; e += NTE) {
-              const int v = e / hh, i = e % hh;
-              const int fn = fns[j0 + v0 + v];
-              const unsigned sid = sids[j0 + v0 + v];
-              const double* yb = c.bhat + (size_t)fn * n;
-              double yt, z2;
-              if constexpr (centro) {
-                yt = (yb[i] + sgn * yb[n - 1 - i]) * RSQRT2;
-                z2 = (normal_elem(rng, gch, a.sweep, sid, n + i) + sgn * normal_elem(rng, gch, a.sweep, sid, 2 * n - 1 - i)) * RSQRT2;
-              } else {
-                yt = yb[i];
-                z2 = normal_elem(rng, gch, a.sweep, sid, n + i);
-              }
-              qrow[(size_t)(v0 + v) * rowlen + i] = sc * (yt - xb[v * ldv + i]) - z2;
+            // z2 = elements n .. 2n-1: pairs (n >> 1) ..
+            const int q0 = n >> 1, q1 = (2 * n - 1) >> 1, nq = q1 - q0 + 1;
+            for (int q = tid; q < R * nq; q += NTE) {
+              const int v = q / nq, pr = q0 + q % nq;
+              double za, zb;
+              rng.normal_pair(gch, a.sweep, sids[j0 + v], (unsigned)pr, za, zb);
+              const int ea = 2 * pr - n, eb = ea + 1;
+              if (ea >= 0 && ea < n) z2b[v * n + ea] = za;
+              if (eb >= 0 && eb < n) z2b[v * n + eb] = zb;
             }
+          }
+          gsync();
+          // ---- prior draws f = L_B z1, right-hand sides q = sqrt(c) (ybar - f) - z2 ----
+          trimv_dmma<false, NWE>(LBt, NTm, xa, xb, ldv, R, warp, lane);
+          gsync();
+          for (int e = tid; e < R * hh; e += NTE) {
+            const int v = e / hh, i = e % hh;
+            const double* yb = c.bhat + (size_t)fns[j0 + v] * n;
+            double yt, z2;
+            if constexpr (centro) {
+              yt = (yb[i] + sgn * yb[n - 1 - i]) * RSQRT2;
+              z2 = (z2b[v * n + i] + sgn * z2b[v * n + n - 1 - i]) * RSQRT2;
+            } else {
+              yt = yb[i];
+              z2 = z2b[v * n + i];
+            }
+            const double fv = xb[v * ldv + i];
+            frow[(size_t)v * rowlen + i] = fv;
+            qrow[(size_t)v * rowlen + i] = sc * (yt - fv) - z2;
           }
           // ---- C = I + c K_o with the q riding along ----
           gsync();
           FT(2);
-          for (int t = tid; t < hpad; t += NTE) sm.dvec[t] = (t < hh) ? 1.0 + cc * (c.offset + jitter) : 0.0;
-          gsync();
-          EngineIO io{WC, Wx, RowSrc{qrow, nullptr, rowlen, cnt, hh}, wrow, rowlen};
-          const int ntl = (cnt + 7) / 8;
-          bool okh;
-          if constexpr (MODE == 2)
-            okh = chol_engine<AUG_RHS, true, SrcScaled<SrcCentro>, NWE>(SrcScaled<SrcCentro>{SrcCentro{tab, n, hh, sgn}, cc, hh}, io, NTm, 1, ntl, sm, sub);
-          else if constexpr (MODE == 1)
-            okh = chol_engine<AUG_RHS, true>(SrcScaled<SrcToeplitz>{SrcToeplitz{tab, n}, cc, n}, io, NTm, 1, ntl, sm);
-          else okh = chol_engine<AUG_RHS, true>(SrcScaled<SrcRbf>{SrcRbf{tab, xsq, n, c.p, sigma}, cc, n}, io, NTm, 1, ntl, sm);
-          const bool okc = !__syncthreads_or(okh ? 0 : 1);
+          for (int t = tid; t < hpad; t += NTE) dvec[t] = (t < hh) ? 1.0 + cc * (c.offset + jitter) : 0.0;
+          __syncthreads();
+          bool okc;
+          if constexpr (MODE == 2) okc = factor(SrcScaled<SrcCentro>{SrcCentro{tab, n, hh, sgn}, cc, hh}, true, WC, R);
+          else if constexpr (MODE == 1) okc = factor(SrcScaled<SrcToeplitz>{SrcToeplitz{tab, n}, cc, n}, true, WC, R);
+          else okc = factor(SrcScaled<SrcRbf>{SrcRbf{tab, xsq, n, c.p, sigma}, cc, n}, true, WC, R);
           FT(3);
           ++nfact;
           if (!okc) { code = GPF_STATUS_NOT_PD; break; }
-          // ---- v = L_C^-T w;  beta = L_B (z1 + sqrt(c) L_B^T v) ----
-          for (int v0 = 0; v0 < cnt; v0 += 8) {
-            const int R = (cnt - v0 < 8) ? cnt - v0 : 8;
-            gsync();
-            for (int e = tid; e < 8 * hpad; e += NTE) {
-              const int v = e / hpad, i = e % hpad;
-              xa[v * ldv + i] = (v < R && i < hh) ? wrow[(size_t)(v0 + v) * rowlen + i] : 0.0;
-            }
-            if (R <= 2) back_solve_g<2, NWE>(WC, NTm, xa, ldv, sm.rinv, sub);
-            else back_solve_g<8, NWE>(WC, NTm, xa, ldv, sm.rinv, sub);
-            FT(4);
-            for (int e = tid; e < R * hh; e += NTE) xa[(e / hh) * ldv + e % hh] *= sc;
-            gsync();
-            trimv_dmma<true, NWE>(LBt, NTm, xa, xb, ldv, R, warp, lane);
+          // ---- v = L_C^-T w ----
+          for (int e = tid; e < FUSED_RB * hpad; e += NTE) {
+            const int v = e / hpad, i = e % hpad;
+            xa[v * ldv + i] = (v < R && i < hh) ? wrow[(size_t)v * rowlen + i] : 0.0;
+          }
+          if (R <= 2) back_solve_g<2, NWE>(WC, NTm, xa, ldv, rinv, sub);
+          else back_solve_g<8, NWE>(WC, NTm, xa, ldv, rinv, sub);
+          FT(4);
+          // ---- beta = f + sqrt(c) K_o v ----
+          if constexpr (MODE >= 1) {
+            if (R <= 2) table_matvec<centro, 2>(tab, n, hh, sgn, c.offset + jitter, xa, xb, ldv, R, tid, NTE);
+            else table_matvec<centro, FUSED_RB>(tab, n, hh, sgn, c.offset + jitter, xa, xb, ldv, R, tid, NTE);
             gsync();
             for (int e = tid; e < R * hh; e += NTE) {
               const int v = e / hh, i = e % hh;
-              xb[v * ldv + i] += normal_elem(rng, gch, a.sweep, sids[j0 + v0 + v], sub * hh + i);
+              xa[v * ldv + i] = fma(sc, xb[v * ldv + i], frow[(size_t)v * rowlen + i]);
             }
+          } else {
+            trimv_dmma<true, NWE>(LBt, NTm, xa, xb, ldv, R, warp, lane);       // K_o v = L_B (L_B^T v)
             gsync();
             trimv_dmma<false, NWE>(LBt, NTm, xb, xa, ldv, R, warp, lane);
-            __syncthreads();
-            FT(5);
-            const double* p0 = sm0.P;
-            const double* p1 = sm1.P;
-            for (int e = threadIdx.x; e < R * hh; e += NTHR) {
+            gsync();
+            for (int e = tid; e < R * hh; e += NTE) {
               const int v = e / hh, i = e % hh;
-              double* Fo = c.F + ((size_t)ch * c.f + fns[j0 + v0 + v]) * n;
-              if constexpr (centro) {
-                const double bp = p0[v * ldv + i], bm = p1[v * ldv + i];
-                Fo[i] = (bp + bm) * RSQRT2;
-                Fo[n - 1 - i] = (bp - bm) * RSQRT2;
-              } else Fo[i] = p0[v * ldv + i];
+              xa[v * ldv + i] = fma(sc, xa[v * ldv + i], frow[(size_t)v * rowlen + i]);
             }
-            __syncthreads();
-            FT(6);
           }
-          ndraw += cnt;
+          __syncthreads();
+          FT(5);
+          for (int e = threadIdx.x; e < R * hh; e += NTHR) {
+            const int v = e / hh, i = e % hh;
+            double* Fo = c.F + ((size_t)ch * c.f + fns[j0 + v]) * n;
+            if constexpr (centro) {
+              const double bp = scratch0[v * ldv + i], bm = scratch1[v * ldv + i];
+              Fo[i] = (bp + bm) * RSQRT2;
+              Fo[n - 1 - i] = (bp - bm) * RSQRT2;
+            } else Fo[i] = scratch0[v * ldv + i];
+          }
+          __syncthreads();
+          FT(6);
+          ndraw += R;
         }
         if (code < 0) break;
       }

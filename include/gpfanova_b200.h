@@ -192,7 +192,7 @@ int gpf_set_profile(gpf_ctx* ctx, int on);
 int gpf_get_profile(gpf_ctx* ctx, double* h_ms6, unsigned long long* h_launches);
 /* development aid: cycle counters of the phases of the fused function kernel, read and cleared (all zero unless the
  * library was built with -DGPF_FTRACE; tools/fused_trace.py) */
-int gpf_debug_trace(gpf_ctx* ctx, unsigned long long* h_cycles8);
+int gpf_debug_trace(gpf_ctx* ctx, unsigned long long* h_cycles24);
 
 #ifdef __cplusplus
 }

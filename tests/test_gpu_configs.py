@@ -113,8 +113,7 @@ def test_fused_launch_equals_sequential_order_at_size(eng, shape):
         assert np.max(np.abs(o - outs[2])) < 1e-7 * scale, (name, np.max(np.abs(o - outs[2])))
     assert fchol[2] == C * d.f and fchol[1] == C * d.f and fchol[0] <= fchol[1]
     if hc:
-        rbs = 32 if max(len(g) for g in groups) > 8 else 8
-        assert fchol[0] == C * sum(-(-len(g) // rbs) for g in groups)      # one factorisation of C per class (and pass)
+        assert fchol[0] == C * sum(-(-len(g) // 8) for g in groups)      # one factorisation of C per class and pass of 8
 
 
 @pytest.mark.parametrize("name", ["cokol5x5_hc_n20", "oneway_n64"])

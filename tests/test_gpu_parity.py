@@ -416,9 +416,9 @@ def test_full_size_identities(eng):
         assert relerr(LC[ch], st["L_C"]) < 1e-10
         assert relerr(mu[ch], st["mu"]) < 1e-10
         # Sigma = K_o - W^T W is rebuilt here in NumPy from the device factor: it cancels |K_o| / |Sigma| ~ 1e5 at n = 256,
-        # so the reconstruction itself carries sqrt(n) eps |K_o| / |Sigma| whatever the accuracy of L_C (checked above)
+        # so the reconstruction itself carries a few sqrt(n) eps |K_o| / |Sigma| whatever the accuracy of L_C (checked above)
         amp = np.max(np.abs(K)) / np.max(np.abs(st["cov"]))
-        assert relerr(cov_from_LC(K, LC[ch], nt[ch], hyper[ch, 0]), st["cov"]) < max(1e-10, np.sqrt(n) * EPS * amp)
+        assert relerr(cov_from_LC(K, LC[ch], nt[ch], hyper[ch, 0]), st["cov"]) < max(1e-10, 4 * np.sqrt(n) * EPS * amp)
         assert relerr(F1[ch, f], orc.function_draw_obs(st, SB, z[ch])) < 1e-8
         m_o, n_o = orc.function_moments(y, d.X, F, f)
         assert relerr(mt[ch], m_o) < 1e-12 and relerr(nt[ch], n_o) < 1e-14

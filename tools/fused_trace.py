@@ -15,6 +15,7 @@ VARIANT = os.path.join(ROOT, "build_variants", "libgpf_ftrace.so")
 
 
 def build(extra=()):
+    extra = list(extra) + [a for a in sys.argv[1:] if a.startswith("-D")]
     from gpfanova_b200 import build as b
     os.makedirs(os.path.dirname(VARIANT), exist_ok=True)
     cmd = [b._nvcc()] + b.NVCC_FLAGS + ["-DGPF_FTRACE"] + list(extra) + ["-o", VARIANT, "gpf_api.cu"]
@@ -28,7 +29,7 @@ def main():
     ap.add_argument("--chains", type=int, default=4096)
     ap.add_argument("--n", type=int, default=256)
     ap.add_argument("--sweeps", type=int, default=5)
-    a = ap.parse_args()
+    a, _ = ap.parse_known_args()
     if a.build:
         return build()
     import numpy as np
@@ -43,7 +44,7 @@ def main():
     eng.set_state(hyper=synthetic.chain_starts(a.chains, len(groups)))
     eng.sweep(20)
     eng.sync()
-    t = (C.c_ulonglong * 8)()
+    t = (C.c_ulonglong * 24)()
     eng._ck(eng._lib.gpf_debug_trace(eng._h, t))
     eng.set_profile(1)
     eng.sweep(a.sweeps)
@@ -58,6 +59,10 @@ def main():
     print("traced items %d, cycles per item %.0f" % (items, tot / items))
     for nm, q in zip(names, v[:7]):
         print("  %-20s %9.0f cycles/item  %5.1f %%" % (nm, q / items, 100.0 * q / max(1, tot)))
+    calls = max(1, v[16])
+    print("small engine: %d traced calls" % calls)
+    for nm, q in zip(["A potrf", "A panel solve", "A tile(1,1)+rhs", "A waiting", "B panel/stores", "B updates", "B rhs", "B waiting"], v[8:16]):
+        print("  %-20s %9.0f cycles/call" % (nm, q / calls))
 
 
 if __name__ == "__main__":
