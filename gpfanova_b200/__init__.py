@@ -11,7 +11,7 @@ Importing the package never needs a GPU; every compute call does (there is no CP
 import logging
 
 from . import _capi, engine  # noqa: F401
-from . import linalg, kernel, sample, base, mean, fanova, prior  # noqa: F401
+from . import linalg, kernel, sample, base, mean, fanova, prior, interval  # noqa: F401
 
 logging.basicConfig()
 logger = logging.getLogger(__name__)

@@ -1,17 +1,19 @@
-"""Base model y(t) = X b(t) (gpfanova/base.py:7-259) with the Gibbs sweep running on the GPU.
+"""Base model  y(t) = X b(t) + noise  -- the API of gpfanova/base.py:7-259 with the Gibbs sweep on the GPU.
 
-Construction, sampler order and label scheme follow the reference (base.py:16-86, 114-138); `sample()` drives the
-fused device sweep (gpf_sweep) for `chains` independent chains instead of looping over Python samplers.
-`parameter_cache` / `parameter_history` keep the reference's schema and always describe chain 0; all chains are
-available through `chain_state()` / `chain_history()`.
+What the reference fixes and this class keeps: the constructor arguments, the ORDER of the samplers (base.py:57-84:
+`y_sigma`; per prior group its functions (each followed by its derivative when derivatives=True), `prior{g}_sigma`,
+`prior{g}_lengthscale`; then the subclass's extra samplers), the label scheme `f{i}(x_t)` (base.py:114-138) and with
+them the columns of `parameter_cache` / `parameter_history`.  `sample()` runs the fused device sweep (gpf_sweep) for
+`chains` independent chains instead of looping over Python samplers; `parameter_cache` / `parameter_history` describe
+chain 0, `chain_state()` / `chain_history()` / `save(f, chain=c)` every chain.
 
-New, additive keyword arguments: chains=1, seed=None, device=None, devices=None (list of GPU ordinals: the chains are
-sharded over them, no inter-GPU communication), store_chains=True.
+Additive keyword arguments: chains=1, seed=None, device=None, devices=None (GPU ordinals: the chains are sharded over
+them, no inter-GPU communication), store_chains=True.
 """
-import os
-import sys
 import logging
+import os
 import random as pyrandom
+import sys
 import time
 
 import numpy as np
@@ -20,7 +22,10 @@ import torch
 
 from . import engine as _engine
 from .kernel import RBF, White
-from .sample import Function, SamplerContainer, Slice
+from .sample import Function, FunctionDerivative, SamplerContainer, Slice
+
+LOG = logging.getLogger(__name__)
+DEFAULT_SLICE = (.1, 10)          # (w, m) of every hyper-parameter slice sampler, base.py:52,75,79
 
 
 class Base(SamplerContainer):
@@ -28,77 +33,40 @@ class Base(SamplerContainer):
 
     def __init__(self, x, y, hyperparam_kwargs={}, derivatives=False, chains=1, seed=None, device=None, devices=None,
                  store_chains=True, *args, **kwargs):
-        self.x = x
-        self.y = y
-        self._observationIndexBaseList = None
-        self.n = self.x.shape[0]
-        assert self.y.shape[0] == self.n, 'x and y must have same first dimension shape!'
-        self.p = self.x.shape[1]
-        self.m = self.y.shape[1]
+        self.x, self.y = x, y
+        self.n, self.p = x.shape
+        assert y.shape[0] == self.n, 'x and y must have same first dimension shape!'
+        self.m = y.shape[1]
         self.chains = int(chains)
         self.seed = int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else int(seed)
         self.device = device
-        self.devices = None if devices is None else list(devices)     # several GPUs of one box: chains are sharded
+        self.devices = None if devices is None else list(devices)
         self.store_chains = store_chains
-        if derivatives:
-            raise NotImplementedError("derivatives=True (FunctionDerivative, sample/function.py:43-66) is not part of "
-                                      "the GPU hot path yet")
+        self.derivatives = bool(derivatives)
+        self._observationIndexBaseList = None
 
         self.design_matrix = None
         self.buildDesignMatrix()
         self.f = self.design_matrix.shape[1]
+        rank = np.linalg.matrix_rank(self.design_matrix)
+        if self.f > rank:
+            LOG.error("design matrix is of rank %d, but there are %d functions!" % (rank, self.f))
+        if np.isnan(self.y).any():
+            LOG.error("NaN values in observation matrix, this is not supported!")
 
-        if self.f > np.linalg.matrix_rank(self.design_matrix):
-            logging.getLogger(__name__).error("design matrix is of rank %d, but there are %d functions!" % (
-                np.linalg.matrix_rank(self.design_matrix), self.f))
-        if np.any(np.isnan(self.y)):
-            logging.getLogger(__name__).error("NaN values in observation matrix, this is not supported!")
-
-        # kernels and samplers, in the reference's order (base.py:51-84)
-        self.y_k = White(self, ['y_sigma'], logspace=True)
-        wm = []
-        w, m = .1, 10
-        if 'y_sigma' in hyperparam_kwargs:
-            w, m = hyperparam_kwargs['y_sigma']
-        elif 'sigma' in hyperparam_kwargs:
-            w, m = hyperparam_kwargs['sigma']
-        wm.append((w, m))
-        samplers = [Slice('y_sigma', 'y_sigma', lambda x: self.observationLikelihood(sigma=x, prior_lb=-2, prior_ub=2),
-                          w, m, base=self, hyper_index=0)]
-        self.kernels = []
-        fxn_names = self.functionNames()
         self._groups = [list(g) for g in self.priorGroups()]
-        self._hyper_names = ['y_sigma']
-        for i, p in enumerate(self._groups):
-            self.kernels.append(RBF(self, ['prior%d_sigma' % i, 'prior%d_lengthscale' % i], logspace=True))
-            for f in p:
-                s = fxn_names[f] if f in fxn_names else "f%d" % f
-                samplers.append(Function('%s' % s, self.functionIndex(f), self, f, self.kernels[-1]))
-            w, m = .1, 10
-            if 'sigma' in hyperparam_kwargs:
-                w, m = hyperparam_kwargs['sigma']
-            wm.append((w, m))
-            samplers.append(Slice('prior%d_sigma' % i, 'prior%d_sigma' % i,
-                                  lambda x, p=i: self.prior_likelihood(p=p, sigma=x, prior_lb=-2, prior_ub=2), w, m,
-                                  base=self, hyper_index=1 + 2 * i))
-            w, m = .1, 10
-            if 'lengthscale' in hyperparam_kwargs:
-                w, m = hyperparam_kwargs['lengthscale']
-            wm.append((w, m))
-            samplers.append(Slice('prior%d_lengthscale' % i, 'prior%d_lengthscale' % i,
-                                  lambda x, p=i: self.prior_likelihood(p=p, lengthscale=x, prior_lb=-2, prior_ub=2), w, m,
-                                  base=self, hyper_index=2 + 2 * i))
-            self._hyper_names += ['prior%d_sigma' % i, 'prior%d_lengthscale' % i]
-        self._slice_wm = wm
+        samplers = self._core_samplers(hyperparam_kwargs)
         self._n_core_samplers = len(samplers)
-        samplers.extend(self._additionalSamplers())
+        samplers += self._additionalSamplers()
 
         self.H = len(self._hyper_names)
         self._flabels = [lab for f in range(self.f) for lab in self.functionIndex(f)]
+        self._dlabels = [lab for f in range(self.f) for lab in self.functionIndex(f, derivative=True)] if self.derivatives else []
         self._eng = None
         self._eng_key = None
         self._manual_calls = 0
         self._chain_blocks = []
+        self._deriv_blocks = []
         self._F = np.zeros((self.chains, self.f, self.n))
         self._hyper = np.zeros((self.chains, self.H))
 
@@ -106,11 +74,43 @@ class Base(SamplerContainer):
         # initial values given by sampler name (container.py:16-18) apply to every chain
         self._F[:] = self.parameter_cache[self._flabels].values.astype(float).reshape(self.f, self.n)[None]
         self._hyper[:] = self.parameter_cache[self._hyper_names].values.astype(float)[None]
-        self._transform_labels = [lab for s in self.samplers[self._n_core_samplers:] for lab in s.parameters]
+        self._transform_labels = [lab for s in self.samplers if s.type == 'Transform' for lab in s.parameters]
         pos = {lab: i for i, lab in enumerate(self.parameter_cache.index)}
         self._pos_h = np.array([pos[l] for l in self._hyper_names], dtype=np.int64)
         self._pos_F = np.array([pos[l] for l in self._flabels], dtype=np.int64)
+        self._pos_D = np.array([pos[l] for l in self._dlabels], dtype=np.int64)
         self._pos_T = np.array([pos[l] for l in self._transform_labels], dtype=np.int64)
+
+    def _core_samplers(self, hyperparam_kwargs):
+        """the reference's sampler list up to the subclass's extras; also fills y_k, kernels, _hyper_names, _slice_wm"""
+        def wm(*keys):
+            for k in keys:
+                if k in hyperparam_kwargs:
+                    return tuple(hyperparam_kwargs[k])
+            return DEFAULT_SLICE
+        names = self.functionNames()
+        self.y_k = White(self, ['y_sigma'], logspace=True)
+        self.kernels = []
+        self._hyper_names = ['y_sigma']
+        self._slice_wm = [wm('y_sigma', 'sigma')]
+        out = [Slice('y_sigma', 'y_sigma', lambda v: self.observationLikelihood(sigma=v, prior_lb=-2, prior_ub=2),
+                     *self._slice_wm[0], base=self, hyper_index=0)]
+        for g, members in enumerate(self._groups):
+            ps, pl = 'prior%d_sigma' % g, 'prior%d_lengthscale' % g
+            kern = RBF(self, [ps, pl], logspace=True)
+            self.kernels.append(kern)
+            for f in members:
+                nm = names.get(f, "f%d" % f)
+                out.append(Function(nm, self.functionIndex(f), self, f, kern))
+                if self.derivatives:
+                    out.append(FunctionDerivative('d' + nm, self.functionIndex(f, derivative=True), self, f, kern))
+            for key, pname, which in (('sigma', ps, 'sigma'), ('lengthscale', pl, 'lengthscale')):
+                self._slice_wm.append(wm(key))
+                out.append(Slice(pname, pname, lambda v, g=g, which=which: self.prior_likelihood(
+                    p=g, prior_lb=-2, prior_ub=2, **{which: v}), *self._slice_wm[-1], base=self,
+                    hyper_index=len(self._hyper_names)))
+                self._hyper_names.append(pname)
+        return out
 
     # ------------------------------------------------------------------ reference protocol (base.py:88-149)
     def _additionalSamplers(self):
@@ -126,25 +126,21 @@ class Base(SamplerContainer):
     def _buildDesignMatrix(self):
         raise NotImplementedError("Implement a design matrix for your model!")
 
-    def functionIndex(self, i, derivative=False, *args, **kwargs):
-        if derivative:
-            return ['df%d(%s)' % (i, z) for z in self._observationIndexBase()]
-        return ['f%d(%s)' % (i, z) for z in self._observationIndexBase()]
-
-    def functionPrior(self, f):
-        priors = self.priorGroups()
-        for i in range(len(priors)):
-            if f in priors[i]:
-                return i
-        return -1
-
-    def _observationIndexBase(self):
-        if self._observationIndexBaseList is None:
-            self._observationIndexBaseList = ['%s' % str(z) for z in self.x]
-        return self._observationIndexBaseList
-
     def priorGroups(self):
         raise NotImplementedError("Implement a prior grouping function for your model!")
+
+    def _observationIndexBase(self):
+        """the time-point part of every label: str() of the row of x (base.py:129-138)"""
+        if self._observationIndexBaseList is None:
+            self._observationIndexBaseList = [str(z) for z in self.x]
+        return self._observationIndexBaseList
+
+    def functionIndex(self, i, derivative=False, *args, **kwargs):
+        stem = 'df%d' if derivative else 'f%d'
+        return [(stem % i) + '(%s)' % z for z in self._observationIndexBase()]
+
+    def functionPrior(self, f):
+        return next((g for g, members in enumerate(self.priorGroups()) if f in members), -1)
 
     def _priorParameters(self, i):
         if i < 0:
@@ -156,35 +152,29 @@ class Base(SamplerContainer):
     def offset(self):
         return 1e-9
 
-    # ------------------------------------------------------------------ state accessors (base.py:151-198)
+    # ------------------------------------------------------------------ state accessors (base.py:151-198), chain 0
     def functionMatrix(self, remove=[], only=[], derivative=False):
-        """current function values of chain 0 from parameter_cache, (n, #functions)"""
-        functions = []
-        if len(only) > 0:
-            for o in only:
-                functions.append(self.functionIndex(o, derivative=derivative))
-        else:
-            for f in range(self.f):
-                functions.append(None if f in remove else self.functionIndex(f, derivative=derivative))
-        out = np.zeros((self.n, len(functions)))
-        for i, z in enumerate(functions):
-            if z is not None:
-                out[:, i] = self.parameter_cache[z]
+        """current function values from parameter_cache, (n, #functions); removed functions are zero columns"""
+        which = list(only) if len(only) > 0 else list(range(self.f))
+        out = np.zeros((self.n, len(which)))
+        for col, f in enumerate(which):
+            if len(only) > 0 or f not in remove:
+                out[:, col] = self.parameter_cache[self.functionIndex(f, derivative=derivative)]
         return out
 
     def functionSamples(self, f, *args, **kwargs):
         return self.parameter_history[self.functionIndex(f, *args, **kwargs)]
 
     def residual(self, remove=[], only=[]):
-        return self.y.T - np.dot(self.design_matrix, self.functionMatrix(remove, only).T)
+        return self.y.T - self.design_matrix.dot(self.functionMatrix(remove, only).T)
 
     def functionResidual(self, f):
-        resid = self.residual(remove=[f])
-        resid = (resid.T / self.design_matrix[:, f].T).T
-        return resid[self.design_matrix[:, f] != 0, :]
+        load = self.design_matrix[:, f]
+        keep = load != 0
+        return self.residual(remove=[f])[keep] / load[keep, None]
 
     def observationMean(self):
-        return np.dot(self.design_matrix, self.functionMatrix().T).ravel()
+        return self.design_matrix.dot(self.functionMatrix().T).ravel()
 
     # ------------------------------------------------------------------ device plumbing
     def engine(self):
@@ -195,7 +185,9 @@ class Base(SamplerContainer):
         if not stale and not (np.array_equal(self._eng.y, self.y, equal_nan=True) and np.array_equal(self._eng.x, self.x)):
             stale = True
         if stale:
+            done = 0
             if self._eng is not None:
+                done = self._eng.sweeps_done      # the Philox stream (keyed by the sweep number) continues across rebuilds
                 self._eng.close()
             w = [a for a, _ in self._slice_wm]
             m = [b for _, b in self._slice_wm]
@@ -207,6 +199,8 @@ class Base(SamplerContainer):
                 self._eng = _engine.ChainEngine(self.x, self.y, self.design_matrix, self._groups, chains=self.chains,
                                                 seed=self.seed, device=dev, slice_w=w, slice_m=m)
             self._eng_key = key
+            for e in getattr(self._eng, "engines", [self._eng]):
+                e.sweeps_done = done
         return self._eng
 
     def _push_state(self):
@@ -287,6 +281,32 @@ class Base(SamplerContainer):
         self._pull_state()
         return float(self._hyper[0, h])
 
+    def _group_log10(self, hyper, g):
+        return hyper[..., 1 + 2 * g], hyper[..., 2 + 2 * g]
+
+    def _device_derivatives(self, hyper, F, stream_id, z=None, want_moments=False):
+        """FunctionDerivative draws (sample/function.py:43-66) for states hyper (R, H), F (R, f, n): (R, f, n) array of
+        beta'_f ~ N(K_ba K_a^-1 beta_f, K_b - K_ba K_a^-1 K_ba^T) with the group's kernel at that state"""
+        R = hyper.shape[0]
+        dF = np.zeros((R, self.f, self.n))
+        moments = {}
+        for g, members in enumerate(self._groups):
+            ls, ll = self._group_log10(hyper, g)
+            zz = None if z is None else np.ascontiguousarray(z[:, members, :])
+            out = _engine.function_derivative(self.x, ls, ll, F[:, members, :], z=zz, seed=self.seed, stream_id=stream_id + g,
+                                              device=self._dev(), want_moments=want_moments, raise_on_error=False)
+            dF[:, members, :] = out[0].cpu().numpy()
+            if (out[-1] < 0).any() and not getattr(self, "_deriv_warned", False):
+                self._deriv_warned = True
+                LOG.error("FunctionDerivative: covariance not positive definite (prior %d); the reference's derivative kernels "
+                          "(rbf.pyx:34-37) only form a covariance at lengthscale 1 -- derivative draws are NaN there" % g)
+            if want_moments:
+                moments[g] = (out[1].cpu().numpy(), out[2].cpu().numpy())
+        return (dF, moments) if want_moments else dF
+
+    def _dev(self):
+        return self.device if self.devices is None else self.devices[0]
+
     # ------------------------------------------------------------------ log densities (base.py:200-243)
     def observationLikelihood(self, sigma=None, prior_ub=None, prior_lb=None):
         """log p(y | functions, sigma) + log U(prior_lb, prior_ub)(sd), sd = sqrt(10**sigma) (base.py:200-214); chain 0"""
@@ -315,7 +335,7 @@ class Base(SamplerContainer):
             val = eng.prior_loglik(p, "sigma", float(sigma))[0]
         st = eng.status(raise_on_error=False)
         if (st < 0).any():
-            logging.getLogger(__name__).error("prior likelihood LinAlgError (%d)" % p)
+            LOG.error("prior likelihood LinAlgError (%d)" % p)
         return float(val)
 
     @staticmethod
@@ -324,37 +344,54 @@ class Base(SamplerContainer):
             raise NotImplementedError("the device log-densities are built with the reference's U(-2, 2) hyper-priors "
                                       "(base.py:57,78,83)")
 
-    def samplePrior(self):
-        """draw functions from their GP priors at the current hyper-parameters and data from the model
-        (base.py:245-259).  K and its factor come from the device; normals from numpy's global stream."""
-        samples = np.zeros((self.f, self.n))
-        for i in range(self.f):
-            K = self.kernels[self.functionPrior(i)].K(self.x)
-            L = _engine.jitchol(K)      # K alone is numerically singular: the jitter ladder (linalg.py:41-54) applies
-            z = torch.as_tensor(np.random.standard_normal(self.n)).to(L.device)
-            samples[i, :] = (L @ z).cpu().numpy()
-        y = np.dot(self.design_matrix, samples) + np.random.normal(
-            0, np.sqrt(pow(10, self.parameter_cache['y_sigma'])), size=(self.m, self.n))
-        return y.T, samples.T
+    def samplePrior(self, size=None, seed=None):
+        """draw functions from their GP priors at the current hyper-parameters and data from the model (base.py:245-259),
+        on the device: one batched launch factors the f kernel matrices (jitchol, i.e. with the jitter ladder: K alone
+        is numerically singular) and draws L z, a second one forms y = X f + noise.  Returns (y (n, m), functions (n, f))
+        like the reference; with size=B, B independent data sets at once: (B, n, m), (B, n, f).
+        Normals are Philox4x32-10 keyed by `seed` (default: drawn from numpy's global stream, which the reference uses)."""
+        B = 1 if size is None else int(size)
+        seed = int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else int(seed)
+        grp = np.array([self.functionPrior(i) for i in range(self.f)])
+        cur = self.parameter_cache
+        ls = np.array([float(cur['prior%d_sigma' % g]) for g in grp])
+        ll = np.array([float(cur['prior%d_lengthscale' % g]) for g in grp])
+        F = _engine.gp_sample(self.x, ls, ll, nsamp=B, seed=seed, stream_id=1, device=self._dev())          # (f, B, n)
+        F = F.permute(1, 0, 2).contiguous()                                                              # (B, f, n)
+        sd = np.sqrt(pow(10.0, float(cur['y_sigma'])))
+        y = _engine.compose_y(F, self.design_matrix, sd, seed=seed, stream_id=2, device=self._dev())      # (B, n, m)
+        y, F = y.cpu().numpy(), F.permute(0, 2, 1).cpu().numpy()
+        return (y[0], F[0]) if size is None else (y, F)
 
     # ------------------------------------------------------------------ the sweep (container.py:29-92)
+    def _transform_plan(self):
+        return []
+
     def _transform_block(self, F):
         """values of the Transform samplers for stored states F (S, f, n) -> (S, #transform labels)"""
         return np.zeros((F.shape[0], 0))
 
+    def _device_transforms(self, F):
+        """Transform values for states F (R, f, n) on the device (gpf_fanova_transform) -> (R, #transform labels)"""
+        plan = self._transform_plan()
+        if not plan or F.shape[0] == 0:
+            return np.zeros((F.shape[0], 0))
+        return _engine.fanova_transform(F, plan, device=self._dev()).reshape(F.shape[0], -1).cpu().numpy()
+
     def _core_order(self, n_sweeps):
         """random=True: shuffle the reference's full sampler list per sweep (container.py:34-35) and keep the relative
-        order of the non-Transform samplers"""
-        order = np.empty((n_sweeps, self._n_core_samplers), dtype=np.int32)
+        order of the samplers the device runs (slices and functions)"""
+        dev_ids = {i: k for k, i in enumerate(i for i, s in enumerate(self.samplers[:self._n_core_samplers])
+                                              if s.type != 'Function' or not getattr(s, 'derivative', False))}
+        order = np.empty((n_sweeps, len(dev_ids)), dtype=np.int32)
         ids = list(range(len(self.samplers)))
         for s in range(n_sweeps):
             pyrandom.shuffle(ids)
-            order[s] = [i for i in ids if i < self._n_core_samplers]
+            order[s] = [dev_ids[i] for i in ids if i in dev_ids]
         return order
 
     def sample(self, n=1, thin=0, verbose=False, random=False):
         """n sweeps of every chain on the device; every `thin`-th state is stored (thin=0: every sweep)."""
-        logger = logging.getLogger(__name__)
         eng = self._push_state()
         start_time = time.time()
         step = 1 if thin == 0 else int(thin)
@@ -363,9 +400,10 @@ class Base(SamplerContainer):
         progress = None
         if verbose:
             def progress(done):
-                logger.info("%d/%d iterations (%.2lf%s) finished in %.2lf minutes" % (
+                LOG.info("%d/%d iterations (%.2lf%s) finished in %.2lf minutes" % (
                     done, n, 100. * done / n, '%', (time.time() - start_time) / 60))
         t_sw = time.time()
+        sweep0 = eng.sweeps_done
         blocks = eng.sweep_host(n, thin=step, order=order, on_chunk=progress,
                                 max_chunk_sweeps=max(step, n // 10) if verbose else None)
         t_sw1 = time.time()
@@ -375,46 +413,66 @@ class Base(SamplerContainer):
             err = e
         self._pull_state()
         if blocks.shape[0]:
-            self._store_blocks(blocks)
+            self._store_blocks(blocks, sweep0)
         if os.environ.get("GPFANOVA_B200_TIMING"):
             sys.stderr.write("sample: push %.3f s  sweep_host %.3f s  pull+store %.3f s\n" % (
                 t_sw - start_time, t_sw1 - t_sw, time.time() - t_sw1))
         if verbose:
-            logger.info("%d samples finished in %.2lf minutes" % (n, (time.time() - start_time) / 60))
+            LOG.info("%d samples finished in %.2lf minutes" % (n, (time.time() - start_time) / 60))
         if err is not None:
             raise err
 
-    def _store_blocks(self, raw):
-        """raw: (S, chains, H + f n) device history -> parameter_history rows (chain 0) in the reference's column order"""
+    def _store_blocks(self, raw, sweep0=0):
+        """raw: (S, chains, H + f n) device history -> parameter_history rows (chain 0) in the reference's column order;
+        with derivatives=True the derivative functions of the stored states are drawn here (they feed nothing back)"""
+        dblock = None
+        if self.derivatives:
+            keep = slice(None) if (self.store_chains and self.chains > 1) else slice(0, 1)
+            sub = raw[:, keep, :]
+            S, Cn = sub.shape[:2]
+            flat = sub.reshape(S * Cn, -1)
+            dblock = self._device_derivatives(flat[:, :self.H], flat[:, self.H:].reshape(S * Cn, self.f, self.n),
+                                              stream_id=0x40000000 + sweep0).reshape(S, Cn, self.f * self.n)
         if self.store_chains and self.chains > 1:
             self._chain_blocks.append(raw)
-        frame = self._frame_from_raw(raw[:, 0, :])
+            if dblock is not None:
+                self._deriv_blocks.append(dblock)
+        frame = self._frame_from_raw(raw[:, 0, :], None if dblock is None else dblock[:, 0, :])
         if self.parameter_history.shape[0] == 0:
             self.parameter_history = frame
         else:
             self.parameter_history = pd.concat([self.parameter_history, frame], ignore_index=True)
         self.parameter_history.index = range(self.parameter_history.shape[0])
+        if dblock is not None:
+            vals = self.parameter_cache.to_numpy(dtype=float, copy=True)
+            vals[self._pos_D] = dblock[-1, 0]
+            self.parameter_cache.iloc[:] = vals
 
-    def _frame_from_raw(self, raw):
-        """(S, H + f n) -> DataFrame with the reference's columns (sampler order; labels base.py:114-138)"""
+    def _rows_from_raw(self, raw, dvals=None):
+        """(S, H + f n) -> (S, #labels) array in the reference's column order (sampler order; labels base.py:114-138);
+        the Transform columns come from the device operator"""
         S = raw.shape[0]
-        hyper = raw[:, :self.H]
         F = raw[:, self.H:].reshape(S, self.f, self.n)
-        cols = self.parameter_cache.index
-        out = np.empty((S, len(cols)))
-        out[:, self._pos_h] = hyper
-        out[:, self._pos_F] = F.reshape(S, self.f * self.n)
+        out = np.zeros((S, len(self.parameter_cache.index)))
+        out[:, self._pos_h] = raw[:, :self.H]
+        out[:, self._pos_F] = raw[:, self.H:]
         if len(self._pos_T):
-            out[:, self._pos_T] = self._transform_block(F)
-        return pd.DataFrame(out, columns=cols)
+            out[:, self._pos_T] = self._device_transforms(F)
+        if dvals is not None and len(self._pos_D):
+            out[:, self._pos_D] = dvals
+        return out
+
+    def _frame_from_raw(self, raw, dvals=None):
+        return pd.DataFrame(self._rows_from_raw(raw, dvals), columns=self.parameter_cache.index)
 
     def store(self):
         """append the current parameter_cache (chain 0) to parameter_history (container.py:90-92)"""
         SamplerContainer.store(self)
 
-    def chain_history(self, chain=None):
-        """stored states of every chain: array (S, chains, H + f n) laid out [hyper | F (f, n)], or a DataFrame with
-        the reference's columns for one chain"""
+    def chain_history(self, chain=None, as_frame=True):
+        """stored states of every chain: array (S, chains, H + f n) laid out [hyper | F (f, n)]; or, for one chain, its
+        history in the reference's schema (all columns of parameter_history, Transforms included) as a DataFrame
+        (as_frame=False: a plain (S, #labels) array)"""
         if not self._chain_blocks:
             raw = np.zeros((0, self.chains, self.H + self.f * self.n))
         else:
@@ -423,8 +481,38 @@ class Base(SamplerContainer):
         if chain is None:
             return raw
         if self.chains == 1:
-            return self.parameter_history
-        return self._frame_from_raw(raw[:, chain, :])
+            return self.parameter_history if as_frame else self.parameter_history.to_numpy(dtype=float)
+        dv = None
+        if self._deriv_blocks:
+            dv = np.concatenate(self._deriv_blocks, axis=0)
+            self._deriv_blocks = [dv]
+            dv = dv[:, chain, :]
+        rows = self._rows_from_raw(raw[:, chain, :], dv)
+        return pd.DataFrame(rows, columns=self.parameter_cache.index) if as_frame else rows
+
+    def save(self, f, chain=None):
+        """CSV of parameter_history (container.py:94-95); chain=c writes that chain's history in the same schema,
+        chain='all' one file per chain (f must contain a %d for the chain number)"""
+        if chain is None:
+            return SamplerContainer.save(self, f)
+        if chain == 'all':
+            for c in range(self.chains):
+                self.save(f % c, chain=c)
+            return
+        rows = self.chain_history(chain, as_frame=False)
+        with open(f, "w") as fh:
+            fh.write(",".join('"%s"' % c.replace('"', '""') if ("," in c or '"' in c) else c for c in self.parameter_cache.index) + "\n")
+            np.savetxt(fh, rows, delimiter=",", fmt="%.17g")
+
+    def chain_diagnostics(self, columns='hyper', split=True):
+        """split-R^ over the chains, pooled posterior mean and variance of the stored states (device operator
+        gpf_chain_diagnostics).  columns: 'hyper' (the 1 + 2P hyper-parameters) or 'all'.  Returns a DataFrame indexed by
+        the column labels of the raw state ([hyper | functions])."""
+        raw = self.chain_history()
+        ncol = self.H if columns == 'hyper' else raw.shape[2]
+        r, mu, var = _engine.chain_diagnostics(raw, 0, ncol, split=split, device=self._dev())
+        labels = (self._hyper_names + self._flabels)[:ncol]
+        return pd.DataFrame({"rhat": r.cpu().numpy(), "mean": mu.cpu().numpy(), "var": var.cpu().numpy()}, index=labels)
 
     def counters(self):
         return self.engine().counters()

@@ -13,6 +13,7 @@
 #include "../../include/gpfanova_b200.h"
 #include "gpf_kernels.cuh"
 #include "gpf_cond.cuh"
+#include "gpf_ops.cuh"
 #include "gpf_schur.cuh"
 
 using namespace gpf;
@@ -340,6 +341,248 @@ int gpf_jitchol(const double* d_A, int n, int batch, int maxtries, double* d_L, 
 
 int gpf_kinv(const double* d_A, int n, int batch, double offset, double* d_Ainv, int* d_status, void* stream) {
   return dense_factor_common(d_A, n, batch, 5, offset, d_Ainv, nullptr, d_status, stream, true);
+}
+
+int gpf_rbf_dist(const double* d_x, int n, int p, const double* d_log10_ls, int batch, double* d_out, void* stream) {
+  if (n < 1 || p < 1 || batch < 0 || !d_x || !d_out || !d_log10_ls) { g_err = "gpf_rbf_dist: bad argument"; return GPF_ERR_ARG; }
+  if (batch == 0) return GPF_OK;
+  const size_t smem = ((size_t)n * p + n) * sizeof(double);
+  if (smem > smem_limit()) { g_err = "gpf_rbf_dist: n*p too large for shared memory"; return GPF_ERR_UNSUPPORTED; }
+  CKS(allow_smem(k_rbf_aux, smem));
+  k_rbf_aux<<<batch, NTHR, smem, (cudaStream_t)stream>>>(d_x, n, p, nullptr, d_log10_ls, d_out, 1);
+  CKS(cudaGetLastError());
+  return GPF_OK;
+}
+
+int gpf_rbf_dK(const double* d_x, int n, int p, const double* d_log10_sigma, const double* d_log10_ls, int cross, int batch,
+               double* d_out, void* stream) {
+  if (n < 1 || p < 1 || batch < 0 || !d_x || !d_out || !d_log10_ls || !d_log10_sigma) { g_err = "gpf_rbf_dK: bad argument"; return GPF_ERR_ARG; }
+  if (batch == 0) return GPF_OK;
+  const size_t smem = ((size_t)n * p + n) * sizeof(double);
+  if (smem > smem_limit()) { g_err = "gpf_rbf_dK: n*p too large for shared memory"; return GPF_ERR_UNSUPPORTED; }
+  CKS(allow_smem(k_rbf_aux, smem));
+  k_rbf_aux<<<batch, NTHR, smem, (cudaStream_t)stream>>>(d_x, n, p, d_log10_sigma, d_log10_ls, d_out, cross ? 3 : 2);
+  CKS(cudaGetLastError());
+  return GPF_OK;
+}
+
+static int gp_common(bool sample, const double* d_x, int n, int p, const double* d_ls, const double* d_ll, int batch, const double* d_F,
+                     int nf, double add_rel, double add_abs, int maxtries, unsigned long long seed, unsigned stream_id, double* d_out,
+                     double* d_logdet, int* d_status, void* stream) {
+  if (n < 1 || n > GPF_MAX_N || p < 1 || batch < 0 || nf < 1 || !d_x || !d_ls || !d_ll || !d_out || !d_status || (!sample && !d_F)) {
+    g_err = "gpf_gp_*: bad argument (1 <= n <= 512, nf >= 1, non-null arrays)";
+    return GPF_ERR_ARG;
+  }
+  if (batch == 0) return GPF_OK;
+  const int NT = (n + TB - 1) / TB, NE = sample ? 0 : (nf + TB - 1) / TB;
+  size_t smem = (engine_smem_doubles(NT, NE) + (size_t)n * p + n) * sizeof(double);
+  if (sample) smem += (size_t)16 * (NT * TB + 4) * sizeof(double);
+  if (smem > smem_limit()) { g_err = "gpf_gp_*: n / number of functions exceed the shared-memory budget of the tile engine"; return GPF_ERR_UNSUPPORTED; }
+  int dev = 0, sms = 148;
+  CKS(cudaGetDevice(&dev));
+  CKS(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = std::min(batch, sms);
+  GpArgs a{};
+  a.x = d_x; a.n = n; a.p = p; a.NT = NT; a.batch = batch; a.nf = nf; a.maxtries = maxtries;
+  a.lsig = d_ls; a.lls = d_ll; a.F = d_F; a.add_rel = add_rel; a.add_abs = add_abs; a.out = d_out; a.logdet = d_logdet;
+  a.status = d_status;
+  a.ws_stride = ((size_t)plt_tiles(NT) + (size_t)NE * NT) * TILE;
+  a.k0 = (unsigned)seed; a.k1 = (unsigned)(seed >> 32); a.stream_id = stream_id;
+  double* ws = nullptr;
+  CKS(cudaMalloc(&ws, (size_t)grid * a.ws_stride * sizeof(double)));
+  a.ws = ws;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = sample ? allow_smem(k_gp_sample, smem) : allow_smem(k_gp_loglik, smem);
+  if (e == cudaSuccess) {
+    if (sample) k_gp_sample<<<grid, NTHR, smem, st>>>(a);
+    else k_gp_loglik<<<grid, NTHR, smem, st>>>(a);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(ws);
+  if (e != cudaSuccess) { g_err = cudaGetErrorString(e); return GPF_ERR_CUDA; }
+  return GPF_OK;
+}
+
+int gpf_gp_loglik(const double* d_x, int n, int p, const double* d_log10_sigma, const double* d_log10_ls, int batch, const double* d_F,
+                  int nf, double add_rel, double add_abs, int maxtries, double* d_ll, double* d_logdet, int* d_status, void* stream) {
+  return gp_common(false, d_x, n, p, d_log10_sigma, d_log10_ls, batch, d_F, nf, add_rel, add_abs, maxtries, 0ull, 0u, d_ll, d_logdet,
+                   d_status, stream);
+}
+
+int gpf_gp_sample(const double* d_x, int n, int p, const double* d_log10_sigma, const double* d_log10_ls, int batch, int nsamp,
+                  const double* d_z_inject, unsigned long long seed, unsigned stream_id, double add_rel, double add_abs, int maxtries,
+                  double* d_out, int* d_status, void* stream) {
+  return gp_common(true, d_x, n, p, d_log10_sigma, d_log10_ls, batch, d_z_inject, nsamp, add_rel, add_abs, maxtries, seed, stream_id,
+                   d_out, nullptr, d_status, stream);
+}
+
+int gpf_function_derivative(const double* d_x, int n, int p, const double* d_log10_sigma, const double* d_log10_ls, int batch,
+                            const double* d_F, int nf, const double* d_z_inject, unsigned long long seed, unsigned stream_id,
+                            double offset, int maxtries, double* d_dF, double* d_mu, double* d_cov, int* d_status, void* stream) {
+  if (n < 1 || n > GPF_MAX_N || p < 1 || batch < 0 || nf < 1 || nf > 32 || !d_x || !d_log10_sigma || !d_log10_ls || !d_F || !d_dF || !d_status) {
+    g_err = "gpf_function_derivative: bad argument (1 <= n <= 512, 1 <= nf <= 32 functions per call)";
+    return GPF_ERR_ARG;
+  }
+  if (batch == 0) return GPF_OK;
+  const int NT = (n + TB - 1) / TB, NE = (nf + n + TB - 1) / TB;
+  const size_t smem = (engine_smem_doubles(NT, NE) + (size_t)n * p + n) * sizeof(double);
+  if (smem > smem_limit()) { g_err = "gpf_function_derivative: n too large for the shared-memory budget (n + nf rows ride along)"; return GPF_ERR_UNSUPPORTED; }
+  int dev = 0, sms = 148;
+  CKS(cudaGetDevice(&dev));
+  CKS(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = std::min(batch, sms);
+  DerivArgs a{};
+  a.x = d_x; a.n = n; a.p = p; a.NT = NT; a.NE = NE; a.batch = batch; a.nf = nf; a.maxtries = maxtries;
+  a.lsig = d_log10_sigma; a.lls = d_log10_ls; a.F = d_F; a.z = d_z_inject; a.offset = offset;
+  a.dF = d_dF; a.mu = d_mu; a.cov = d_cov; a.status = d_status;
+  a.ws_stride = deriv_ws_doubles(NT, NE, nf, n);
+  a.k0 = (unsigned)seed; a.k1 = (unsigned)(seed >> 32); a.stream_id = stream_id;
+  double* ws = nullptr;
+  CKS(cudaMalloc(&ws, (size_t)grid * a.ws_stride * sizeof(double)));
+  a.ws = ws;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = allow_smem(k_function_derivative, smem);
+  if (e == cudaSuccess) {
+    k_function_derivative<<<grid, NTHR, smem, st>>>(a);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(ws);
+  if (e != cudaSuccess) { g_err = cudaGetErrorString(e); return GPF_ERR_CUDA; }
+  return GPF_OK;
+}
+
+int gpf_compose_y(const double* d_F, const double* d_X, const double* d_sd, int batch, int n, int m, int f, unsigned long long seed,
+                  unsigned stream_id, double* d_y, void* stream) {
+  if (!d_F || !d_X || !d_sd || !d_y || batch < 0 || n < 1 || m < 1 || f < 1) { g_err = "gpf_compose_y: bad argument"; return GPF_ERR_ARG; }
+  if (batch == 0) return GPF_OK;
+  const size_t total = (size_t)batch * n * m;
+  const int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 8);
+  k_compose_y<<<grid, 256, 0, (cudaStream_t)stream>>>(d_F, d_X, d_sd, batch, n, m, f, d_y, (unsigned)seed, (unsigned)(seed >> 32), stream_id);
+  CKS(cudaGetLastError());
+  return GPF_OK;
+}
+
+int gpf_fanova_transform(const double* d_F, long long rows, int f, int n, int nblk, const int* h_in0, const int* h_nin, const int* h_nout,
+                         const int* h_fpv, const double* h_coef, double* d_out, void* stream) {
+  if (!d_F || !d_out || rows < 0 || f < 1 || n < 1 || nblk < 0 || (nblk && (!h_in0 || !h_nin || !h_nout || !h_fpv || !h_coef))) {
+    g_err = "gpf_fanova_transform: bad argument";
+    return GPF_ERR_ARG;
+  }
+  if (rows == 0 || nblk == 0) return GPF_OK;
+  std::vector<int> out0(nblk), coff(nblk), cblk, cj0;
+  int Q = 0;
+  size_t nc = 0;
+  for (int b = 0; b < nblk; ++b) {
+    if (h_in0[b] < 0 || h_nin[b] < 1 || h_in0[b] + h_nin[b] > f || h_nout[b] < 1) { g_err = "gpf_fanova_transform: block out of range"; return GPF_ERR_ARG; }
+    out0[b] = Q;
+    coff[b] = (int)nc;
+    for (int j0 = 0; j0 < h_nout[b]; j0 += 8) { cblk.push_back(b); cj0.push_back(j0); }
+    Q += h_nout[b] + (h_fpv[b] ? 1 : 0);
+    nc += (size_t)h_nout[b] * h_nin[b];
+  }
+  // description -> device (one allocation)
+  const size_t ni = (size_t)6 * nblk + 2 * cblk.size();
+  std::vector<int> hi(ni);
+  int* q = hi.data();
+  std::copy(h_in0, h_in0 + nblk, q);
+  std::copy(h_nin, h_nin + nblk, q + nblk);
+  std::copy(out0.begin(), out0.end(), q + 2 * nblk);
+  std::copy(h_nout, h_nout + nblk, q + 3 * nblk);
+  std::copy(coff.begin(), coff.end(), q + 4 * nblk);
+  std::copy(h_fpv, h_fpv + nblk, q + 5 * nblk);
+  std::copy(cblk.begin(), cblk.end(), q + 6 * nblk);
+  std::copy(cj0.begin(), cj0.end(), q + 6 * nblk + cblk.size());
+  int* di = nullptr;
+  double* dc = nullptr;
+  CKS(cudaMalloc(&di, ni * sizeof(int)));
+  cudaError_t e = cudaMalloc(&dc, nc * sizeof(double));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(di, hi.data(), ni * sizeof(int), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dc, h_coef, nc * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    TransformDesc d{};
+    d.nchunk = (int)cblk.size();
+    d.in0 = di; d.nin = di + nblk; d.out0 = di + 2 * nblk; d.nout = di + 3 * nblk; d.coef_off = di + 4 * nblk; d.fpv = di + 5 * nblk;
+    d.chunk_blk = di + 6 * nblk; d.chunk_j0 = di + 6 * nblk + cblk.size();
+    d.coef = dc; d.f = f; d.n = n; d.Q = Q;
+    for (long long r0 = 0; r0 < rows && e == cudaSuccess; r0 += 32768) {          // grid.x limit is generous; keep launches bounded
+      const int nr = (int)std::min<long long>(32768, rows - r0);
+      k_transform<<<dim3(nr, d.nchunk), 128, 0, st>>>(d_F + (size_t)r0 * f * n, d_out + (size_t)r0 * Q * n, d);
+      k_transform_fpv<<<nr, 128, 0, st>>>(d_out + (size_t)r0 * Q * n, d, nblk);
+      e = cudaGetLastError();
+    }
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(di);
+  if (dc) cudaFree(dc);
+  if (e != cudaSuccess) { g_err = cudaGetErrorString(e); return GPF_ERR_CUDA; }
+  return GPF_OK;
+}
+
+int gpf_chain_diagnostics(const double* d_hist, int S, int C, long long cols, int col0, int ncol, int split, double* d_rhat,
+                          double* d_mean, double* d_var, void* stream) {
+  if (!d_hist || !d_rhat || !d_mean || !d_var || S < 2 || C < 1 || col0 < 0 || ncol < 1 || col0 + ncol > cols) {
+    g_err = "gpf_chain_diagnostics: bad argument (S >= 2 stored rows, columns inside the row)";
+    return GPF_ERR_ARG;
+  }
+  const int halves = (split && S >= 4) ? 2 : 1, len = S / halves, nseq = halves * C;
+  double* tmp = nullptr;
+  CKS(cudaMalloc(&tmp, (size_t)2 * nseq * ncol * sizeof(double)));
+  double* mean = tmp;
+  double* var = tmp + (size_t)nseq * ncol;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaSuccess;
+  for (int h = 0; h < halves && e == cudaSuccess; ++h) {
+    // split chains: first and last `len` rows (the middle row of an odd S is dropped)
+    const int s0 = (h == 0) ? 0 : S - len;
+    for (int c0 = 0; c0 < C && e == cudaSuccess; c0 += 32768) {
+      const int nc = std::min(32768, C - c0);
+      k_seq_moments<<<dim3((ncol + 127) / 128, nc), 128, 0, st>>>(d_hist + (size_t)c0 * cols, S, C, (size_t)cols, col0, ncol, s0, s0 + len,
+                                                               mean + ((size_t)h * C + c0) * ncol, var + ((size_t)h * C + c0) * ncol);
+      e = cudaGetLastError();
+    }
+  }
+  if (e == cudaSuccess) {
+    k_rhat<<<(ncol + 127) / 128, 128, 0, st>>>(mean, var, nseq, ncol, len, d_rhat, d_mean, d_var);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(tmp);
+  if (e != cudaSuccess) { g_err = cudaGetErrorString(e); return GPF_ERR_CUDA; }
+  return GPF_OK;
+}
+
+int gpf_row_sort(double* d_v, int rows, int S, void* stream) {
+  if (!d_v || rows < 0 || S < 1 || S > 8192) { g_err = "gpf_row_sort: 1 <= S <= 8192"; return GPF_ERR_ARG; }
+  if (rows == 0) return GPF_OK;
+  int P2 = 1;
+  while (P2 < S) P2 <<= 1;
+  CKS(allow_smem(k_row_sort, (size_t)P2 * sizeof(double)));
+  k_row_sort<<<rows, 256, (size_t)P2 * sizeof(double), (cudaStream_t)stream>>>(d_v, S, P2);
+  CKS(cudaGetLastError());
+  return GPF_OK;
+}
+
+int gpf_function_interval(const double* d_samples, int batch, int S, int n, double alpha, double start, double tol, int maxiter,
+                          double* d_mean, double* d_std, double* d_eps, int* d_iters, void* stream) {
+  if (!d_samples || !d_mean || !d_std || !d_eps || !d_iters || batch < 0 || S < 1 || n < 1 || alpha < 0 || alpha > 1) {
+    g_err = "gpf_function_interval: bad argument (must provide alpha between 0 and 1)";
+    return GPF_ERR_ARG;
+  }
+  if (batch == 0) return GPF_OK;
+  // interval.py:66-67: alpha moved to the closest of k/S, k = 0..S-1 (first one on ties)
+  double best = 1e300, aeff = 0.0;
+  for (int k = 0; k < S; ++k) {
+    const double v = (double)k / (double)S, dlt = std::fabs(v - alpha);
+    if (dlt < best) { best = dlt; aeff = v; }
+  }
+  const size_t smem = (size_t)2 * n * sizeof(double);
+  CKS(allow_smem(k_band, smem));
+  k_band<<<batch, 256, smem, (cudaStream_t)stream>>>(d_samples, S, n, aeff, alpha, start, tol, maxiter, d_mean, d_std, d_eps, d_iters);
+  CKS(cudaGetLastError());
+  return GPF_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -97,6 +97,209 @@ def kinv(A, offset=OFFSET, device=None):
     return out[0] if single else out
 
 
+def _dev_f64(a, dev):
+    if isinstance(a, torch.Tensor):
+        return a.to(device=dev, dtype=torch.float64).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(np.asarray(a, dtype=np.float64))).to(dev)
+
+
+def _x_and_params(x, device, *params):
+    dev = _require_cuda(device)
+    x = _dev_f64(x, dev)
+    if x.dim() == 1:
+        x = x[:, None]
+    ps = [_dev_f64(np.atleast_1d(np.asarray(p_, dtype=np.float64)), dev) for p_ in params]
+    for q in ps[1:]:
+        assert q.shape == ps[0].shape
+    return dev, x, ps
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def rbf_dist(x, log10_lengthscale, device=None):
+    """RBF.dist (kernel/rbf.pyx:8-14) for a batch of lengthscales (log10): (batch, n, n) CUDA tensor of scaled distances"""
+    dev, x, (l,) = _x_and_params(x, device, log10_lengthscale)
+    n, p = x.shape
+    out = torch.empty((l.numel(), n, n), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _capi.check(_capi.lib().gpf_rbf_dist(_ptr(x), n, p, _ptr(l), l.numel(), _ptr(out), _stream(dev)))
+    return out
+
+
+def rbf_dK(x, log10_sigma, log10_lengthscale, cross=False, device=None):
+    """RBF._dK (kernel/rbf.pyx:21-38) for a batch of (sigma, lengthscale) pairs (log10): (batch, n, n) CUDA tensor"""
+    dev, x, (s, l) = _x_and_params(x, device, log10_sigma, log10_lengthscale)
+    n, p = x.shape
+    out = torch.empty((s.numel(), n, n), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _capi.check(_capi.lib().gpf_rbf_dK(_ptr(x), n, p, _ptr(s), _ptr(l), int(bool(cross)), s.numel(), _ptr(out), _stream(dev)))
+    return out
+
+
+def gp_loglik(x, log10_sigma, log10_lengthscale, F, add_rel=0.0, add_abs=0.0, maxtries=5, device=None, return_info=False):
+    """sum_f log N(F[b, f]; 0, K_b + (add_rel mean(K_b) + add_abs) I) for a batch of (sigma, lengthscale) pairs.
+    F: (batch, nf, n) or (nf, n) shared by the whole batch.  Returns a (batch,) CUDA tensor; raises LinAlgError like
+    linalg.jitchol if a covariance is not positive definite even with jitter."""
+    dev, x, (s, l) = _x_and_params(x, device, log10_sigma, log10_lengthscale)
+    n, p = x.shape
+    b = s.numel()
+    F = _dev_f64(F, dev)
+    if F.dim() == 2:
+        F = F[None].expand(b, -1, -1).contiguous()
+    assert F.shape[0] == b and F.shape[2] == n
+    ll = torch.empty(b, dtype=torch.float64, device=dev)
+    ld = torch.empty(b, dtype=torch.float64, device=dev)
+    status = torch.zeros(b, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _capi.check(_capi.lib().gpf_gp_loglik(_ptr(x), n, p, _ptr(s), _ptr(l), b, _ptr(F), F.shape[1], float(add_rel), float(add_abs),
+                                               int(maxtries), _ptr(ll), _ptr(ld), _ptr(status), _stream(dev)))
+    tries = _status_raise(status)
+    return (ll, ld, tries) if return_info else ll
+
+
+def gp_sample(x, log10_sigma, log10_lengthscale, nsamp=1, z=None, seed=0, stream_id=0, add_rel=0.0, add_abs=0.0, maxtries=5,
+              device=None):
+    """nsamp draws from N(0, K_b + add I) for every (sigma, lengthscale) pair of the batch (base.py:249-254):
+    L z with L = jitchol(K_b + add I).  z: (batch, nsamp, n) injected normals or None (Philox keyed by seed / stream_id).
+    Returns a (batch, nsamp, n) CUDA tensor."""
+    dev, x, (s, l) = _x_and_params(x, device, log10_sigma, log10_lengthscale)
+    n, p = x.shape
+    b = s.numel()
+    zt = None
+    if z is not None:
+        zt = _dev_f64(z, dev)
+        assert tuple(zt.shape) == (b, nsamp, n)
+    out = torch.empty((b, int(nsamp), n), dtype=torch.float64, device=dev)
+    status = torch.zeros(b, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _capi.check(_capi.lib().gpf_gp_sample(_ptr(x), n, p, _ptr(s), _ptr(l), b, int(nsamp), _ptr(zt), int(seed) & (2 ** 64 - 1),
+                                               int(stream_id) & 0xffffffff, float(add_rel), float(add_abs), int(maxtries), _ptr(out),
+                                               _ptr(status), _stream(dev)))
+    _status_raise(status)
+    return out
+
+
+def function_derivative(x, log10_sigma, log10_lengthscale, F, z=None, seed=0, stream_id=0, maxtries=5, device=None,
+                        want_moments=False, raise_on_error=True):
+    """FunctionDerivative (sample/function.py:43-66) for a batch of kernels: F (batch, nf, n) function values ->
+    draws of their derivatives (batch, nf, n); want_moments: also (mu (batch, nf, n), cov (batch, n, n)).
+    Where cov is not positive definite even with jitter (the reference's derivative kernels only form a covariance at
+    lengthscale 1, rbf.pyx:34-37) the draws are NaN and, unless raise_on_error=False, LinAlgError is raised; the last
+    element of the returned tuple is the per-item status."""
+    dev, x, (s, l) = _x_and_params(x, device, log10_sigma, log10_lengthscale)
+    n, p = x.shape
+    b = s.numel()
+    F = _dev_f64(F, dev)
+    assert F.dim() == 3 and F.shape[0] == b and F.shape[2] == n
+    nf = F.shape[1]
+    zt = None if z is None else _dev_f64(z, dev)
+    dF = torch.empty_like(F)
+    mu = torch.empty_like(F) if want_moments else None
+    cov = torch.empty((b, n, n), dtype=torch.float64, device=dev) if want_moments else None
+    for f0 in range(0, nf, 32):                       # at most 32 functions ride along one factorisation
+        f1 = min(nf, f0 + 32)
+        Fc = F[:, f0:f1].contiguous()
+        dc = torch.empty_like(Fc)
+        mc = torch.empty_like(Fc) if want_moments else None
+        zc = None if zt is None else zt[:, f0:f1].contiguous()
+        status = torch.zeros(b, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _capi.check(_capi.lib().gpf_function_derivative(
+                _ptr(x), n, p, _ptr(s), _ptr(l), b, _ptr(Fc), f1 - f0, _ptr(zc), int(seed) & (2 ** 64 - 1),
+                (int(stream_id) + f0) & 0xffffffff, OFFSET, int(maxtries), _ptr(dc), _ptr(mc), _ptr(cov if f0 == 0 else None),
+                _ptr(status), _stream(dev)))
+        if raise_on_error:
+            _status_raise(status)
+        dF[:, f0:f1] = dc
+        if want_moments:
+            mu[:, f0:f1] = mc
+    return (dF, mu, cov, status) if want_moments else (dF, status)
+
+
+def compose_y(F, X, sd, seed=0, stream_id=0, device=None):
+    """y[b] (n, m) = F[b]^T X^T + sd[b] * N(0, 1) noise (base.py:256-257) for a batch of function sets F (batch, f, n)"""
+    dev = _require_cuda(device)
+    F = _dev_f64(F, dev)
+    X = _dev_f64(X, dev)
+    b, f, n = F.shape
+    m = X.shape[0]
+    assert X.shape[1] == f
+    sdt = _dev_f64(np.broadcast_to(np.asarray(sd, dtype=np.float64), (b,)), dev)
+    y = torch.empty((b, n, m), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _capi.check(_capi.lib().gpf_compose_y(_ptr(F), _ptr(X), _ptr(sdt), b, n, m, f, int(seed) & (2 ** 64 - 1),
+                                               int(stream_id) & 0xffffffff, _ptr(y), _stream(dev)))
+    return y
+
+
+def fanova_transform(F, blocks, device=None):
+    """FANOVA's Transform samplers (fanova.py:58-81) on the device for many stored states at once.
+    F: (rows, f, n).  blocks: list of (in0, coef (nout, nin), fpv) -- the block's contrast functions in0 .. in0+nin are
+    mapped to nout effect rows, followed by the finite-population-variance row when fpv.  Returns (rows, Q, n) CUDA tensor."""
+    dev = _require_cuda(device)
+    F = _dev_f64(F, dev)
+    rows, f, n = F.shape
+    in0 = np.array([b[0] for b in blocks], dtype=np.int32)
+    nin = np.array([np.asarray(b[1]).shape[1] for b in blocks], dtype=np.int32)
+    nout = np.array([np.asarray(b[1]).shape[0] for b in blocks], dtype=np.int32)
+    fpv = np.array([1 if b[2] else 0 for b in blocks], dtype=np.int32)
+    coef = np.ascontiguousarray(np.concatenate([np.asarray(b[1], dtype=np.float64).ravel() for b in blocks])) if blocks else np.zeros(1)
+    Q = int((nout + fpv).sum())
+    out = torch.empty((rows, Q, n), dtype=torch.float64, device=dev)
+    if rows and Q:
+        with torch.cuda.device(dev):
+            _capi.check(_capi.lib().gpf_fanova_transform(_ptr(F), rows, f, n, len(blocks), in0.ctypes.data_as(C.c_void_p),
+                                                          nin.ctypes.data_as(C.c_void_p), nout.ctypes.data_as(C.c_void_p),
+                                                          fpv.ctypes.data_as(C.c_void_p), coef.ctypes.data_as(C.c_void_p), _ptr(out),
+                                                          _stream(dev)))
+    return out
+
+
+def chain_diagnostics(hist, col0=0, ncol=None, split=True, device=None):
+    """split-R^ over chains, pooled mean and posterior-variance estimate of the columns col0 .. col0+ncol of a stored
+    history hist (S, C, cols) (the layout ChainEngine.sweep writes).  Returns three (ncol,) CUDA tensors."""
+    dev = _require_cuda(device)
+    hist = _dev_f64(hist, dev)
+    S, Cn, cols = hist.shape
+    ncol = cols - col0 if ncol is None else int(ncol)
+    r, mu, var = (torch.empty(ncol, dtype=torch.float64, device=dev) for _ in range(3))
+    with torch.cuda.device(dev):
+        _capi.check(_capi.lib().gpf_chain_diagnostics(_ptr(hist), S, Cn, cols, int(col0), ncol, int(bool(split)), _ptr(r), _ptr(mu),
+                                                       _ptr(var), _stream(dev)))
+    return r, mu, var
+
+
+def row_sort(v, device=None):
+    """ascending sort of every row of v (rows, S <= 8192) on the device; returns a new CUDA tensor"""
+    dev = _require_cuda(device)
+    v = _dev_f64(v, dev).clone()
+    if v.dim() == 1:
+        v = v[None]
+    with torch.cuda.device(dev):
+        _capi.check(_capi.lib().gpf_row_sort(_ptr(v), v.shape[0], v.shape[1], _stream(dev)))
+    return v
+
+
+def function_interval(samples, alpha=.95, start=1e-6, tol=1e-6, maxiter=100, device=None):
+    """FunctionInterval (interval.py:62-131) for a batch of sample sets (batch, S, n) or one (S, n).
+    Returns (mean, std, epsilon, evaluations) as CUDA tensors."""
+    dev = _require_cuda(device)
+    X = _dev_f64(samples, dev)
+    if X.dim() == 2:
+        X = X[None]
+    b, S, n = X.shape
+    mean = torch.empty((b, n), dtype=torch.float64, device=dev)
+    std = torch.empty((b, n), dtype=torch.float64, device=dev)
+    eps = torch.empty(b, dtype=torch.float64, device=dev)
+    it = torch.zeros(b, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _capi.check(_capi.lib().gpf_function_interval(_ptr(X), b, S, n, float(alpha), float(start), float(tol), int(maxiter),
+                                                       _ptr(mean), _ptr(std), _ptr(eps), _ptr(it), _stream(dev)))
+    return mean, std, eps, it
+
+
 # ----------------------------------------------------------------------------------------------
 # sampler context
 # ----------------------------------------------------------------------------------------------
@@ -116,10 +319,11 @@ _PREFAULT = None
 
 
 def _prefault_pool():
+    """page-touching threads (one per concurrently sampling engine: EngineGroup runs one sweep_host per device)"""
     global _PREFAULT
     if _PREFAULT is None:
         from concurrent.futures import ThreadPoolExecutor
-        _PREFAULT = ThreadPoolExecutor(max_workers=1)
+        _PREFAULT = ThreadPoolExecutor(max_workers=8)
     return _PREFAULT
 
 
@@ -362,16 +566,24 @@ class ChainEngine(object):
             self._dev_hist = [torch.empty((cap, self.C, cols), dtype=torch.float64, device=self.dev) for _ in range(2)]
         t_begin = time.perf_counter()
         out = np.empty((rows_total, self.C, cols))
+        # Fresh pageable memory: the first write to every 4 KB page faults (~2 GB/s per thread).  A background thread
+        # touches the pages in drain order while the GPU runs the first sweeps; `touched` is the number of doubles it has
+        # passed.  A drain never writes a region the toucher has not finished with (it waits for `touched` to pass the end
+        # of its region), so the toucher's zeros can never land on copied data, and it is joined before the array is
+        # returned.
+        touched = [out.size]
+        toucher = None
         if out.nbytes >= (64 << 20):
-            # fresh pageable memory: the first write to every 4 KB page faults (~2 GB/s per thread).  Touch the pages from
-            # a background thread while the GPU runs the first sweeps, so that the drains copy at memcpy speed
             flat = out.reshape(-1)
-            blk = 8 << 20                                      # doubles per block (64 MB), in drain order
+            blk = 2 << 20                                      # doubles per block (16 MB), in drain order
+            touched[0] = 0
 
             def prefault():
                 for a in range(0, flat.size, blk):
                     flat[a:a + blk:512] = 0.0
-            _prefault_pool().submit(prefault)
+                    touched[0] = min(flat.size, a + blk)
+                touched[0] = flat.size
+            toucher = _prefault_pool().submit(prefault)
         pending = []                                           # (buffer index, first row, rows)
         done, row0, i = 0, 0, 0
 
@@ -388,6 +600,9 @@ class ChainEngine(object):
                 tm["copy"] += time.perf_counter() - t1
 
         def _drain_copy(b, r0, nr):
+            end = (r0 + nr) * self.C * cols
+            while touched[0] < end:                            # the page toucher is still inside this region
+                time.sleep(0.0002)
             dst = out[r0:r0 + nr].reshape(-1)
             src = self._stage[b].numpy()[:nr].reshape(-1)
             # the copy into fresh pageable memory is page-fault bound (~2 GB/s per thread): spread it over a few threads
@@ -420,6 +635,8 @@ class ChainEngine(object):
                 on_chunk(done)
         while pending:
             drain()
+        if toucher is not None:
+            toucher.result()                                   # never leave a writer behind the returned array
         self.sync()
         if tm is not None:
             sys.stderr.write("sweep_host: rows %d chunk rows %d  event wait %.3f s  copy %.3f s  total %.3f s\n" % (

@@ -1,14 +1,13 @@
 """Prior over a group of latent functions (gpfanova/prior.py:6-111).
 
-The reference's class is an unfinished refactor (it is not imported by gpfanova/__init__.py and calls methods that
-do not exist, prior.py:46,50,94), so there is no behaviour to be bug-compatible with; this keeps its shape -- one RBF
-kernel shared by a set of functions, `loglikelihood` and `sample` -- backed by the same device operators as the model.
-"""
+The reference's class is an unfinished refactor (it is not imported by gpfanova/__init__.py and calls methods that do not
+exist, prior.py:46,50,94), so there is no behaviour to be bug-compatible with; this keeps its shape -- one RBF kernel
+shared by a set of functions, `loglikelihood` and `sample` -- on the batched device operators gpf_gp_loglik / gpf_gp_sample
+(jitchol with the reference's jitter ladder, log-determinant from the pivots, quadratic forms from rows riding along the
+factorisation, draws L z)."""
 import numpy as np
-import torch
 
 from . import engine
-from .kernel import RBF
 
 
 class Prior(object):
@@ -18,27 +17,37 @@ class Prior(object):
         self.x = np.asarray(x, dtype=np.float64)
         self.n = self.x.shape[0]
         self.kernel = kernel
-        self.functions = list(functions)
+        self._functions = [int(f) for f in functions]
         self.base = base
         self.name = name
 
-    def loglikelihood(self, F, *args, **kwargs):
-        """sum_f log N(F[:, f]; 0, K + mean(K) 1e-6 I)  (the MVN part of base.py:216-243) through the device
-        Cholesky: log-determinant from the pivots, quadratic forms from triangular solves."""
+    def functions(self):
+        return self._functions
+
+    def _log10(self, *args, **kwargs):
+        return self.kernel._log10_params(*args, **kwargs)
+
+    def loglikelihood(self, F=None, *args, **kwargs):
+        """sum_f log N(F[:, f]; 0, L L^T), L = jitchol(K)  (prior.py:86-99).  F: (n, #functions) values of this prior's
+        functions; default: the current values in the model's parameter_cache.  Kernel parameters may be overridden by
+        position or name like Kernel.K (log10 values for logspace kernels)."""
+        if F is None:
+            F = self.base.functionMatrix(only=self._functions)
         F = np.asarray(F, dtype=np.float64)
         if F.ndim == 1:
             F = F[:, None]
-        K = self.kernel.K(self.x, *args, **kwargs)
-        cov = K + K.mean() * np.eye(self.n) * 1e-6
-        L, logdet, _ = engine.jitchol(cov, return_info=True)
-        V = torch.linalg.solve_triangular(L, torch.as_tensor(F).to(L.device), upper=False)
-        quad = (V * V).sum(0)
-        ll = -0.5 * (self.n * np.log(2 * np.pi) + logdet + quad)
-        return float(ll.sum().item())
+        ls, ll = self._log10(*args, **kwargs)
+        return float(engine.gp_loglik(self.x, ls, ll, F.T[None])[0].item())
 
-    def sample(self, size=1, *args, **kwargs):
-        """draws from N(0, K) (base.py:245-254) using the device kernel matrix and factor"""
-        K = self.kernel.K(self.x, *args, **kwargs)
-        L = engine.jitchol(K)
-        z = torch.as_tensor(np.random.standard_normal((self.n, size))).to(L.device)
-        return (L @ z).cpu().numpy()
+    def loglikelihoods(self, log10_sigma, log10_lengthscale, F):
+        """batched: one value per (sigma, lengthscale) pair; F (batch, #functions, n) or (#functions, n) shared"""
+        return engine.gp_loglik(self.x, log10_sigma, log10_lengthscale, F).cpu().numpy()
+
+    def sample(self, size=None, seed=None, *args, **kwargs):
+        """draws from N(0, L L^T), L = jitchol(K) (prior.py:67-84): (n, #functions), one draw per function of this prior;
+        size=S: (S, n) draws"""
+        ls, ll = self._log10(*args, **kwargs)
+        seed = int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else int(seed)
+        k = len(self._functions) if size is None else int(size)
+        out = engine.gp_sample(self.x, ls, ll, nsamp=k, seed=seed)[0].cpu().numpy()
+        return out.T if size is None else out

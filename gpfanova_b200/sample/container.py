@@ -1,97 +1,88 @@
-"""SamplerContainer (gpfanova/sample/container.py:6-105): ordered sampler list, parameter_cache / parameter_history,
-thinning, CSV save / load.  Base overrides sample() with the fused device sweep; this generic loop stays for
-containers assembled from user samplers."""
+"""SamplerContainer -- the state store and sweep driver API of gpfanova/sample/container.py:6-105: an ordered list of
+samplers, `parameter_cache` (current value of every label), `parameter_history` (one row per stored sweep), thinning,
+CSV save / load.  Base overrides sample() with the fused device sweep; the generic loop below serves containers
+assembled from arbitrary user samplers."""
 import logging
 import random as pyrandom
 import time
 
+import numpy as np
 import pandas as pd
 
 from .sampler import Sampler
+
+LOG = logging.getLogger(__name__)
 
 
 class SamplerContainer(object):
 
     def __init__(self, samplers, parameterFile=None, *args, **kwargs):
-        self.samplers = [a for a in samplers if issubclass(type(a), Sampler)]
-        self.sampler_dict = {a.name: a for a in self.samplers}
-        ind = self.build_index()
-        self.parameter_cache = pd.Series([0.0] * len(ind), index=ind)
-        self.parameter_history = pd.DataFrame(columns=ind)
-        for k, v in kwargs.items():
-            if k in self.sampler_dict:
-                self.parameter_cache[self.sampler_dict[k].parameters] = v
+        self.samplers = [s for s in samplers if isinstance(s, Sampler)]
+        self.sampler_dict = {s.name: s for s in self.samplers}
+        labels = self.build_index()
+        self.parameter_cache = pd.Series(np.zeros(len(labels)), index=labels)
+        self.parameter_history = pd.DataFrame(columns=labels)
+        # keyword arguments named after a sampler give its initial value (container.py:16-18)
+        for name in set(kwargs) & set(self.sampler_dict):
+            self.parameter_cache[self.sampler_dict[name].parameters] = kwargs[name]
         self.load(parameterFile)
 
     def build_index(self):
-        ind = []
-        for s in self.samplers:
-            ind += s.parameters
-        return ind
+        return [lab for s in self.samplers for lab in s.parameters]
 
     def _sample(self, random=False):
-        logger = logging.getLogger(__name__)
-        ind = list(range(len(self.samplers)))
+        """one sweep: every sampler once, in list order or shuffled (container.py:29-53)"""
+        todo = list(self.samplers)
         if random:
-            pyrandom.shuffle(ind)
-        for i in ind:
-            sampler = self.samplers[i]
-            logger.debug('sampling %s' % str(sampler))
-            args = []
-            if sampler.current_param_dependent:
-                param = self.parameter_cache[sampler.parameters]
-                if len(sampler.parameters) == 1:
-                    param = param.iloc[0]
-                args += [param]
-            sample = sampler.sample(*args)
-            self.parameter_cache[sampler.parameters] = sample
+            pyrandom.shuffle(todo)
+        for s in todo:
+            LOG.debug('sampling %s' % str(s))
+            args = ()
+            if s.current_param_dependent:
+                cur = self.parameter_cache[s.parameters]
+                args = (cur.iloc[0] if len(s.parameters) == 1 else cur,)
+            self.parameter_cache[s.parameters] = s.sample(*args)
 
     def sample(self, n=1, thin=0, verbose=False, random=False):
-        logger = logging.getLogger(__name__)
-        start = self.parameter_history.shape[0]
-        start_time = time.time()
+        t0 = time.time()
+        stored = 0
         for i in range(n):
             self._sample(random=random)
             if thin == 0 or (i + 1) % thin == 0:
                 self.store()
-                j = self.parameter_history.shape[0] - start
+                stored += 1
                 if verbose:
-                    logger.info("%d/%d iterations (%.2lf%s) finished in %.2lf minutes" % (
-                        j, n, 100. * j / n, '%', (time.time() - start_time) / 60))
+                    LOG.info("%d/%d iterations (%.2lf%s) finished in %.2lf minutes" % (
+                        stored, n, 100. * stored / n, '%', (time.time() - t0) / 60))
         if verbose:
-            logger.info("%d samples finished in %.2lf minutes" % (n, (time.time() - start_time) / 60))
+            LOG.info("%d samples finished in %.2lf minutes" % (n, (time.time() - t0) / 60))
 
     def parameterSamples(self, name):
-        if name not in self.sampler_dict:
-            return None
-        return self.parameter_history[self.sampler_dict[name].parameters]
+        s = self.sampler_dict.get(name)
+        return None if s is None else self.parameter_history[s.parameters]
 
     def parameterCurrent(self, name):
-        if name not in self.sampler_dict:
-            return None
-        return self.parameter_cache[self.sampler_dict[name].parameters]
+        s = self.sampler_dict.get(name)
+        return None if s is None else self.parameter_cache[s.parameters]
 
     def store(self):
-        row = self.parameter_cache.to_frame().T
-        if self.parameter_history.shape[0] == 0:
-            self.parameter_history = row.reset_index(drop=True)
-        else:
-            self.parameter_history = pd.concat([self.parameter_history, row], ignore_index=True)
-        self.parameter_history.index = range(self.parameter_history.shape[0])
+        """append the current parameter_cache as a new row of parameter_history (container.py:90-92)"""
+        row = pd.DataFrame([self.parameter_cache.to_numpy()], columns=self.parameter_cache.index)
+        hist = self.parameter_history
+        self.parameter_history = row if hist.shape[0] == 0 else pd.concat([hist, row], ignore_index=True)
 
     def save(self, f):
         self.parameter_history.to_csv(f, index=False)
 
     def load(self, f):
-        if f is None:
-            return
-        self.parameter_history = pd.read_csv(f, index_col=None)
+        if f is not None:
+            self.parameter_history = pd.read_csv(f, index_col=None)
 
     def resume_from_last(self):
         """copy the last stored row back into parameter_cache (what analysis/hsalTF/hsalTF.py:123 does by hand)"""
-        if self.parameter_history.shape[0] > 0:
+        if self.parameter_history.shape[0]:
             last = self.parameter_history.iloc[-1]
             self.parameter_cache[last.index] = last.values.astype(float)
 
     def __repr__(self):
-        return "\n".join(['SamplerContainer:'] + [str(samp) for samp in self.samplers])
+        return "\n".join(['SamplerContainer:'] + [str(s) for s in self.samplers])

@@ -66,6 +66,69 @@ int gpf_jitchol(const double* d_A, int n, int batch, int maxtries, double* d_L, 
  * d_A, d_Ainv: batch x n x n full matrices. */
 int gpf_kinv(const double* d_A, int n, int batch, double offset, double* d_Ainv, int* d_status, void* stream);
 
+/* RBF.dist, kernel/rbf.pyx:8-14: scaled distances sqrt(clip(-2 X X^T + |X_i|^2 + |X_j|^2, 0)), X = x / 10^l_b.
+ * d_out: batch x n x n. */
+int gpf_rbf_dist(const double* d_x, int n, int p, const double* d_log10_ls, int batch, double* d_out, void* stream);
+
+/* RBF._dK, kernel/rbf.pyx:21-38 (used by FunctionDerivative, sample/function.py:43-66), with the reference's own
+ * scaling: diff = x_i - x_j on the first input dimension;  cross: (-1/l) diff K;  else (1/l)(1 - diff^2 / l) K.
+ * d_out: batch x n x n. */
+int gpf_rbf_dK(const double* d_x, int n, int p, const double* d_log10_sigma, const double* d_log10_ls, int cross, int batch,
+               double* d_out, void* stream);
+
+/* sum over nf functions of log N(F_f; 0, K + (add_rel mean(K) + add_abs) I) for a batch of (sigma, lengthscale) pairs, each
+ * with its own functions d_F (batch x nf x n); Cholesky with linalg.jitchol's ladder (maxtries), log-determinant from the
+ * pivots, quadratic forms from the rows riding along.  Replaces the multivariate-normal log-pdf of prior.py:86-99
+ * (add_rel = 0: cov = L L^T of jitchol(K)) and of base.py:222,233-238 (add_rel = 1e-6).
+ * d_ll: batch; d_logdet (may be NULL): batch; d_status: batch (GPF_STATUS_*). */
+int gpf_gp_loglik(const double* d_x, int n, int p, const double* d_log10_sigma, const double* d_log10_ls, int batch, const double* d_F,
+                  int nf, double add_rel, double add_abs, int maxtries, double* d_ll, double* d_logdet, int* d_status, void* stream);
+
+/* nsamp draws L z from N(0, K + add I), L = jitchol(K + add I), for every (sigma, lengthscale) pair of the batch:
+ * Base.samplePrior's function draws (base.py:249-254) and Prior.sample (prior.py:67-84), batched.
+ * z: d_z_inject (batch x nsamp x n) or, if NULL, Philox4x32-10 keyed by seed with counter (pair, draw, stream_id, batch item).
+ * d_out: batch x nsamp x n. */
+int gpf_gp_sample(const double* d_x, int n, int p, const double* d_log10_sigma, const double* d_log10_ls, int batch, int nsamp,
+                  const double* d_z_inject, unsigned long long seed, unsigned stream_id, double add_rel, double add_abs, int maxtries,
+                  double* d_out, int* d_status, void* stream);
+
+/* FunctionDerivative, sample/function.py:43-66, for a batch of (sigma, lengthscale) pairs with nf <= 32 functions each
+ * (d_F: batch x nf x n):  mu_f = K_ba K_a^-1 beta_f,  cov = K_b - K_ba K_a^-1 K_ba^T,  draw beta'_f = mu_f + L_cov z_f,
+ * K_a^-1 = (K + offset I)^-1 (kernel.pyx:51-64), K_b / K_ba = RBF._dK without / with cross (rbf.pyx:21-38), L_cov =
+ * jitchol(cov).  z: d_z_inject (batch x nf x n) or Philox (counter: pair, function, stream_id, batch item).
+ * d_dF: batch x nf x n;  d_mu (batch x nf x n) and d_cov (batch x n x n) may be NULL;  d_status: batch. */
+int gpf_function_derivative(const double* d_x, int n, int p, const double* d_log10_sigma, const double* d_log10_ls, int batch,
+                            const double* d_F, int nf, const double* d_z_inject, unsigned long long seed, unsigned stream_id,
+                            double offset, int maxtries, double* d_dF, double* d_mu, double* d_cov, int* d_status, void* stream);
+
+/* y[b] (n x m) = F[b]^T X^T + sd[b] * standard normal noise (base.py:256-257) for a batch of function sets F (batch x f x n);
+ * X: m x f design matrix; noise from Philox keyed by seed (counter: pair, 0xffff, stream_id, batch item). */
+int gpf_compose_y(const double* d_F, const double* d_X, const double* d_sd, int batch, int n, int m, int f, unsigned long long seed,
+                  unsigned stream_id, double* d_y, void* stream);
+
+/* FANOVA's Transform samplers (fanova.py:58-81 -> effectSample :106-115, finitePopulationVarianceSample :117-124) for `rows`
+ * stored states at once.  d_F: rows x f x n.  Block b maps its contrast functions in0[b] .. in0[b]+nin[b] to nout[b] effect
+ * rows through h_coef (the blocks' nout x nin contrast matrices, row-major, concatenated) and, if h_fpv[b], appends the
+ * finite-population variance row diag(a P a^T)/(nout-1).  d_out: rows x Q x n, Q = sum_b (nout[b] + fpv[b]), blocks in order. */
+int gpf_fanova_transform(const double* d_F, long long rows, int f, int n, int nblk, const int* h_in0, const int* h_nin, const int* h_nout,
+                         const int* h_fpv, const double* h_coef, double* d_out, void* stream);
+
+/* Diagnostics over the stored history d_hist (S rows x C chains x cols, the layout gpf_sweep writes) for the columns
+ * col0 .. col0+ncol: split-R^ over the C chains (split != 0: every chain cut in halves), pooled mean and the posterior
+ * variance estimate.  d_rhat, d_mean, d_var: ncol each. */
+int gpf_chain_diagnostics(const double* d_hist, int S, int C, long long cols, int col0, int ncol, int split, double* d_rhat,
+                          double* d_mean, double* d_var, void* stream);
+
+/* ascending sort of every row of d_v (rows x S, S <= 8192), in place: the sorted log densities of ScalarInterval
+ * (interval.py:32-35; Chen & Shao HPD threshold = element int(S alpha)). */
+int gpf_row_sort(double* d_v, int rows, int S, void* stream);
+
+/* FunctionInterval (interval.py:62-131) for a batch of sample sets d_samples (batch x S x n): mean, population std, and
+ * the epsilon found by the reference's doubling + bisection on the fraction of samples inside mean -+ 2 std -+ epsilon.
+ * d_mean, d_std: batch x n; d_eps: batch; d_iters: batch (evaluations of the coverage). */
+int gpf_function_interval(const double* d_samples, int batch, int S, int n, double alpha, double start, double tol, int maxiter,
+                          double* d_mean, double* d_std, double* d_eps, int* d_iters, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Sampler context: C chains of one model  y (n x m) = F (n x f) X^T (f x m) + noise
  * replaces Base.__init__ state + SamplerContainer.parameter_cache (base.py:16-86, container.py:8-20)

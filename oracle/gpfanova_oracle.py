@@ -640,3 +640,90 @@ def fanova_transforms(design, F):
                         v = np.dot(Fi, design.contrasts_interaction[(k, i)][l * design.mk[i] + j, :])
                         out.append(('(%s,%s)_(%d,%d)' % (suf(k), suf(i), l, j), v))
     return out
+
+
+# --------------------------------------------------------------------------
+# "next" rows of SURVEY.md 8f: derivative sampler, intervals, diagnostics
+# --------------------------------------------------------------------------
+def rbf_dK(X, sigma, lengthscale, cross=False):
+    """kernel/rbf.pyx:21-38 (RBF._dK), including its scaling by 1/lengthscale (not 1/lengthscale^2) and its use of the
+    UNSCALED first input dimension for diff."""
+    k = rbf_K(X, sigma, lengthscale)
+    diff = X[:, 0][:, None] - X[:, 0][None, :]                      # rbf.pyx:30-32
+    if cross:
+        return (-1. / lengthscale) * diff * k                       # rbf.pyx:34-35
+    return (1. / lengthscale) * (1 - (1. / lengthscale) * (diff ** 2)) * k     # rbf.pyx:37
+
+
+def function_derivative_params(X, beta, sigma, lengthscale):
+    """sample/function.py:51-60 (FunctionDerivative._params): mu = K_ba K_a^-1 beta, cov = K_b - K_ba K_a^-1 K_ba^T with
+    K_a^-1 = Kernel.K_inv (kernel.pyx:51-64)."""
+    ka_inv = K_inv(rbf_K(X, sigma, lengthscale))[0]
+    kb = rbf_dK(X, sigma, lengthscale)
+    kba = rbf_dK(X, sigma, lengthscale, cross=True)
+    mu = np.dot(kba, np.dot(ka_inv, beta))
+    cov = kb - np.dot(kba, np.dot(ka_inv, kba.T))
+    return mu, cov
+
+
+def scalar_interval_threshold(samples, alpha, pi):
+    """interval.py:21-35 (ScalarInterval.__init__): sorted densities, threshold epsilon[int(n alpha)]"""
+    eps = sorted(pi(t) for t in samples)
+    return eps[int(len(samples) * alpha)], eps
+
+
+def function_interval(samples, alpha, start=1e-6, tol=1e-6, maxiter=100):
+    """interval.py:62-115 (FunctionInterval.__init__), statement by statement.  Returns dict(alpha, mean, std, epsilon,
+    lb, ub, evaluations)."""
+    samples = np.asarray(samples, dtype=float)
+    n = samples.shape[0]
+    alphaPotential = 1. * np.arange(n) / n                                                      # :65
+    alpha_eff = [v for v in alphaPotential if abs(v - alpha) == abs(alpha - alphaPotential).min()][0]   # :66
+    mean = samples.mean(0)                                                                      # :68
+    std = samples.std(0)                                                                        # :69
+    lb, ub = mean - 2 * std, mean + 2 * std                                                     # :70
+    evals = [0]
+
+    def check(x):                                                                               # :75
+        evals[0] += 1
+        return 1. * sum((samples > lb - x).all(1) & (samples < ub + x).all(1)) / n
+    epsilon = start
+    while check(epsilon) < alpha_eff:                                                           # :80-82
+        epsilon *= 2
+    eLb, eUb = epsilon / 2, epsilon                                                             # :87
+    i = 0
+    while True:                                                                                 # :89-110
+        if abs(check(eLb) - alpha) < tol:
+            epsilon = eLb
+            break
+        elif abs(check(eUb) - alpha) < tol:
+            epsilon = eUb
+            break
+        nb = (eLb + eUb) / 2
+        if check(nb) < alpha:
+            eLb = nb
+        else:
+            eUb = nb
+        i += 1
+        if i > maxiter:
+            epsilon = eLb
+            break
+    return dict(alpha=alpha_eff, mean=mean, std=std, epsilon=epsilon, lb=mean - std - epsilon, ub=mean + std + epsilon,
+                evaluations=evals[0])
+
+
+def split_rhat(hist, split=True):
+    """split-R^ (Gelman et al., BDA3 11.4) per column of hist (S, C, cols): every chain cut into its first and last
+    S // 2 rows.  Not in the reference (one chain per process); restated here as the checker of gpf_chain_diagnostics.
+    Returns (rhat, pooled mean, posterior variance estimate)."""
+    S, C, cols = hist.shape
+    if split and S >= 4:
+        L = S // 2
+        seqs = np.concatenate([hist[:L], hist[S - L:]], axis=1)       # (L, 2C, cols)
+    else:
+        L, seqs = S, hist
+    means = seqs.mean(0)
+    W = seqs.var(0, ddof=1).mean(0)
+    Bn = means.var(0, ddof=1)
+    vhat = (L - 1.0) / L * W + Bn
+    return np.sqrt(vhat / W), means.mean(0), vhat

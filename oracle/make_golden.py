@@ -138,6 +138,17 @@ def stage_case(gp, name, x, y, effect, F, hyper, cands, **kw):
     if tvals:
         out['transform_names'] = np.array(tnames)
         out['transform_vals'] = np.array(tvals)
+    if kw.get('derivatives', False):
+        # FunctionDerivative (sample/function.py:43-66): the (mu, cov) of every derivative sampler, and the derivative kernels
+        for g in range(P):
+            out['dK_%d' % g] = m.kernels[g].dK(m.x)
+            out['dKcross_%d' % g] = m.kernels[g].dK(m.x, cross=True)
+        names_ = m.functionNames()
+        for f in range(m.f):
+            s_ = m.sampler_dict['d' + names_.get(f, 'f%d' % f)]
+            mu_, cov_ = s_._params()
+            out['dmu_%d' % f] = np.asarray(mu_)[:, 0]
+            out['dcov_%d' % f] = np.asarray(cov_)
     out['sampler_names'] = np.array([s.name for s in m.samplers])
     out['sampler_types'] = np.array([s.type for s in m.samplers])
     out['index'] = np.array(list(m.parameter_cache.index))
@@ -239,6 +250,16 @@ def main():
     y, fs = prior_data(gp, x, effect, 77, [-2, 0, 0, 0, 0])
     F = fs + 0.05 * np.random.default_rng(13).standard_normal(fs.shape)
     stage_case(gp, 'oneway_n64', x, y, effect, F, [-1.6, 0.2, -0.1, -0.3, 0.15], cands)
+
+    # derivatives=True (base.py:72-73): one-way, n = 20, lengthscales away from 1 (the reference's dK scaling shows)
+    n = 20
+    x = np.linspace(-1, 1, n)[:, None]
+    effect = np.array(list(range(3)) * 3)[:, None]
+    y, fs = prior_data(gp, x, effect, 55, [-2, 0, 0, 0, 0])
+    F = fs + 0.02 * np.random.default_rng(14).standard_normal(fs.shape)
+    stage_case(gp, 'oneway_n20_deriv', x, y, effect, F, [-1.5, 0.1, 0.15, -0.2, -0.1], cands, derivatives=True)
+    # lengthscale 1: the only case in which the reference's derivative kernels are a consistent joint covariance
+    stage_case(gp, 'oneway_n20_deriv_l1', x, y, effect, F, [-1.5, 0.1, 0.0, -0.2, 0.0], cands, derivatives=True)
 
     if only and 'jitchol' not in only:
         return

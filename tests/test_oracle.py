@@ -270,3 +270,38 @@ def test_reference_floor_against_arbiter():
                 assert abs(c[key][i] - tru[i]) <= 5e-9 * max(1, abs(tru[i]))
                 o = orc.prior_loglik(m.x, m.F[:, m.groups[0]].T, m.hyper[1], m.hyper[2], cand, which)
                 assert abs(o - tru[i]) <= 5e-9 * max(1, abs(tru[i]))
+
+
+@pytest.mark.parametrize("name", ["oneway_n20_deriv", "oneway_n20_deriv_l1"])
+def test_derivative_restatement_matches_reference(name):
+    """rbf_dK is the reference's RBF._dK bit for bit; FunctionDerivative._params to the conditioning of K_inv
+    (kernel.pyx:51-64 inverts a cond-1e11 matrix: two evaluations of the same formula differ by ~1e-6)"""
+    c = load_case(name)
+    for g in range(len(c["groups"])):
+        s, l = 10.0 ** c["hyper"][1 + 2 * g], 10.0 ** c["hyper"][2 + 2 * g]
+        assert np.array_equal(orc.rbf_dK(c["x"], s, l), c["dK_%d" % g])
+        assert np.array_equal(orc.rbf_dK(c["x"], s, l, cross=True), c["dKcross_%d" % g])
+        for f in c["groups"][g]:
+            mu, cov = orc.function_derivative_params(c["x"], c["F"][:, f], s, l)
+            assert relerr(mu, c["dmu_%d" % f]) < 2e-5
+            assert np.max(np.abs(cov - c["dcov_%d" % f])) < 2e-5 * max(np.max(np.abs(c["dK_%d" % g])), 1e-12)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="live reference only in the build container")
+def test_interval_restatement_matches_live_reference():
+    """oracle.function_interval / scalar_interval_threshold against gpfanova/interval.py of the live reference"""
+    import build_ref
+    build_ref.build(quiet=True)
+    gp = build_ref.import_ref()
+    rng = np.random.default_rng(4)
+    for S, n, alpha in ((200, 12, .95), (333, 5, .9), (64, 30, .5)):
+        X = np.cumsum(rng.standard_normal((S, n)), axis=1) * 0.3 + rng.standard_normal((S, 1))
+        ref = gp.interval.FunctionInterval(X, alpha)
+        got = orc.function_interval(X, alpha)
+        assert got["epsilon"] == ref.epsilon and got["alpha"] == ref.alpha
+        assert np.array_equal(got["lb"], ref.lb) and np.array_equal(got["ub"], ref.ub)
+        x = rng.standard_normal(S)
+        pi = lambda t: -0.5 * t * t
+        ref = gp.interval.ScalarInterval(x, alpha, pi)
+        thr, eps = orc.scalar_interval_threshold(x, alpha, pi)
+        assert thr == ref.epj and eps == ref.epsilon
