@@ -226,7 +226,7 @@ class Base(SamplerContainer):
         vals[self._pos_h] = self._hyper[0]
         vals[self._pos_F] = self._F[0].ravel()
         if len(self._pos_T):
-            vals[self._pos_T] = self._transform_block(self._F[0][None])[0]
+            vals[self._pos_T] = self._device_transforms(np.ascontiguousarray(self._F[0][None]))[0]
         self.parameter_cache.iloc[:] = vals
 
     def set_chain_state(self, hyper=None, F=None):
@@ -299,7 +299,7 @@ class Base(SamplerContainer):
             if (out[-1] < 0).any() and not getattr(self, "_deriv_warned", False):
                 self._deriv_warned = True
                 LOG.error("FunctionDerivative: covariance not positive definite (prior %d); the reference's derivative kernels "
-                          "(rbf.pyx:34-37) only form a covariance at lengthscale 1 -- derivative draws are NaN there" % g)
+                          "(rbf.pyx:34-37) only form a covariance for lengthscales <= 1 -- derivative draws are NaN there" % g)
             if want_moments:
                 moments[g] = (out[1].cpu().numpy(), out[2].cpu().numpy())
         return (dF, moments) if want_moments else dF

@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_function_derivative(DerivArgs a) {
       }
       __syncthreads();
       if (ccode < 0) {
-        // the reference's K_b / K_ba scaling (rbf.pyx:34-37) only gives a covariance for lengthscale 1; otherwise cov is
+        // the reference's K_b / K_ba scaling (rbf.pyx:34-37) only gives a covariance for lengthscales <= 1; beyond that cov is
         // indefinite and there is no Cholesky draw: the means stay available, the draws are NaN, the status says why
         code = ccode;
         for (int e = threadIdx.x; e < a.nf * n; e += NTHR) a.dF[(size_t)b * a.nf * n + e] = nan("");

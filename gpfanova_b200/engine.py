@@ -185,8 +185,8 @@ def function_derivative(x, log10_sigma, log10_lengthscale, F, z=None, seed=0, st
                         want_moments=False, raise_on_error=True):
     """FunctionDerivative (sample/function.py:43-66) for a batch of kernels: F (batch, nf, n) function values ->
     draws of their derivatives (batch, nf, n); want_moments: also (mu (batch, nf, n), cov (batch, n, n)).
-    Where cov is not positive definite even with jitter (the reference's derivative kernels only form a covariance at
-    lengthscale 1, rbf.pyx:34-37) the draws are NaN and, unless raise_on_error=False, LinAlgError is raised; the last
+    Where cov is not positive definite even with jitter (the reference's derivative kernels only form a covariance for
+    lengthscales <= 1, rbf.pyx:34-37) the draws are NaN and, unless raise_on_error=False, LinAlgError is raised; the last
     element of the returned tuple is the per-item status."""
     dev, x, (s, l) = _x_and_params(x, device, log10_sigma, log10_lengthscale)
     n, p = x.shape
