@@ -76,6 +76,7 @@ SIGNATURES = {
     "gpf_sweep": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_void_p, C.c_void_p, C.c_longlong,
                             C.POINTER(C.c_longlong)]),
     "gpf_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "gpf_get_option": (C.c_int, [C.c_void_p, C.c_int]),
     "gpf_set_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "gpf_get_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "gpf_debug_trace": (C.c_int, [C.c_void_p, C.c_void_p]),

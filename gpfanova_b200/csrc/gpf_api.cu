@@ -15,6 +15,7 @@
 #include "gpf_cond.cuh"
 #include "gpf_ops.cuh"
 #include "gpf_schur.cuh"
+#include "gpf_schurfn.cuh"
 
 using namespace gpf;
 
@@ -57,6 +58,8 @@ struct gpf_ctx {
   int *d_cls1_off = nullptr, *d_gcls1_off = nullptr;   // option 2 = 0: every function its own class
   unsigned* d_cls_sid = nullptr;
   double* d_kinv_tmp = nullptr;       // scratch of the K_inv operator (gpf_group_kinv with an output buffer)
+  bool schurfn_ok = false;            // uniform grid, balanced design, n <= 256, groups of at most 4: O(n^2) function step
+  int use_schurfn = 1;
   std::vector<int> schur_warps;       // per group: warps per CTA of the Schur slice kernel (0: dense engine)
   int use_schur = 1;
   int batch = 1;                       // batch independent function draws / K_inv of all groups into one launch
@@ -207,9 +210,23 @@ int launch_function(gpf_ctx* c, int fn, unsigned sampler_id, unsigned sweep, con
 
 // every function of the model in one launch (only when the draws are independent of each other, c->indep):
 // one item per (prior group, chain) -- factor of K_o, then the group's classes (k_group_fused)
+bool schurfn_active(const gpf_ctx* c) { return c->schurfn_ok && c->use_schurfn && !c->dev.centro; }
+
 int launch_all_functions(gpf_ctx* c, unsigned sweep) {
   Timer t(c, 2);
   CK(c, cudaMemsetAsync(c->dev.sched, 0, sizeof(int), c->stream));
+  if (schurfn_active(c)) {
+    // uniform grid: both K_o and C = I + c K_o are Toeplitz -- O(n^2) Schur recursions, one warp per (group, chain)
+    SchurFnArgs a{c->d_gorder, c->share ? c->d_gcls_off : c->d_gcls1_off, c->share ? c->d_cls_off : c->d_cls1_off, c->d_cls_fn,
+                  c->d_cls_sid, sweep};
+    const int nld = ((c->dev.n + 7) / 8) * 8;
+    const size_t smem = (size_t)4 * SFN_NG * nld * sizeof(double);
+    const int grid = std::min((c->dev.C * c->dev.P + 3) / 4, 3 * c->sms);
+    k_group_schurfn<<<grid, 128, smem, c->stream>>>(c->dev, a);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    return GPF_OK;
+  }
   const int grid = std::min(c->dev.C * c->dev.P, 2 * c->sms);
   FusedArgs a{c->d_gorder, c->share ? c->d_gcls_off : c->d_gcls1_off, c->share ? c->d_cls_off : c->d_cls1_off, c->d_cls_fn,
               c->d_cls_sid, sweep};
@@ -709,6 +726,14 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
   }
   c->ncls = (int)coff.size() - 1;
   (void)maxcls;
+  {
+    size_t gmax = 0;
+    for (auto& grp : c->groups) gmax = std::max(gmax, grp.size());
+    c->schurfn_ok = c->toeplitz && c->indep && d->n <= 256 && d->n >= 8 && gmax <= (size_t)SFN_NG;
+    // the Schur function step uses the full Cholesky factor of K_o as the square root of the prior draw; the dense kernels
+    // then do the same (no centrosymmetric split), so that every path of one context implements one draw contract
+    if (c->schurfn_ok) v.centro = 0;
+  }
   // shared-memory budgets
   const size_t xsd = (size_t)d->n * d->p + d->n;
   c->smem_kinv = (engine_smem_doubles(v.NT, 0) + xsd) * sizeof(double);
@@ -756,6 +781,7 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
     if (e == cudaSuccess) e = allow_smem(k_prior<true>, sp);
     if (e == cudaSuccess) e = allow_smem(k_prior<false>, sp);
     if (e == cudaSuccess) e = allow_smem(k_prior_schur<0>, 112 * 1024);
+    if (e == cudaSuccess) e = allow_smem(k_group_schurfn, (size_t)4 * SFN_NG * 256 * sizeof(double));
     if (e != cudaSuccess) { c->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return fail(GPF_ERR_CUDA); }
   }
   c->grid = std::min(v.C, 2 * c->sms);
@@ -1134,8 +1160,23 @@ int gpf_set_option(gpf_ctx* c, int option, int value) {
     return GPF_OK;
   }
   if (option == 4) { c->dev.bhat = value ? c->d_bhat : nullptr; return GPF_OK; }
+  if (option == 5) { c->use_schurfn = value; return GPF_OK; }
   c->err = "gpf_set_option: unknown option";
   return GPF_ERR_ARG;
+}
+
+// effective setting of an option (what the kernels of the next sweep will do); -1 for unknown options
+int gpf_get_option(gpf_ctx* c, int option) {
+  switch (option) {
+    case 0: return c->use_schur;
+    case 1: return c->batch;
+    case 2: return c->share;
+    case 3: return c->dev.centro;
+    case 4: return c->dev.bhat != nullptr;
+    case 5: return schurfn_active(c) ? 1 : 0;
+    case 6: return c->indep ? 1 : 0;       // (read-only) balanced design, nothing missing
+    default: return -1;
+  }
 }
 
 int gpf_set_profile(gpf_ctx* c, int on) { c->profile = on; return GPF_OK; }

@@ -536,8 +536,13 @@ class ChainEngine(object):
         1: batched launches (balanced designs: one fused kernel per sweep for all function draws); 2: shared factorisation
         for functions with identical conditional precision; 3: centrosymmetric split on uniform grids (even n >= 64): all
         n^3 work of the function step on the two half-size blocks; 4: observation likelihood about the
-        least-squares fit (balanced designs, nothing missing)"""
+        least-squares fit (balanced designs, nothing missing); 5: function step by the O(n^2) Schur algorithm (uniform grid,
+        balanced design, n <= 256, prior groups of at most four functions)"""
         self._ck(self._lib.gpf_set_option(self._h, int(option), int(value)))
+
+    def get_option(self, option):
+        """effective value of an option (5: O(n^2) Schur function step active; 3: split factors of K_o; 6: balanced design)"""
+        return int(self._lib.gpf_get_option(self._h, int(option)))
 
     def sweep_host(self, n_sweeps=1, thin=0, order=None, stage_bytes=96 << 20, max_chunk_sweeps=None, on_chunk=None):
         """sweep() with the stored states delivered to the host as ONE numpy array (rows, C, H + f*n).
@@ -701,6 +706,9 @@ class EngineGroup(object):
     def set_option(self, option, value):
         for e in self.engines:
             e.set_option(option, value)
+
+    def get_option(self, option):
+        return self.engines[0].get_option(option)
 
     def set_state(self, F=None, hyper=None):
         for e, s in zip(self.engines, self._slices()):

@@ -249,8 +249,15 @@ int gpf_sweep(gpf_ctx* ctx, int n_sweeps, int thin, unsigned sweep0, const int* 
  * 0 = full-size matrices; changes the square root of K_o the prior draw uses, i.e. the map from z1 to the draw);
  * 4 = balanced design with nothing missing: the residual sum of squares of base.py:196-214 is evaluated about the
  * least-squares fit, ||y - X F||^2 = ||y - X bhat||^2 + sum_f (X^T X)[f,f] ||F_f - bhat_f||^2 (O(f n) per chain instead
- * of O(n m f), all terms non-negative; default 1; 0 = per-observation loop, always used otherwise). */
+ * of O(n m f), all terms non-negative; default 1; 0 = per-observation loop, always used otherwise);
+ * 5 = uniform grid, balanced design with nothing missing, n <= 256 and at most four functions per prior group: K_o and
+ * C = I + c K_o are symmetric positive definite Toeplitz matrices and the whole function step runs on the Schur
+ * algorithm, O(n^2) per function, one warp per (prior group, chain) (default 1 where it applies; 0 = dense fused kernel).
+ * Where option 5 applies, option 3 defaults to 0: the prior draw then uses the full Cholesky factor of K_o in every
+ * kernel of the context; setting option 3 to 1 selects the split factors and with them the dense kernels.
+ * gpf_get_option returns the EFFECTIVE value (option 6, read-only: 1 if the design is balanced with nothing missing). */
 int gpf_set_option(gpf_ctx* ctx, int option, int value);
+int gpf_get_option(gpf_ctx* ctx, int option);
 int gpf_set_profile(gpf_ctx* ctx, int on);
 int gpf_get_profile(gpf_ctx* ctx, double* h_ms6, unsigned long long* h_launches);
 /* development aid: cycle counters of the phases of the fused function kernel, read and cleared (all zero unless the

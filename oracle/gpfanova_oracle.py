@@ -562,6 +562,9 @@ class Model(object):
             self.order.append(('slice', 1 + 2 * g))
             self.order.append(('slice', 2 + 2 * g))
         self.counters = dict(chol=0, logp=0, jitter=0)
+        # square root of K_o used by the prior draw: True = block factor of the centrosymmetric split (the device's dense
+        # kernels on uniform even grids with option 3 on), False = full Cholesky factor; None = split wherever it applies
+        self.split = None
 
     # -- log densities on current state ---------------------------------
     def logp_hyper(self, h, cand):
@@ -577,7 +580,8 @@ class Model(object):
         """z: 2n standard normals [z1 | z2] (function_draw_obs)"""
         g = [i for i, grp in enumerate(self.groups) if f in grp][0]
         K = rbf_K(self.x, 10.0 ** self.hyper[1 + 2 * g], 10.0 ** self.hyper[2 + 2 * g])
-        SB, jit, nt = prior_sqrt(K, uniform_even_grid(self.x))
+        split = uniform_even_grid(self.x) if self.split is None else (bool(self.split) and uniform_even_grid(self.x))
+        SB, jit, nt = prior_sqrt(K, split)
         m_t, n_t = function_moments(self.y, self.X, self.F, f)
         st = function_conditional_obs(m_t, n_t, self.hyper[0], K, jit)
         self.counters['jitter'] += nt

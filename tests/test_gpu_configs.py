@@ -55,12 +55,23 @@ SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("shape", SHAPES, ids=[s[0] for s in SHAPES])
-def test_sweeps_at_config_shapes_follow_oracle(eng, shape):
+# which function-step kernel a shape takes by default, and whether the dense split variant is worth a second run:
+#   uniform grid, n <= 256, groups of <= 4 functions -> O(n^2) Schur kernel (option 5); option 3 = 1 -> dense fused kernel on
+#   the two half-size blocks
+PATHS = [(s, "default") for s in SHAPES] + [(s, "dense_split") for s in SHAPES if s[0] in ("cfg5_n256", "cfg2_n100_64chains", "hc3x3_n200")]
+
+
+@pytest.mark.parametrize("shape,path", PATHS, ids=["%s-%s" % (s[0], p) for s, p in PATHS])
+def test_sweeps_at_config_shapes_follow_oracle(eng, shape, path):
     name, levels, reps, n, hc, grid, C, S, och = shape
     x, y, d, groups, F = make_problem(levels, reps, n, hc, seed=len(name) + n, grid=grid)
     seed = 4242
     e = eng.ChainEngine(x, y, d.X, groups, chains=C, seed=seed, chain_offset=5)
+    if path == "dense_split":
+        e.set_option(3, 1)
+        assert e.get_option(3) == 1 and e.get_option(5) == 0
+    elif name in ("cfg5_n256", "cfg2_n100_64chains", "hc3x3_n200"):
+        assert e.get_option(5) == 1 and e.get_option(3) == 0
     rng = np.random.default_rng(3)
     hyper = np.concatenate([np.full((C, 1), -2.0), rng.uniform(-0.7, 0.7, size=(C, e.H - 1))], axis=1)
     e.set_state(F=np.zeros((C, e.f, n)), hyper=hyper)
@@ -75,6 +86,7 @@ def test_sweeps_at_config_shapes_follow_oracle(eng, shape):
     st = orc.Stream(seed)
     for ch in och:
         m = orc.Model(x, y, d.X, groups)
+        m.split = bool(e.get_option(3))
         m.hyper = hyper[ch].copy()
         for s in range(S):
             m.sweep(st, ch + 5, s)
@@ -83,12 +95,14 @@ def test_sweeps_at_config_shapes_follow_oracle(eng, shape):
     e.close()
 
 
-@pytest.mark.parametrize("shape", [s for s in SHAPES if s[0] in ("cfg5_n256", "hc3x3_n200", "oneway12_hc_n100", "odd_n101",
-                                                               "nonuniform_n72", "cokol9x9_hc_n200")],
-                         ids=lambda s: s[0])
-def test_fused_launch_equals_sequential_order_at_size(eng, shape):
+SEQ = [(s, p) for s, p in PATHS if s[0] != "cfg2_n100_64chains"]
+
+
+@pytest.mark.parametrize("shape,path", SEQ, ids=["%s-%s" % (s[0], p) for s, p in SEQ])
+def test_fused_launch_equals_sequential_order_at_size(eng, shape, path):
     """gpf_set_option(1, 0): one launch per sampler with the general kernel (own factorisation of C per function, factor of
-    K_o from HBM); default: one fused launch per sweep.  Same Philox stream, same draws to rounding."""
+    K_o from HBM); default: one fused launch per sweep (the O(n^2) Schur kernel where it applies, else the dense fused
+    kernel).  Same Philox stream, same square root of K_o, same draws to rounding."""
     name, levels, reps, n, hc, grid, C, S, och = shape
     x, y, d, groups, F = make_problem(levels, reps, n, hc, seed=7 + n, grid=grid)
     C = min(C, 3)
@@ -96,6 +110,9 @@ def test_fused_launch_equals_sequential_order_at_size(eng, shape):
     outs, fchol = [], []
     for batch, share in ((1, 1), (1, 0), (0, 0)):
         e = eng.ChainEngine(x, y, d.X, groups, chains=C, seed=99)
+        if path == "dense_split":
+            e.set_option(3, 1)
+        schur_path = bool(e.get_option(5))
         e.set_option(1, batch)
         e.set_option(2, share)
         hyper = np.concatenate([np.full((C, 1), -2.0), np.random.default_rng(8).uniform(-0.7, 0.7, size=(C, e.H - 1))], axis=1)
@@ -113,7 +130,8 @@ def test_fused_launch_equals_sequential_order_at_size(eng, shape):
         assert np.max(np.abs(o - outs[2])) < 1e-7 * scale, (name, np.max(np.abs(o - outs[2])))
     assert fchol[2] == C * d.f and fchol[1] == C * d.f and fchol[0] <= fchol[1]
     if hc:
-        assert fchol[0] == C * sum(-(-len(g) // 8) for g in groups)      # one factorisation of C per class and pass of 8
+        per = 2 if schur_path else 8       # functions per pass: Schur kernel 2 (registers), dense fused kernel 8 (rows riding along)
+        assert fchol[0] == C * sum(-(-len(g) // per) for g in groups)      # one factorisation of C per class and pass
 
 
 @pytest.mark.parametrize("name", ["cokol5x5_hc_n20", "oneway_n64"])
@@ -132,6 +150,7 @@ def test_new_goldens_whole_sweeps(eng, name):
     stream = orc.Stream(seed)
     for ch in range(C):
         m = oracle_model(c)
+        m.split = bool(e.get_option(3))
         for s in range(S):
             m.sweep(stream, ch, s)
             assert np.allclose(hist[s, ch, :e.H], m.hyper, rtol=0, atol=1e-6), (name, ch, s)

@@ -118,6 +118,18 @@ int main(){
   {float ms=timeit([&]{k_dmma1688<4><<<grid,256>>>(out,iters,1e-3,1e-3);},5); printf(",\"dmma1688_tflops\":%.2f",2.0*1024*(grid*8.0)*4*iters/ms/1e9);}
   {float ms=timeit([&]{k_dmma16816<4><<<grid,256>>>(out,iters,1e-3,1e-3);},5); printf(",\"dmma16816_tflops\":%.2f",2.0*2048*(grid*8.0)*4*iters/ms/1e9);}
   {float ms=timeit([&]{k_exp<<<grid,256>>>(out,iters,1e-4);},5); printf(",\"exp_gops\":%.1f",grid*256.0*4*iters/ms/1e6);}
+  // sustained: the same kernels back to back for ~3 s each (power / clock settle), one event pair around the whole run
+  {
+    auto sustained=[&](auto launch,double flop_per_launch){
+      cudaEvent_t a,b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+      launch(); CK(cudaDeviceSynchronize());
+      float one=timeit(launch,2); int reps=(int)(3000.0f/one)+1;
+      CK(cudaEventRecord(a)); for(int r=0;r<reps;r++) launch(); CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
+      float ms; CK(cudaEventElapsedTime(&ms,a,b)); return flop_per_launch*reps/ms/1e9;
+    };
+    printf(",\"dfma_tflops_sustained\":%.2f",sustained([&]{k_dfma<8><<<grid,256>>>(out,iters,1.0000001,1e-9);},2.0*grid*256.0*8*iters));
+    printf(",\"dmma884_tflops_sustained\":%.2f",sustained([&]{k_dmma884<8><<<grid,256>>>(out,iters,1e-3,1e-3);},2.0*256*(grid*8.0)*8*iters));
+  }
   k_lat<<<1,32>>>(cyc,out,2000,1.7); CK(cudaDeviceSynchronize()); long long h[6]; CK(cudaMemcpy(h,cyc,48,cudaMemcpyDeviceToHost));
   printf(",\"lat_cycles\":{\"sqrt_add\":%lld,\"div_add\":%lld,\"rsqrt_add\":%lld,\"dfma\":%lld,\"dmma884\":%lld,\"shfl64_add\":%lld}}\n",h[0],h[1],h[2],h[3],h[4],h[5]);
   return 0;
