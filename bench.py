@@ -208,23 +208,29 @@ def ncu_traffic(kernel_file, n, chains_per_gpu):
         return None
 
 
-def flops_model(n, f, P, ng_list, counts, schur):
-    """algorithmic FP64 flops of what was executed (counted by the kernels), DESIGN.md 5:
-    factor of K_o = K + 1e-9 I per (prior group, chain, sweep) and factor of C = I + c K_o per class of functions: n^3/3
-    each -- on a uniform grid with even n >= 64 two n/2 blocks through the centrosymmetric split, n^3/12;
-    per function draw two triangular solves (the forward one rides along the factorisation) and three triangular
-    products: 5 n^2 (split: 2.5 n^2);  K_inv operator (not on the sweep path): n^3 (split: n^3/4);
-    slice factorisation: dense n^3/3 + |g| n^2, or -- uniform grid, Schur algorithm -- (3 + |g|) n^2."""
-    n3 = float(n) ** 3
-    split = schur and n % 2 == 0 and n >= 64
-    per_fact = n3 / 12 if split else n3 / 3
+def flops_model(n, f, P, ng_list, counts, schur, schurfn):
+    """algorithmic FP64 flops of what was executed (counted by the kernels), DESIGN.md 5.
+    Schur recursion on an n x n Toeplitz matrix: one hyperbolic rotation per step, 6 flops per live position = 3 n^2;
+    every right-hand side riding along adds n^2 (forward substitution, 2 flops per position).
+      slice evaluation               (3 + |g|) n^2        (rotation + quadratic forms of the group's functions)
+      function step, K_o pass        3 n^2 + n^2 per function of the group (prior draw f = L_B z1 accumulated)
+      function step, C pass          6 n^2 (rotation of the Toeplitz generator and of the inverse-factor rows)
+                                     + 2 n^2 per function (forward substitution + accumulation of v = L^-T y)
+    Dense paths (non-uniform grids, n > 256, large groups): factor of K_o per (group, chain, sweep) and of C per class
+    n^3/3 each (centrosymmetric split: two half-size blocks, n^3/12); per draw two triangular solves and one to three
+    triangular products ~ 5 n^2; dense slice factorisation n^3/3 + |g| n^2.  K_inv operator (not on the sweep path) n^3."""
+    n2, n3 = float(n) ** 2, float(n) ** 3
     bfact = counts.get("ko_factor", 0)
-    fchol = counts.get("function_chol", counts["draws"])       # functions with identical conditional precision share one
-    inv = counts["inverses"] * (n3 / 4 if split else n3)
-    draws = (bfact + fchol) * per_fact + counts["draws"] * (2.5 if split else 5.0) * n * n
+    fchol = counts.get("function_chol", counts["draws"])       # passes over C: functions with the same precision share one
+    inv = counts["inverses"] * n3
+    if schurfn:
+        draws = bfact * 3 * n2 + counts["draws"] * n2 + fchol * 6 * n2 + counts["draws"] * 2 * n2
+    else:
+        split = schur and n % 2 == 0 and n >= 64
+        draws = (bfact + fchol) * (n3 / 12 if split else n3 / 3) + counts["draws"] * (2.5 if split else 5.0) * n2
     prior_facts = counts["chol"] - counts["inverses"] - fchol - bfact
     gbar = float(np.mean(ng_list))
-    per = (3.0 + gbar) * n * n if schur else (n3 / 3 + gbar * n * n)
+    per = (3.0 + gbar) * n2 if schur else (n3 / 3 + gbar * n2)
     return {"kinv": inv, "function": draws, "prior_slice": prior_facts * per, "prior_factorisations": prior_facts,
             "total": inv + draws + prior_facts * per}
 
@@ -325,6 +331,7 @@ def main():
     prof, _ = eng.profile()
     counts_prof = eng.counters()
     eng.set_profile(0)
+    schurfn = bool(eng.get_option(5))
     el = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(el, op=dist.ReduceOp.MAX)
@@ -334,23 +341,33 @@ def main():
     # ---------------- roofline of the dominant kernel (largest share of the step) ----------------
     peak, peak_src = fp64_peak()
     schur = bool(np.allclose(np.diff(x[:, 0]), np.diff(x[:, 0])[0], rtol=0, atol=1e-13)) and x.shape[1] == 1
-    fm = flops_model(n, f, P, [len(g) for g in groups], counts_prof, schur)
-    fm_timed = flops_model(n, f, P, [len(g) for g in groups], counts, schur)
+    fm = flops_model(n, f, P, [len(g) for g in groups], counts_prof, schur, schurfn)
+    fm_timed = flops_model(n, f, P, [len(g) for g in groups], counts, schur, schurfn)
+    fn_name = ("k_group_schurfn (all Function._sample draws of a sweep on a uniform grid, one warp per (prior group, chain): Schur "
+               "recursions on the Toeplitz matrices K_o and I + c K_o, prior draws, embedded inverse factor, Philox normals)"
+               if schurfn else
+               "k_group_fused (all Function._sample draws of a sweep, one (prior group, chain) item per CTA: RBF build + "
+               "jitchol(K_o) + per class jitchol(I + c K_o) with the right-hand sides riding along, solves, Philox draws; "
+               "centrosymmetric split: half-size blocks)")
     kern = {"kinv": ("k_group_factor (jitchol(K + 1e-9 I) of every prior group; only launched by sequential sweeps)", args.steps),
-            "function": ("k_group_fused (all Function._sample draws of a sweep, one (prior group, chain) item per CTA: RBF build + "
-                         "jitchol(K_o) + per class jitchol(I + c K_o) with the right-hand sides riding along, solves, Philox draws; "
-                         "centrosymmetric split: half-size blocks)", args.steps),
-            "prior_slice": ("k_prior_schur (sigma+lengthscale slice steps: Toeplitz/Schur GP log-likelihood)" if schur else
+            "function": (fn_name, args.steps),
+            "prior_slice": ("k_prior_schur (sigma+lengthscale slice steps: Toeplitz/Schur GP log-likelihood, one warp per chain; "
+                            "one launch per prior group)" if schur else
                             "k_prior (sigma+lengthscale slice steps: dense GP log-likelihood)", P * args.steps)}
     dom = max(("kinv", "function", "prior_slice"), key=lambda k: prof[k])
     tf = {k: (fm[k] / (prof[k] * 1e-3) / 1e12 if prof[k] > 0 else 0.0) for k in kern}
+    ncu_file = {"function": "ncu_r02_k_group_schurfn.txt" if schurfn else "ncu_r02_k_group_fused.txt",
+                "prior_slice": "ncu_r02_k_prior_schur.txt"}.get(dom, "")
     roofline = {"bound": "tensor", "kernel": kern[dom][0], "achieved": tf[dom], "peak": peak, "unit": "TFLOP/s",
                 "frac": tf[dom] / peak,
-                "traffic": ncu_traffic({"function": "ncu_r02_k_group_fused.txt"}.get(dom, ""), n, C),
-                "traffic_note": "bytes per launch from profiles/ncu_r02_*.txt (one ncu --set full capture of this workload); "
-                                "the kernel is FP64-tensor/latency bound: its algorithmic HBM bytes are the function values it "
-                                "writes (%.0f MB per launch) plus the shared L2-resident inputs; matrices never leave the "
-                                "CTA's L2-resident workspace" % (C * f * n * 8 / 1e6),
+                "bound_note": "FP64 pipe: B200 issues FP64 FMA and FP64 tensor (DMMA) work at the same rate (measured 33.98 / "
+                              "37.09 TFLOP/s sustained, profiles/fp64_peak_r02.json); the Schur kernels are FMA work, the dense "
+                              "kernels DMMA -- one denominator for both",
+                "traffic": ncu_traffic(ncu_file, n, C),
+                "traffic_note": "bytes per launch from profiles/%s (one ncu --set full capture of this workload).  Algorithmic "
+                                "HBM bytes per sweep: the function values written (%.0f MB) and read back by the slice kernels "
+                                "and the y_sigma kernel; every matrix is generated and consumed in registers" % (
+                                    ncu_file, C * f * n * 8 / 1e6),
                 "peak_source": peak_src,
                 "flops_per_launch": fm[dom] / kern[dom][1], "ms_per_launch": prof[dom] / kern[dom][1],
                 "share_of_step": prof[dom] / prof["total"] if prof["total"] else None,
@@ -419,8 +436,9 @@ def main():
                 "config": {"workload": WORKLOAD, "n": n, "m": int(eff.shape[0]), "f": int(f), "P": P, "chains": total_chains,
                            "chains_per_gpu": C, "parallelism": "chains sharded over %d GPU(s), no collective" % world,
                            "burnin_sweeps": args.burnin,
-                           "l2": "working set %.1f GB of per-chain K_inv tiles + state >> 126 MB L2; no flush needed" % (
-                               P * C * (n // 32) * (n // 32 + 1) / 2 * 8192 / 1e9)},
+                           "l2": "no flush needed: the per-chain state read and written every sweep (%.0f MB of function values + "
+                                 "hyper-parameters for %d chains) is the only HBM traffic of the Schur path and is touched once "
+                                 "per kernel; the matrices live in registers" % (C * f * n * 8 / 1e6, C)},
                 "wall_ms_per_step": 1e3 * wall / args.steps, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": e2e, "gpu_launches": int(launches1 - launches0)}
         print(json.dumps(line), flush=True)

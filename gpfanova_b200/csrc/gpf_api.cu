@@ -221,7 +221,7 @@ int launch_all_functions(gpf_ctx* c, unsigned sweep) {
                   c->d_cls_sid, sweep};
     const int nld = ((c->dev.n + 7) / 8) * 8;
     const size_t smem = (size_t)4 * SFN_NG * nld * sizeof(double);
-    const int grid = std::min((c->dev.C * c->dev.P + 3) / 4, 3 * c->sms);
+    const int grid = std::min((c->dev.C * c->dev.P + 3) / 4, GPF_SFN_MINB * c->sms);
     k_group_schurfn<<<grid, 128, smem, c->stream>>>(c->dev, a);
     ++c->launches;
     CK(c, cudaGetLastError());

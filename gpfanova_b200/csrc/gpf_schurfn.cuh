@@ -193,7 +193,10 @@ __device__ __forceinline__ void sfn_normals8(const Stream& rng, unsigned gch, un
   (void)n_valid_from;
 }
 
-__global__ void __launch_bounds__(128, 3) k_group_schurfn(CtxDev c, SchurFnArgs a) {
+#ifndef GPF_SFN_MINB
+#define GPF_SFN_MINB 3
+#endif
+__global__ void __launch_bounds__(128, GPF_SFN_MINB) k_group_schurfn(CtxDev c, SchurFnArgs a) {
   extern __shared__ __align__(16) double gpf_smem_sfn[];      // per warp: SFN_NG x nld (z1 of the group's functions, then their q)
   const int n = c.n, nld = ((n + 7) >> 3) << 3;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

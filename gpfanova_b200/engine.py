@@ -303,7 +303,7 @@ def function_interval(samples, alpha=.95, start=1e-6, tol=1e-6, maxiter=100, dev
 # ----------------------------------------------------------------------------------------------
 # sampler context
 # ----------------------------------------------------------------------------------------------
-_COPY_THREADS = max(1, int(os.environ.get("GPFANOVA_B200_COPY_THREADS", "4")))
+_COPY_THREADS = max(1, int(os.environ.get("GPFANOVA_B200_COPY_THREADS", str(min(8, max(2, (os.cpu_count() or 4) // 2))))))
 _POOL = None
 
 
