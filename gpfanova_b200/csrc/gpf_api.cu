@@ -259,7 +259,7 @@ int launch_prior(gpf_ctx* c, int g, int mode, const double* cand, double* outv, 
   if (uses_schur(c, g)) {
     const int ng = (int)c->groups[g].size();
     if (c->dev.n <= 256 && ng <= 4) {       // vectors in registers
-      const int grid = std::min((c->dev.C + 3) / 4, 3 * c->sms);   // 4 warps per CTA, 3 CTAs per SM (168 registers)
+      const int grid = std::min((c->dev.C + 3) / 4, schur_minb(ng <= 2 ? ng : 4) * c->sms);   // 4 warps per CTA
       if (ng == 1) k_prior_schur<1><<<grid, 128, 0, st>>>(dev, a);
       else if (ng == 2) k_prior_schur<2><<<grid, 128, 0, st>>>(dev, a);
       else k_prior_schur<4><<<grid, 128, 0, st>>>(dev, a);

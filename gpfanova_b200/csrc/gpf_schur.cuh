@@ -179,16 +179,172 @@ __device__ __forceinline__ SchurOut schur_eval_reg(const CtxDev& c, int n, int n
   return out;
 }
 
+// ---- staged, square-root-free version (the one the kernels call) ---------------------------------------------------------------------
+// Two changes against schur_eval_reg above, same recursion:
+//  (1) SCALED GENERATOR.  With (u, v) multiplied by the running product of the rotation cosines the rotation needs neither the
+//      square root nor the division by c:   u' = u - rho v,   v' = e v - rho u'   (e = 1 - rho^2; three multiply-adds per position
+//      instead of four).  The pivot of the scaled column is the Schur complement  g_k = L[k][k]^2 = g_{k-1} e_{k-1},  so
+//          rho_k = v[k+1] / g_k,      log det = sum_k log g_k,      L[p][k] w_k = u[p] (r[k] / g_k),     w_k^2 = r[k]^2 / g_k
+//      and the only non-FMA operation left on the loop-carried chain is one reciprocal (1 / e).  Same mixed (stable) downdating
+//      form, up to the diagonal scaling -- checked against 60-digit factorisations next to the normalised recursion
+//      (tools/schur_scaled_probe.py: errors equal within noise).
+//  (2) STAGES.  Column k only has n - k live positions.  A lane owns W consecutive slots; after 16 W steps the lower sixteen
+//      lanes hold nothing live any more, so the upper sixteen lanes' slots are spread over all 32 lanes at W/2 slots per lane
+//      (W shuffles per vector) and the recursion goes on with half the instructions per step: 8 -> 4 -> 2 -> 1 slots per lane,
+//      1376 instead of 2048 vector instructions per vector for n = 256.  n <= 128 / 64 / 32 enter at W = 4 / 2 / 1.
+struct SchurScal {
+  double ginv, prod, quad;   // 1 / g_k, running product of the ginv (exponent split off into e2), sum of w_k^2
+  int e2;
+  bool ok;
+};
+
+// 1/x from the MUFU seed (rel. error r ~ 2^-23) and one third-order step y (1 + r + r^2); x > 0 finite (callers check)
+__device__ __forceinline__ double rcp_nr(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double r = fma(-x, y, 1.0);
+  return fma(y, fma(r, r, r), y);
+}
+
+// steps  base .. base + 16 W - 1  (W == 1: 32 steps) of the recursion; slot p = base + W lane + q is held in register q
+template <int W, int NG>
+__device__ __forceinline__ void schur_stage(int n, int base, int lane, double (&col)[W], double (&v)[W], double (&r)[NG][W],
+                                            SchurScal& sc) {
+  constexpr int NK = (W == 1) ? 32 : 16;
+  constexpr int FR = (W >= 8) ? 1 : 8 / W;      // blocks between two exponent splits of prod (every 8 steps)
+  for (int K = 0; K < NK; ++K) {
+    if (base + W * K >= n || !sc.ok) break;
+#pragma unroll
+    for (int s = 0; s < W; ++s) {
+      const int k = base + W * K + s;
+      // ---- forward substitution with column k (logical slot q of this lane is col[(q - s) mod W]) ----
+#pragma unroll
+      for (int qq = 0; qq < NG; ++qq) {
+        const double rraw = __shfl_sync(FULLMASK, r[qq][s], K);
+        const double rk = (k < n) ? rraw : 0.0;
+        const double wt = rk * sc.ginv;
+        sc.quad = fma(rk, wt, sc.quad);
+#pragma unroll
+        for (int q = 0; q < W; ++q) r[qq][q] = fma(-col[(q - s + W) % W], wt, r[qq][q]);
+      }
+      if (k < n) sc.prod *= sc.ginv;
+      // ---- hyperbolic rotation that produces column k+1 ----
+      const double vk1 = (s < W - 1) ? __shfl_sync(FULLMASK, v[(s + 1) % W], K) : __shfl_sync(FULLMASK, v[0], (K + 1) & 31);
+      const double rho = (k + 1 < n) ? vk1 * sc.ginv : 0.0;
+      const double e = fma(-rho, rho, 1.0);
+      if (!(e > 0.0)) sc.ok = false;
+      sc.ginv *= rcp_nr(sc.ok ? e : 1.0);       // g_{k+1} = g_k e
+      // shift the column down by one slot: only the register holding the lane's last logical slot crosses lanes
+      col[(W - 1 - s + W) % W] = __shfl_up_sync(FULLMASK, col[(W - 1 - s + W) % W], 1);
+#pragma unroll
+      for (int q = 0; q < W; ++q) {
+        const int pc = (q - s - 1 + 2 * W) % W;
+        const double un = fma(-rho, v[q], col[pc]);
+        v[q] = fma(-rho, un, e * v[q]);
+        col[pc] = un;
+      }
+    }
+    if ((K + 1) % FR == 0 || K == NK - 1) {
+      int ex;
+      sc.prod = frexp(sc.prod, &ex);
+      sc.e2 += ex;
+    }
+  }
+}
+
+// the upper sixteen lanes' 16 W slots, re-dealt to all 32 lanes at W/2 slots each
+template <int W>
+__device__ __forceinline__ void schur_repack(const double (&in)[W], double (&out)[W / 2], int lane) {
+  const int src = 16 + (lane >> 1);
+#pragma unroll
+  for (int q = 0; q < W / 2; ++q) {
+    const double lo = __shfl_sync(FULLMASK, in[q], src);
+    const double hi = __shfl_sync(FULLMASK, in[q + W / 2], src);
+    out[q] = (lane & 1) ? hi : lo;
+  }
+}
+
+template <int W, int NG>
+__device__ __forceinline__ void schur_chain(int n, int base, int lane, double (&col)[W], double (&v)[W], double (&r)[NG][W],
+                                            SchurScal& sc) {
+  schur_stage<W, NG>(n, base, lane, col, v, r, sc);
+  if constexpr (W > 1) {
+    if (base + 16 * W < n && sc.ok) {
+      double col2[W / 2], v2[W / 2], r2[NG][W / 2];
+      schur_repack<W>(col, col2, lane);
+      schur_repack<W>(v, v2, lane);
+#pragma unroll
+      for (int qq = 0; qq < NG; ++qq) schur_repack<W>(r[qq], r2[qq], lane);
+      schur_chain<W / 2, NG>(n, base + 16 * W, lane, col2, v2, r2, sc);
+    }
+  }
+}
+
+// lag table, jitter, generator and right-hand sides at W0 slots per lane, then the staged recursion
+template <int W0, int NG>
+__device__ __forceinline__ SchurOut schur_eval_entry(const CtxDev& c, int n, int ng, const int* __restrict__ fns,
+                                                     const double* __restrict__ Fc, double sigma, double ls, int lane) {
+  double col[W0], v[W0], r[NG][W0];
+  const double scl = -0.5 / (ls * ls);
+  double part = 0.0;
+#pragma unroll
+  for (int q = 0; q < W0; ++q) {
+    const int i = lane * W0 + q;
+    const double t = (i < n) ? sigma * exp(c.d2[i] * scl) : 0.0;
+    col[q] = t;
+    if (i < n) part += (i == 0 ? (double)n : 2.0 * (double)(n - i)) * t;
+  }
+  part = warp_sum(part);
+  const double jit = part / ((double)n * (double)n) * c.prior_jitter;   // base.py:222
+  const double t0 = __shfl_sync(FULLMASK, col[0], 0) + jit;
+  SchurOut out{0.0, 0.0, true};
+  if (!(t0 > 0.0) || !(t0 < 1.0e300)) { out.ok = false; return out; }
+#pragma unroll
+  for (int q = 0; q < W0; ++q) {
+    const int i = lane * W0 + q;
+    if (i == 0) col[q] = t0;
+    v[q] = (i == 0) ? 0.0 : col[q];
+  }
+#pragma unroll
+  for (int qq = 0; qq < NG; ++qq)
+#pragma unroll
+    for (int q = 0; q < W0; ++q) {
+      const int i = lane * W0 + q;
+      r[qq][q] = (qq < ng && i < n) ? Fc[(size_t)fns[qq] * n + i] : 0.0;
+    }
+  SchurScal sc{rcp_nr(t0), 1.0, 0.0, 0, true};
+  schur_chain<W0, NG>(n, 0, lane, col, v, r, sc);
+  if (!sc.ok) { out.ok = false; return out; }
+  out.logdet = -(log(sc.prod) + (double)sc.e2 * 0.6931471805599453);
+  out.quad = sc.quad;
+  return out;
+}
+
+template <int NG>
+__device__ __forceinline__ SchurOut schur_eval_staged(const CtxDev& c, int n, int ng, const int* __restrict__ fns,
+                                                      const double* __restrict__ Fc, double sigma, double ls, int lane) {
+  if (n > 128) return schur_eval_entry<8, NG>(c, n, ng, fns, Fc, sigma, ls, lane);
+  if (n > 64) return schur_eval_entry<4, NG>(c, n, ng, fns, Fc, sigma, ls, lane);
+  if (n > 32) return schur_eval_entry<2, NG>(c, n, ng, fns, Fc, sigma, ls, lane);
+  return schur_eval_entry<1, NG>(c, n, ng, fns, Fc, sigma, ls, lane);
+}
+
 // warp-level chain hand-out
 __device__ __forceinline__ int next_chain_warp(int* sched, int lane) {
-  int t = 0;
-  if (lane == 0) t = atomicAdd(sched, 1);
-  return __shfl_sync(FULLMASK, t, 0);
+  unsigned t = 0u;
+  if (lane == 0) t = (unsigned)atomicAdd(sched, 1);
+  return (int)__reduce_max_sync(FULLMASK, t);      // (REDUX writes a uniform register: the chain loop is provably convergent)
 }
 
 // same modes as k_prior (PriorArgs): 0/1 evaluate sigma / lengthscale candidate, 2/3 slice step, 4 fused sigma + ls
+// resident CTAs per SM of the register-resident variants: groups of one or two functions need fewer registers
+#ifndef GPF_SCHUR_MINB_SMALL
+#define GPF_SCHUR_MINB_SMALL 3
+#endif
+__host__ __device__ constexpr int schur_minb(int NG) { return NG == 0 ? 2 : (NG <= 2 ? GPF_SCHUR_MINB_SMALL : 3); }
+
 template <int NG>   // NG > 0: register-resident evaluation (n <= 256, group size <= NG); 0: shared-memory evaluation
-__global__ void __launch_bounds__(NG > 0 ? 128 : NTHR, NG > 0 ? 3 : 2) k_prior_schur(CtxDev c, PriorArgs a) {
+__global__ void __launch_bounds__(NG > 0 ? 128 : NTHR, schur_minb(NG)) k_prior_schur(CtxDev c, PriorArgs a) {
   extern __shared__ __align__(16) double gpf_smem_schur[];
   const int n = c.n, g = a.g, mode = a.mode;
   const int ng = c.group_off[g + 1] - c.group_off[g];
@@ -222,7 +378,13 @@ __global__ void __launch_bounds__(NG > 0 ? 128 : NTHR, NG > 0 ? 3 : 2) k_prior_s
       const bool inb = basef || (l_eval >= lb && l_eval <= ub);   // base.py:224-231: outside the prior -> -inf
       SchurOut o{0.0, 0.0, true};
       if (inb) {
-        if constexpr (NG > 0) o = schur_eval_reg<NG>(c, n, ng, fns, Fc, exp10(s_fact), exp10(l_eval), lane);
+        if constexpr (NG > 0) {
+#ifdef GPF_SCHUR_LEGACY
+          o = schur_eval_reg<NG>(c, n, ng, fns, Fc, exp10(s_fact), exp10(l_eval), lane);
+#else
+          o = schur_eval_staged<NG>(c, n, ng, fns, Fc, exp10(s_fact), exp10(l_eval), lane);
+#endif
+        }
         else o = schur_eval(c, n, ng, fns, Fc, exp10(s_fact), exp10(l_eval), us, v, ev, r, lane);
         ++nfact;
         if (!o.ok) failed = 1;

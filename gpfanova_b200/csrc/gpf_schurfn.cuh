@@ -5,8 +5,8 @@
 //     K_o = K + (offset + jitter) I          and          C = I + c K_o,   c = n_f / (sigma_y + offset),
 // are symmetric positive definite TOEPLITZ matrices, so the Schur algorithm (gpf_schur.cuh) yields the columns of their
 // Cholesky factors one per step with one hyperbolic rotation and O(n) work -- no n x n storage, no n^3.  One WARP does one
-// (prior group, chain) item, every vector register-resident (lane l owns positions 8l .. 8l+7, n <= 256, at most four
-// functions per group):
+// (prior group, chain) item, every vector register-resident (n <= 256, at most four functions per group; the scaled,
+// square-root-free form of the recursion and the staged register layout are those of gpf_schur.cuh):
 //   1. columns of L_B = chol(K_o):  prior draws  f_j = L_B z1_j  accumulate as the columns appear (never stored);
 //   2. right-hand sides  q_j = sqrt(c) (ybar_j - f_j) - z2_j  for every function of the group;
 //   3. per class (functions sharing c): the generalized Schur recursion on the embedding [[C, I], [I, 0]] -- whose
@@ -26,6 +26,7 @@
 namespace gpf {
 
 constexpr int SFN_NG = 4;          // functions per prior group held in registers
+constexpr int SFN_NC = 2;          // right-hand sides per pass of the embedded recursion
 
 struct SchurFnArgs {
   const int* gorder;      // P groups, largest first
@@ -36,309 +37,390 @@ struct SchurFnArgs {
   unsigned sweep;
 };
 
-// first column of  scale * (K + add0 I)  [+ 1 on the diagonal when plus_one]: registers col/v of the Schur generator
-// (lane owns positions 8 lane + q).  Returns 1 / L[0][0], or a NaN-free 0 with ok = false if the pivot is not positive.
-__device__ __forceinline__ double schurfn_init(const CtxDev& c, int n, double sigma, double ls, double scale, double diag_add,
-                                               double (&col)[8], double (&v)[8], int lane, bool& ok) {
+// Register layouts.  The recursion works on two sets of vectors that only meet in the scalars rho, e, 1/g of a step:
+//   * the COLUMN set (column k of L, v, right-hand sides / prior-draw accumulators) is live on positions >= k: it starts at
+//     W0 slots per lane (W0 = 8, 4, 2, 1 for n <= 256, 128, 64, 32) and is re-dealt at half the width whenever its lower
+//     sixteen lanes have died (schur_repack) -- slot p = 32 (W0 - WC) + WC lane + q at width WC;
+//   * the INVERSE set (column k of L^-T, its partner b, the solution accumulators) is live on positions <= k: it starts at
+//     one slot per lane and is spread out to twice the width eight steps before position 32 WA would be touched
+//     (sfn_expand) -- slot p = WA lane + q.
+// Every switch falls on a multiple of 8 steps, where the register renaming of both sets is back at the identity.
+
+// first column of  scale * K + diag_add I  as the (unnormalised) generator; returns 1 / g_0
+template <int W>
+__device__ __forceinline__ double sfn_init(const CtxDev& c, int n, double sigma, double ls, double scale, double diag_add,
+                                           double (&col)[W], double (&v)[W], int lane, bool& ok) {
   const double sc = -0.5 / (ls * ls);
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const int i = lane * 8 + q;
+  for (int q = 0; q < W; ++q) {
+    const int i = lane * W + q;
     col[q] = (i < n) ? scale * sigma * exp(c.d2[i] * sc) : 0.0;
   }
   const double t0 = __shfl_sync(FULLMASK, col[0], 0) + diag_add;
   ok = (t0 > 0.0) && (t0 < 1.0e300);
-  const double uinv = ok ? rsqrt_nr(t0) : 0.0;
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const int i = lane * 8 + q;
-    const double u = ((i == 0) ? t0 : col[q]) * uinv;
-    col[q] = u;
-    v[q] = (i == 0) ? 0.0 : u;
+  for (int q = 0; q < W; ++q) {
+    const int i = lane * W + q;
+    if (i == 0) col[q] = t0;
+    v[q] = (i == 0) ? 0.0 : col[q];
   }
-  return uinv;
+  return ok ? rcp_nr(t0) : 1.0;
 }
 
-// the hyperbolic rotation that turns column k into column k+1 (step s of block K); returns false on breakdown.
-// INV: the same shift + rotation on the inverse-factor rows (a, b): a becomes column k+1 of L^-T.
-template <int s, bool INV>
-__device__ __forceinline__ bool schurfn_rotate(int n, int K, int lane, double (&col)[8], double (&v)[8], double (&a)[8], double (&b)[8],
-                                               double& uinv) {
-  const int k = 8 * K + s;
-  const double vk1 = (s < 7) ? __shfl_sync(FULLMASK, v[(s + 1) & 7], K) : __shfl_sync(FULLMASK, v[0], (K + 1) & 31);
-  const double rho = (k + 1 < n) ? vk1 * uinv : 0.0;
-  const double e = fma(-rho, rho, 1.0);
-  const bool ok = e > 0.0;
-  const double cinv = rsqrt_nr(ok ? e : 1.0);
-  const double cc = e * cinv;
-  uinv *= cinv;                             // L[k+1][k+1] = L[k][k] c
-  // shift the column down by one position: only the register holding logical position 7 crosses lanes
-  col[(7 - s) & 7] = __shfl_up_sync(FULLMASK, col[(7 - s) & 7], 1);
-  if constexpr (INV) {
-    const double up = __shfl_up_sync(FULLMASK, a[(7 - s) & 7], 1);
-    a[(7 - s) & 7] = (lane == 0) ? 0.0 : up;           // position 0 of the shifted column is an exact zero
-  }
+// steps k0 .. k1-1 (multiples of max(WC, WA)); op.column(s, k, Kc, col, a, ginv) sees every column before it is rotated away.
+// INV: the same shift + rotation on the inverse set (a, b): a becomes column k+1 of L^-T (times the common scale).
+template <int WC, int WA, bool INV, class Op>
+__device__ __forceinline__ void sfn_segment(int n, int k0, int k1, int baseC, int lane, double (&col)[WC], double (&v)[WC],
+                                            double (&a)[WA], double (&b)[WA], double& ginv, bool& ok, Op& op) {
+  constexpr int U = (WC > WA) ? WC : WA;
+  for (int kb = k0; kb < k1; kb += U) {
+    if (!ok) break;
+    const int Kc0 = (kb - baseC) / WC;
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const int pc = (q - s - 1) & 7;
-    const double un = (col[pc] - rho * v[q]) * cinv;
-    v[q] = fma(cc, v[q], -rho * un);
-    col[pc] = un;
-    if constexpr (INV) {
-      const double an = (a[pc] - rho * b[q]) * cinv;
-      b[q] = fma(cc, b[q], -rho * an);
-      a[pc] = an;
+    for (int s = 0; s < U; ++s) {
+      const int k = kb + s, Kc = Kc0 + s / WC;
+      const int sC = s % WC, sA = s % WA;
+      op.column(s, k, Kc, col, a, ginv);
+      const double vk1 = (sC < WC - 1) ? __shfl_sync(FULLMASK, v[(sC + 1) % WC], Kc) : __shfl_sync(FULLMASK, v[0], (Kc + 1) & 31);
+      const double rho = (k + 1 < n) ? vk1 * ginv : 0.0;
+      const double e = fma(-rho, rho, 1.0);
+      if (!(e > 0.0)) ok = false;
+      ginv *= rcp_nr(ok ? e : 1.0);             // g_{k+1} = g_k e
+      col[(2 * WC - 1 - sC) % WC] = __shfl_up_sync(FULLMASK, col[(2 * WC - 1 - sC) % WC], 1);
+#pragma unroll
+      for (int q = 0; q < WC; ++q) {
+        const int pc = (q - sC - 1 + 2 * WC) % WC;
+        const double un = fma(-rho, v[q], col[pc]);
+        v[q] = fma(-rho, un, e * v[q]);
+        col[pc] = un;
+      }
+      if constexpr (INV) {
+        const double up = __shfl_up_sync(FULLMASK, a[(2 * WA - 1 - sA) % WA], 1);
+        a[(2 * WA - 1 - sA) % WA] = (lane == 0) ? 0.0 : up;       // position 0 of the shifted column is an exact zero
+#pragma unroll
+        for (int q = 0; q < WA; ++q) {
+          const int pa = (q - sA - 1 + 2 * WA) % WA;
+          const double an = fma(-rho, b[q], a[pa]);
+          b[q] = fma(-rho, an, e * b[q]);
+          a[pa] = an;
+        }
+      }
     }
   }
-  return ok;
 }
 
-template <int s, bool INV, class Op>
-__device__ __forceinline__ bool schurfn_block_step(int n, int K, int lane, double (&col)[8], double (&v)[8], double (&a)[8],
-                                                   double (&b)[8], double& uinv, Op& op) {
-  op.template column<s>(K, col, a, uinv);   // column k = 8K + s: logical position q of this lane is col[(q - s) & 7] (a likewise)
-  return schurfn_rotate<s, INV>(n, K, lane, col, v, a, b, uinv);
-}
-
-// run the recursion over all columns; op.column<s>(K, col, a, uinv) sees every column before it is rotated away
-template <bool INV, class Op>
-__device__ __forceinline__ bool schurfn_run(int n, int lane, double (&col)[8], double (&v)[8], double (&a)[8], double (&b)[8], double uinv,
-                                            Op& op) {
-  bool ok = true;
-  const int nblk = (n + 7) >> 3;
-  for (int K = 0; K < nblk && ok; ++K) {
-    ok = schurfn_block_step<0, INV>(n, K, lane, col, v, a, b, uinv, op) && ok;
-    ok = schurfn_block_step<1, INV>(n, K, lane, col, v, a, b, uinv, op) && ok;
-    ok = schurfn_block_step<2, INV>(n, K, lane, col, v, a, b, uinv, op) && ok;
-    ok = schurfn_block_step<3, INV>(n, K, lane, col, v, a, b, uinv, op) && ok;
-    ok = schurfn_block_step<4, INV>(n, K, lane, col, v, a, b, uinv, op) && ok;
-    ok = schurfn_block_step<5, INV>(n, K, lane, col, v, a, b, uinv, op) && ok;
-    ok = schurfn_block_step<6, INV>(n, K, lane, col, v, a, b, uinv, op) && ok;
-    ok = schurfn_block_step<7, INV>(n, K, lane, col, v, a, b, uinv, op) && ok;
+// the inverse set at twice the width: lanes 0..15 take over the slots of two old lanes each, lanes 16..31 start at zero
+template <int W>
+__device__ __forceinline__ void sfn_expand(const double (&in)[W], double (&out)[2 * W], int lane) {
+#pragma unroll
+  for (int q = 0; q < 2 * W; ++q) {
+    const double val = __shfl_sync(FULLMASK, in[q % W], (2 * lane + (q >= W ? 1 : 0)) & 31);
+    out[q] = (lane < 16) ? val : 0.0;
   }
-  return ok;
 }
 
-// f_j += L[:, k] z1_j[k]   (positions above the diagonal of the column hold dead values: masked); z1 in shared memory
+// f_j += L[:, k] z1_j[k]  with L[p][k] = u[p] / sqrt(g_k)  (positions above the diagonal of the column hold dead values:
+// masked); z1 in shared memory
+template <int WC>
 struct OpPriorDraw {
-  int n, nld, lane, ng;
+  int ng, nld, lane;
   const double* zs;               // ng x nld
-  double (&f)[SFN_NG][8];
-  template <int s>
-  __device__ __forceinline__ void column(int K, const double (&col)[8], const double (&)[8], double) {
-    const int k = 8 * K + s;
+  double (&f)[SFN_NG][WC];
+  __device__ __forceinline__ void column(int s, int k, int Kc, const double (&col)[WC], const double (&)[1], double ginv) {
+    const int sC = s % WC;
+    const double su = ginv * rsqrt_nr(ginv);      // 1 / L[k][k]
 #pragma unroll
     for (int j = 0; j < SFN_NG; ++j) {
       if (j < ng) {
-        const double zk = zs[j * nld + k];
+        const double zk = zs[j * nld + k] * su;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const bool live = (q >= s) ? (lane >= K) : (lane > K);
-          if (live) f[j][q] = fma(col[(q - s) & 7], zk, f[j][q]);
+        for (int q = 0; q < WC; ++q) {
+          const bool live = (q >= sC) ? (lane >= Kc) : (lane > Kc);
+          if (live) f[j][q] = fma(col[(q - sC + WC) % WC], zk, f[j][q]);
         }
       }
     }
   }
 };
 
-// one column of the solve  v = C^-1 q  for up to SFN_NC right-hand sides: y_k = r_k / L[k][k], r -= L[:, k] y_k,
-// v += L^-T[:, k] y_k   (L^-T[:, k] is exactly zero below position k: no masking needed)
-constexpr int SFN_NC = 2;
+// one column of the solve  v = C^-1 q  for up to SFN_NC right-hand sides:  wt = r_k / g_k,  r -= u wt,  v += a wt
+// (a = column k of L^-T times the scale of u; it is exactly zero below position k: no masking needed)
+template <int WC, int WA>
 struct OpSolve {
   int n, nm;                      // time points, right-hand sides in this pass
-  double (&r)[SFN_NC][8];
-  double (&vo)[SFN_NC][8];
-  template <int s>
-  __device__ __forceinline__ void column(int K, const double (&col)[8], const double (&a)[8], double uinv) {
-    const int k = 8 * K + s;
+  double (&r)[SFN_NC][WC];
+  double (&vo)[SFN_NC][WA];
+  __device__ __forceinline__ void column(int s, int k, int Kc, const double (&col)[WC], const double (&a)[WA], double ginv) {
+    const int sC = s % WC, sA = s % WA;
 #pragma unroll
     for (int j = 0; j < SFN_NC; ++j) {
       if (j < nm) {
-        const double w = (k < n) ? __shfl_sync(FULLMASK, r[j][s], K) * uinv : 0.0;
+        const double rraw = __shfl_sync(FULLMASK, r[j][sC], Kc);
+        const double wt = (k < n) ? rraw * ginv : 0.0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          r[j][q] = fma(-col[(q - s) & 7], w, r[j][q]);
-          vo[j][q] = fma(a[(q - s) & 7], w, vo[j][q]);
-        }
+        for (int q = 0; q < WC; ++q) r[j][q] = fma(-col[(q - sC + WC) % WC], wt, r[j][q]);
+#pragma unroll
+        for (int q = 0; q < WA; ++q) vo[j][q] = fma(a[(q - sA + WA) % WA], wt, vo[j][q]);
       }
     }
   }
 };
 
-__device__ __forceinline__ void sfn_normals8(const Stream& rng, unsigned gch, unsigned sweep, unsigned sid, int e0, int n_valid_from,
-                                             int n_valid_to, int lane, double (&out)[8]) {
-  // elements e0 + 8 lane + q of the function's normal vector; valid element range [n_valid_from, n_valid_to)
+// prior draws: the column set through its stages; finished positions of f (below the current column) are parked in the
+// shared-memory rows of z1 they no longer need
+template <int W0, int WC>
+__device__ __forceinline__ void sfn_prior_chain(int n, int n8, int lane, double (&col)[WC], double (&v)[WC], double (&f)[SFN_NG][WC],
+                                                double& ginv, bool& ok, int ng, int nld, double* zs) {
+  constexpr int baseC = 32 * (W0 - WC);
+  constexpr int K1 = (WC > 1) ? baseC + 16 * WC : 32 * W0;
+  double da[1] = {0.0}, db[1] = {0.0};
+  OpPriorDraw<WC> op{ng, nld, lane, zs, f};
+  sfn_segment<WC, 1, false>(n, baseC, (K1 < n8) ? K1 : n8, baseC, lane, col, v, da, db, ginv, ok, op);
+  if constexpr (WC > 1) {
+    if (K1 < n8 && ok) {
+      __syncwarp();
+      if (lane < 16) {
 #pragma unroll
-  for (int q = 0; q < 8; ++q) out[q] = 0.0;
-  const int base = e0 + 8 * lane;
+        for (int j = 0; j < SFN_NG; ++j)
+          if (j < ng) {
+#pragma unroll
+            for (int q = 0; q < WC; ++q) zs[j * nld + baseC + WC * lane + q] = f[j][q];
+          }
+      }
+      double col2[WC / 2], v2[WC / 2], f2[SFN_NG][WC / 2];
+      schur_repack<WC>(col, col2, lane);
+      schur_repack<WC>(v, v2, lane);
+#pragma unroll
+      for (int j = 0; j < SFN_NG; ++j) schur_repack<WC>(f[j], f2[j], lane);
+      sfn_prior_chain<W0, WC / 2>(n, n8, lane, col2, v2, f2, ginv, ok, ng, nld, zs);
+      return;
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < SFN_NG; ++j)
+    if (j < ng) {
+#pragma unroll
+      for (int q = 0; q < WC; ++q) {
+        const int p = baseC + WC * lane + q;
+        if (p < nld) zs[j * nld + p] = f[j][q];
+      }
+    }
+}
+
+// the embedded recursion through the stages of both sets (compile-time schedule: K0 = first step of this segment)
+template <int W0, int WC, int WA, int K0>
+__device__ __forceinline__ void sfn_solve_chain(int n, int n8, int lane, double (&col)[WC], double (&v)[WC], double (&a)[WA], double (&b)[WA],
+                                                double (&rq)[SFN_NC][WC], double (&vo)[SFN_NC][WA], double& ginv, bool& ok, int nm,
+                                                double (&vout)[SFN_NC][W0]) {
+  constexpr int baseC = 32 * (W0 - WC);
+  constexpr int kc = (WC > 1) ? baseC + 16 * WC : (1 << 30);      // the column set is re-dealt here
+  constexpr int ka = (WA < W0) ? 32 * WA - 8 : (1 << 30);         // the inverse set is spread out here
+  constexpr int kx = (kc < ka) ? kc : ka;
+  constexpr int K1 = (kx < 32 * W0) ? kx : 32 * W0;
+  {
+    OpSolve<WC, WA> op{n, nm, rq, vo};
+    sfn_segment<WC, WA, true>(n, K0, (K1 < n8) ? K1 : n8, baseC, lane, col, v, a, b, ginv, ok, op);
+  }
+  if constexpr (K1 < 32 * W0) {
+    if (K1 < n8 && ok) {
+      if constexpr (ka < kc) {
+        double a2[2 * WA], b2[2 * WA], vo2[SFN_NC][2 * WA];
+        sfn_expand<WA>(a, a2, lane);
+        sfn_expand<WA>(b, b2, lane);
+#pragma unroll
+        for (int j = 0; j < SFN_NC; ++j) sfn_expand<WA>(vo[j], vo2[j], lane);
+        sfn_solve_chain<W0, WC, 2 * WA, K1>(n, n8, lane, col, v, a2, b2, rq, vo2, ginv, ok, nm, vout);
+      } else {
+        double col2[WC / 2], v2[WC / 2], rq2[SFN_NC][WC / 2];
+        schur_repack<WC>(col, col2, lane);
+        schur_repack<WC>(v, v2, lane);
+#pragma unroll
+        for (int j = 0; j < SFN_NC; ++j) schur_repack<WC>(rq[j], rq2[j], lane);
+        sfn_solve_chain<W0, WC / 2, WA, K1>(n, n8, lane, col2, v2, a, b, rq2, vo, ginv, ok, nm, vout);
+      }
+      return;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < SFN_NC; ++j)
+#pragma unroll
+    for (int q = 0; q < W0; ++q) {
+      if constexpr (WA == W0) vout[j][q] = vo[j][q];
+      else vout[j][q] = 0.0;                      // only reached after a breakdown (n > 16 W0 otherwise passes every expansion)
+    }
+}
+
+// elements e0 + W lane + q of a function's normal vector, valid below n_valid_to
+template <int W>
+__device__ __forceinline__ void sfn_normals(const Stream& rng, unsigned gch, unsigned sweep, unsigned sid, int e0, int n_valid_to, int lane,
+                                            double (&out)[W]) {
+#pragma unroll
+  for (int q = 0; q < W; ++q) out[q] = 0.0;
+  const int base = e0 + W * lane;
   if (base >= n_valid_to) return;
-  if ((base & 1) == 0) {
+  if (W > 1 && (base & 1) == 0) {
 #pragma unroll
-    for (int q = 0; q < 8; q += 2) {
+    for (int q = 0; q < W; q += 2) {
       const int e = base + q;
       if (e < n_valid_to) {
         double za, zb;
         rng.normal_pair(gch, sweep, sid, (unsigned)(e >> 1), za, zb);
         out[q] = za;
-        if (e + 1 < n_valid_to) out[q + 1] = zb;
+        if (q + 1 < W && e + 1 < n_valid_to) out[q + 1] = zb;
       }
     }
   } else {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < W; ++q) {
       const int e = base + q;
       if (e < n_valid_to) out[q] = normal_elem(rng, gch, sweep, sid, e);
     }
   }
-  (void)n_valid_from;
+}
+
+// one (prior group, chain) item at W0 slots per lane
+template <int W0>
+__device__ __forceinline__ void sfn_item(const CtxDev& c, const SchurFnArgs& a, const Stream& rng, int ch, int g, int lane, double* zs) {
+  const int n = c.n, nld = ((n + 7) >> 3) << 3;
+  const unsigned gch = (unsigned)(ch + c.chain_offset);
+  const double sigma = exp10(c.hyper[(size_t)ch * c.H + 1 + 2 * g]);
+  const double ls = exp10(c.hyper[(size_t)ch * c.H + 2 + 2 * g]);
+  const double yinv = 1.0 / (exp10(c.hyper[(size_t)ch * c.H]) + c.offset);
+  const int f0 = c.group_off[g], ng = c.group_off[g + 1] - f0;          // functions of the group: group_fns[f0 .. f0+ng)
+  const int* gf = c.group_fns + f0;
+  // sampler id of every function of the group (from the class lists) and its class's c
+  unsigned sid[SFN_NG];
+  double ccls[SFN_NG];
+#pragma unroll
+  for (int j = 0; j < SFN_NG; ++j) { sid[j] = 0u; ccls[j] = 1.0; }
+  for (int cls = a.gcls_off[g]; cls < a.gcls_off[g + 1]; ++cls)
+    for (int t = a.cls_off[cls]; t < a.cls_off[cls + 1]; ++t) {
+      const int fn = a.cls_fn[t];
+#pragma unroll
+      for (int j = 0; j < SFN_NG; ++j)
+        if (j < ng && gf[j] == fn) { sid[j] = a.cls_sid[t]; ccls[j] = c.G[(size_t)fn * c.f + fn] * yinv; }
+    }
+  // ---------------- 1. prior draws through the columns of chol(K_o), jitter ladder on breakdown ----------------
+  int tries = 0, code = 0;
+  double jitter = 0.0;
+  for (;;) {
+    __syncwarp();
+    for (int j = 0; j < ng; ++j) {                 // z1 (regenerated on a retry: finished draws overwrite it)
+      double z[W0];
+      sfn_normals<W0>(rng, gch, a.sweep, sid[j], 0, n, lane, z);
+#pragma unroll
+      for (int q = 0; q < W0; ++q)
+        if (W0 * lane + q < nld) zs[j * nld + W0 * lane + q] = z[q];
+    }
+    __syncwarp();
+    double col[W0], v[W0], f[SFN_NG][W0];
+    bool ok;
+    double ginv = sfn_init<W0>(c, n, sigma, ls, 1.0, c.offset + jitter, col, v, lane, ok);
+#pragma unroll
+    for (int j = 0; j < SFN_NG; ++j)
+#pragma unroll
+      for (int q = 0; q < W0; ++q) f[j][q] = 0.0;
+    if (ok) sfn_prior_chain<W0, W0>(n, nld, lane, col, v, f, ginv, ok, ng, nld, zs);
+    if (ok) { code = tries; break; }
+    const double dm = sigma + c.offset;                // jitchol ladder (linalg.py:41-54)
+    if (tries == 0) {
+      if (!(dm > 0.0)) { code = GPF_STATUS_NONPOS_DIAG; break; }
+      jitter = dm * 1e-6;
+    } else jitter *= 10.0;
+    ++tries;
+    if (tries > c.maxtries || !isfinite(jitter)) { code = GPF_STATUS_NOT_PD; break; }
+  }
+  int nfact = 0, ndraw = 0;
+  if (code >= 0) {
+    // ---------------- 2. q_j = sqrt(c_j) (ybar_j - f_j) - z2_j, parked in shared memory ----------------
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < SFN_NG; ++j)
+      if (j < ng) {
+        double z2[W0];
+        sfn_normals<W0>(rng, gch, a.sweep, sid[j], n, 2 * n, lane, z2);
+        const double* yb = c.bhat + (size_t)gf[j] * n;
+        const double sc = sqrt(ccls[j]);
+#pragma unroll
+        for (int q = 0; q < W0; ++q) {
+          const int i = W0 * lane + q;
+          if (i < nld) zs[j * nld + i] = (i < n) ? sc * (yb[i] - zs[j * nld + i]) - z2[q] : 0.0;
+        }
+      }
+    __syncwarp();
+    // ---------------- 3. per class, two functions per pass: v = C^-1 q by the embedded recursion ----------------
+    for (int cls = a.gcls_off[g]; cls < a.gcls_off[g + 1] && code >= 0; ++cls) {
+      int mem[SFN_NG], nmem = 0;
+      double cc = 1.0;
+      for (int t = a.cls_off[cls]; t < a.cls_off[cls + 1]; ++t) {
+        const int fn = a.cls_fn[t];
+#pragma unroll
+        for (int j = 0; j < SFN_NG; ++j)
+          if (j < ng && gf[j] == fn) { mem[nmem++] = j; cc = ccls[j]; }
+      }
+      const double isc = 1.0 / sqrt(cc);
+      for (int m0 = 0; m0 < nmem; m0 += SFN_NC) {
+        const int nm = (nmem - m0 < SFN_NC) ? nmem - m0 : SFN_NC;
+        double rq[SFN_NC][W0], vo[SFN_NC][1], vout[SFN_NC][W0];
+#pragma unroll
+        for (int j = 0; j < SFN_NC; ++j) {
+#pragma unroll
+          for (int q = 0; q < W0; ++q) rq[j][q] = (j < nm && W0 * lane + q < nld) ? zs[mem[m0 + j] * nld + W0 * lane + q] : 0.0;
+          vo[j][0] = 0.0;
+        }
+        double col[W0], v[W0], ia[1], ib[1];
+        bool ok;
+        double ginv = sfn_init<W0>(c, n, sigma, ls, cc, 1.0 + cc * (c.offset + jitter), col, v, lane, ok);
+        ia[0] = ib[0] = (lane == 0) ? 1.0 : 0.0;          // generator rows [e0 e0] (times the scale sqrt(t0) of the column set)
+        if (ok) sfn_solve_chain<W0, W0, 1, 0>(n, nld, lane, col, v, ia, ib, rq, vo, ginv, ok, nm, vout);
+        ++nfact;
+        if (!ok) { code = GPF_STATUS_NOT_PD; break; }
+        // ---------------- 4. beta_j = ybar_j - (z2_j + v_j) / sqrt(c) ----------------
+#pragma unroll
+        for (int j = 0; j < SFN_NC; ++j)
+          if (j < nm) {
+            const int gj = mem[m0 + j];
+            double z2[W0];
+            sfn_normals<W0>(rng, gch, a.sweep, sid[gj], n, 2 * n, lane, z2);
+            const double* yb = c.bhat + (size_t)gf[gj] * n;
+            double* Fo = c.F + ((size_t)ch * c.f + gf[gj]) * n;
+#pragma unroll
+            for (int q = 0; q < W0; ++q) {
+              const int i = W0 * lane + q;
+              if (i < n) Fo[i] = yb[i] - (z2[q] + vout[j][q]) * isc;
+            }
+          }
+        ndraw += nm;
+      }
+    }
+  }
+  if (lane == 0) {
+    status_merge(c.status + ch, code);
+    atomicAdd(c.counters + CNT_CHOL, 1ull + (unsigned long long)tries + (unsigned long long)nfact);
+    atomicAdd(c.counters + CNT_BFACT, 1ull + (unsigned long long)tries);
+    atomicAdd(c.counters + CNT_FNCHOL, (unsigned long long)nfact);
+    atomicAdd(c.counters + CNT_DRAW, (unsigned long long)ndraw);
+    if (tries) atomicAdd(c.counters + CNT_JITTER, (unsigned long long)tries);
+  }
+  __syncwarp();
 }
 
 #ifndef GPF_SFN_MINB
 #define GPF_SFN_MINB 3
 #endif
 __global__ void __launch_bounds__(128, GPF_SFN_MINB) k_group_schurfn(CtxDev c, SchurFnArgs a) {
-  extern __shared__ __align__(16) double gpf_smem_sfn[];      // per warp: SFN_NG x nld (z1 of the group's functions, then their q)
+  extern __shared__ __align__(16) double gpf_smem_sfn[];      // per warp: SFN_NG x nld (z1 / finished prior draws, then the right-hand sides q)
   const int n = c.n, nld = ((n + 7) >> 3) << 3;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Stream rng{c.k0, c.k1};
   double* zs = gpf_smem_sfn + (size_t)warp * (SFN_NG * nld);
   for (int item = next_chain_warp(c.sched, lane); item < c.C * c.P; item = next_chain_warp(c.sched, lane)) {
     const int ch = item % c.C, g = a.gorder[item / c.C];
-    const unsigned gch = (unsigned)(ch + c.chain_offset);
-    const double sigma = exp10(c.hyper[(size_t)ch * c.H + 1 + 2 * g]);
-    const double ls = exp10(c.hyper[(size_t)ch * c.H + 2 + 2 * g]);
-    const double yinv = 1.0 / (exp10(c.hyper[(size_t)ch * c.H]) + c.offset);
-    const int f0 = c.group_off[g], ng = c.group_off[g + 1] - f0;          // functions of the group: group_fns[f0 .. f0+ng)
-    const int* gf = c.group_fns + f0;
-    // sampler id of every function of the group (from the class lists) and its class's c
-    unsigned sid[SFN_NG];
-    double ccls[SFN_NG];
-#pragma unroll
-    for (int j = 0; j < SFN_NG; ++j) { sid[j] = 0u; ccls[j] = 1.0; }
-    for (int cls = a.gcls_off[g]; cls < a.gcls_off[g + 1]; ++cls)
-      for (int t = a.cls_off[cls]; t < a.cls_off[cls + 1]; ++t) {
-        const int fn = a.cls_fn[t];
-#pragma unroll
-        for (int j = 0; j < SFN_NG; ++j)
-          if (j < ng && gf[j] == fn) { sid[j] = a.cls_sid[t]; ccls[j] = c.G[(size_t)fn * c.f + fn] * yinv; }
-      }
-    // ---------------- 1. prior draws through the columns of chol(K_o), jitter ladder on breakdown ----------------
-    double r[SFN_NG][8];           // f, then q, then y, then v
-    int tries = 0, code = 0;
-    double jitter = 0.0;
-    {
-      __syncwarp();
-      for (int j = 0; j < ng; ++j) {
-        double z[8];
-        sfn_normals8(rng, gch, a.sweep, sid[j], 0, 0, n, lane, z);
-        if (8 * lane < nld) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) zs[j * nld + 8 * lane + q] = z[q];
-        }
-      }
-      __syncwarp();
-      for (;;) {
-        double col[8], v[8], da[8], db[8];      // (da, db unused without the inverse factor)
-        bool ok;
-        double uinv = schurfn_init(c, n, sigma, ls, 1.0, c.offset + jitter, col, v, lane, ok);
-#pragma unroll
-        for (int j = 0; j < SFN_NG; ++j)
-#pragma unroll
-          for (int q = 0; q < 8; ++q) r[j][q] = 0.0;
-        if (ok) {
-          OpPriorDraw op{n, nld, lane, ng, zs, r};
-          ok = schurfn_run<false>(n, lane, col, v, da, db, uinv, op);
-        }
-        if (ok) { code = tries; break; }
-        const double dm = sigma + c.offset;                // jitchol ladder (linalg.py:41-54)
-        if (tries == 0) {
-          if (!(dm > 0.0)) { code = GPF_STATUS_NONPOS_DIAG; break; }
-          jitter = dm * 1e-6;
-        } else jitter *= 10.0;
-        ++tries;
-        if (tries > c.maxtries || !isfinite(jitter)) { code = GPF_STATUS_NOT_PD; break; }
-      }
-    }
-    int nfact = 0, ndraw = 0;
-    if (code >= 0) {
-      // ---------------- 2. q_j = sqrt(c_j) (ybar_j - f_j) - z2_j, parked in shared memory ----------------
-      __syncwarp();
-#pragma unroll
-      for (int j = 0; j < SFN_NG; ++j)
-        if (j < ng) {
-          double z2[8];
-          sfn_normals8(rng, gch, a.sweep, sid[j], n, n, 2 * n, lane, z2);
-          const double* yb = c.bhat + (size_t)gf[j] * n;
-          const double sc = sqrt(ccls[j]);
-          if (8 * lane < nld) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int i = 8 * lane + q;
-              zs[j * nld + i] = (i < n) ? sc * (yb[i] - r[j][q]) - z2[q] : 0.0;
-            }
-          }
-        }
-      __syncwarp();
-      // ---------------- 3. per class, two functions per pass: v = C^-1 q by the embedded recursion ----------------
-      for (int cls = a.gcls_off[g]; cls < a.gcls_off[g + 1] && code >= 0; ++cls) {
-        int mem[SFN_NG], nmem = 0;
-        double cc = 1.0;
-        for (int t = a.cls_off[cls]; t < a.cls_off[cls + 1]; ++t) {
-          const int fn = a.cls_fn[t];
-#pragma unroll
-          for (int j = 0; j < SFN_NG; ++j)
-            if (j < ng && gf[j] == fn) { mem[nmem++] = j; cc = ccls[j]; }
-        }
-        const double isc = 1.0 / sqrt(cc);
-        for (int m0 = 0; m0 < nmem; m0 += SFN_NC) {
-          const int nm = (nmem - m0 < SFN_NC) ? nmem - m0 : SFN_NC;
-          double rq[SFN_NC][8], vo[SFN_NC][8];
-#pragma unroll
-          for (int j = 0; j < SFN_NC; ++j)
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              rq[j][q] = (j < nm && 8 * lane < nld) ? zs[mem[m0 + j] * nld + 8 * lane + q] : 0.0;
-              vo[j][q] = 0.0;
-            }
-          double col[8], v[8], ia[8], ib[8];
-          bool ok;
-          double uinv = schurfn_init(c, n, sigma, ls, cc, 1.0 + cc * (c.offset + jitter), col, v, lane, ok);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) ia[q] = ib[q] = (lane == 0 && q == 0) ? uinv : 0.0;      // generator rows [e0 e0] / sqrt(t0)
-          if (ok) {
-            OpSolve op{n, nm, rq, vo};
-            ok = schurfn_run<true>(n, lane, col, v, ia, ib, uinv, op);
-          }
-          ++nfact;
-          if (!ok) { code = GPF_STATUS_NOT_PD; break; }
-          // ---------------- 4. beta_j = ybar_j - (z2_j + v_j) / sqrt(c) ----------------
-#pragma unroll
-          for (int j = 0; j < SFN_NC; ++j)
-            if (j < nm) {
-              const int gj = mem[m0 + j];
-              double z2[8];
-              sfn_normals8(rng, gch, a.sweep, sid[gj], n, n, 2 * n, lane, z2);
-              const double* yb = c.bhat + (size_t)gf[gj] * n;
-              double* Fo = c.F + ((size_t)ch * c.f + gf[gj]) * n;
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const int i = 8 * lane + q;
-                if (i < n) Fo[i] = yb[i] - (z2[q] + vo[j][q]) * isc;
-              }
-            }
-          ndraw += nm;
-        }
-      }
-    }
-    if (lane == 0) {
-      status_merge(c.status + ch, code);
-      atomicAdd(c.counters + CNT_CHOL, 1ull + (unsigned long long)tries + (unsigned long long)nfact);
-      atomicAdd(c.counters + CNT_BFACT, 1ull + (unsigned long long)tries);
-      atomicAdd(c.counters + CNT_FNCHOL, (unsigned long long)nfact);
-      atomicAdd(c.counters + CNT_DRAW, (unsigned long long)ndraw);
-      if (tries) atomicAdd(c.counters + CNT_JITTER, (unsigned long long)tries);
-    }
-    __syncwarp();
+    if (n > 128) sfn_item<8>(c, a, rng, ch, g, lane, zs);
+    else if (n > 64) sfn_item<4>(c, a, rng, ch, g, lane, zs);
+    else if (n > 32) sfn_item<2>(c, a, rng, ch, g, lane, zs);
+    else sfn_item<1>(c, a, rng, ch, g, lane, zs);
   }
 }
 

@@ -303,7 +303,14 @@ def function_interval(samples, alpha=.95, start=1e-6, tol=1e-6, maxiter=100, dev
 # ----------------------------------------------------------------------------------------------
 # sampler context
 # ----------------------------------------------------------------------------------------------
-_COPY_THREADS = max(1, int(os.environ.get("GPFANOVA_B200_COPY_THREADS", str(min(8, max(2, (os.cpu_count() or 4) // 2))))))
+def _host_threads():
+    """threads this process may use for host copies / page touching: half the cores, shared by the ranks of the box"""
+    local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    return max(1, min(8, (os.cpu_count() or 4) // (2 * local_world)))
+
+
+_COPY_THREADS = max(1, int(os.environ.get("GPFANOVA_B200_COPY_THREADS", str(max(2, _host_threads())))))
+_TOUCH_THREADS = max(1, int(os.environ.get("GPFANOVA_B200_TOUCH_THREADS", str(_host_threads()))))
 _POOL = None
 
 
@@ -319,11 +326,11 @@ _PREFAULT = None
 
 
 def _prefault_pool():
-    """page-touching threads (one per concurrently sampling engine: EngineGroup runs one sweep_host per device)"""
+    """page-touching threads (shared by the engines of an EngineGroup, which run one sweep_host per device)"""
     global _PREFAULT
     if _PREFAULT is None:
         from concurrent.futures import ThreadPoolExecutor
-        _PREFAULT = ThreadPoolExecutor(max_workers=8)
+        _PREFAULT = ThreadPoolExecutor(max_workers=max(8, _TOUCH_THREADS))
     return _PREFAULT
 
 
@@ -571,24 +578,29 @@ class ChainEngine(object):
             self._dev_hist = [torch.empty((cap, self.C, cols), dtype=torch.float64, device=self.dev) for _ in range(2)]
         t_begin = time.perf_counter()
         out = np.empty((rows_total, self.C, cols))
-        # Fresh pageable memory: the first write to every 4 KB page faults (~2 GB/s per thread).  A background thread
-        # touches the pages in drain order while the GPU runs the first sweeps; `touched` is the number of doubles it has
-        # passed.  A drain never writes a region the toucher has not finished with (it waits for `touched` to pass the end
-        # of its region), so the toucher's zeros can never land on copied data, and it is joined before the array is
+        # Fresh pageable memory: the first write to every 4 KB page faults (~2 GB/s for ONE thread, but the faults of
+        # several threads run side by side: 26 GB/s with eight, tools/pagefault_probe.py).  Background threads touch the
+        # pages in drain order (thread j takes blocks j, j + T, j + 2T, ...) while the GPU runs the first sweeps;
+        # `touched()` is the length of the prefix every thread has passed.  A drain never writes a region the touchers
+        # have not finished with, so their zeros can never land on copied data, and they are joined before the array is
         # returned.
-        touched = [out.size]
-        toucher = None
+        touchers = []
+        touched = lambda: out.size
         if out.nbytes >= (64 << 20):
             flat = out.reshape(-1)
-            blk = 2 << 20                                      # doubles per block (16 MB), in drain order
-            touched[0] = 0
+            blk = 1 << 20                                      # doubles per block (8 MB), in drain order
+            nblk = -(-flat.size // blk)
+            nthr = min(_TOUCH_THREADS, nblk)
+            prog = [0] * nthr                                  # blocks finished by each thread
 
-            def prefault():
-                for a in range(0, flat.size, blk):
-                    flat[a:a + blk:512] = 0.0
-                    touched[0] = min(flat.size, a + blk)
-                touched[0] = flat.size
-            toucher = _prefault_pool().submit(prefault)
+            def prefault(j):
+                for bidx in range(j, nblk, nthr):
+                    flat[bidx * blk:(bidx + 1) * blk:512] = 0.0
+                    prog[j] += 1
+
+            def touched():
+                return min(flat.size, min(prog[j] * nthr + j for j in range(nthr)) * blk)
+            touchers = [_prefault_pool().submit(prefault, j) for j in range(nthr)]
         pending = []                                           # (buffer index, first row, rows)
         done, row0, i = 0, 0, 0
 
@@ -606,7 +618,7 @@ class ChainEngine(object):
 
         def _drain_copy(b, r0, nr):
             end = (r0 + nr) * self.C * cols
-            while touched[0] < end:                            # the page toucher is still inside this region
+            while touched() < end:                             # the page touchers are still inside this region
                 time.sleep(0.0002)
             dst = out[r0:r0 + nr].reshape(-1)
             src = self._stage[b].numpy()[:nr].reshape(-1)
@@ -640,8 +652,8 @@ class ChainEngine(object):
                 on_chunk(done)
         while pending:
             drain()
-        if toucher is not None:
-            toucher.result()                                   # never leave a writer behind the returned array
+        for t in touchers:
+            t.result()                                         # never leave a writer behind the returned array
         self.sync()
         if tm is not None:
             sys.stderr.write("sweep_host: rows %d chunk rows %d  event wait %.3f s  copy %.3f s  total %.3f s\n" % (
