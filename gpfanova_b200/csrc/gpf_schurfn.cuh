@@ -121,23 +121,21 @@ __device__ __forceinline__ void sfn_expand(const double (&in)[W], double (&out)[
 
 // f_j += L[:, k] z1_j[k]  with L[p][k] = u[p] / sqrt(g_k)  (positions above the diagonal of the column hold dead values:
 // masked); z1 in shared memory
-template <int WC>
+template <int WC, int NGT>
 struct OpPriorDraw {
-  int ng, nld, lane;
-  const double* zs;               // ng x nld
-  double (&f)[SFN_NG][WC];
+  int nld, lane;
+  const double* zs;               // NGT x nld (rows of absent functions are zero)
+  double (&f)[NGT][WC];
   __device__ __forceinline__ void column(int s, int k, int Kc, const double (&col)[WC], const double (&)[1], double ginv) {
     const int sC = s % WC;
     const double su = ginv * rsqrt_nr(ginv);      // 1 / L[k][k]
 #pragma unroll
-    for (int j = 0; j < SFN_NG; ++j) {
-      if (j < ng) {
-        const double zk = zs[j * nld + k] * su;
+    for (int j = 0; j < NGT; ++j) {
+      const double zk = zs[j * nld + k] * su;
 #pragma unroll
-        for (int q = 0; q < WC; ++q) {
-          const bool live = (q >= sC) ? (lane >= Kc) : (lane > Kc);
-          if (live) f[j][q] = fma(col[(q - sC + WC) % WC], zk, f[j][q]);
-        }
+      for (int q = 0; q < WC; ++q) {
+        const bool live = (q >= sC) ? (lane >= Kc) : (lane > Kc);
+        if (live) f[j][q] = fma(col[(q - sC + WC) % WC], zk, f[j][q]);
       }
     }
   }
@@ -145,105 +143,100 @@ struct OpPriorDraw {
 
 // one column of the solve  v = C^-1 q  for up to SFN_NC right-hand sides:  wt = r_k / g_k,  r -= u wt,  v += a wt
 // (a = column k of L^-T times the scale of u; it is exactly zero below position k: no masking needed)
-template <int WC, int WA>
+template <int WC, int WA, int NM>
 struct OpSolve {
-  int n, nm;                      // time points, right-hand sides in this pass
-  double (&r)[SFN_NC][WC];
-  double (&vo)[SFN_NC][WA];
+  int n;                          // time points
+  double (&r)[NM][WC];
+  double (&vo)[NM][WA];
   __device__ __forceinline__ void column(int s, int k, int Kc, const double (&col)[WC], const double (&a)[WA], double ginv) {
     const int sC = s % WC, sA = s % WA;
 #pragma unroll
-    for (int j = 0; j < SFN_NC; ++j) {
-      if (j < nm) {
-        const double rraw = __shfl_sync(FULLMASK, r[j][sC], Kc);
-        const double wt = (k < n) ? rraw * ginv : 0.0;
+    for (int j = 0; j < NM; ++j) {
+      const double rraw = __shfl_sync(FULLMASK, r[j][sC], Kc);
+      const double wt = (k < n) ? rraw * ginv : 0.0;
 #pragma unroll
-        for (int q = 0; q < WC; ++q) r[j][q] = fma(-col[(q - sC + WC) % WC], wt, r[j][q]);
+      for (int q = 0; q < WC; ++q) r[j][q] = fma(-col[(q - sC + WC) % WC], wt, r[j][q]);
 #pragma unroll
-        for (int q = 0; q < WA; ++q) vo[j][q] = fma(a[(q - sA + WA) % WA], wt, vo[j][q]);
-      }
+      for (int q = 0; q < WA; ++q) vo[j][q] = fma(a[(q - sA + WA) % WA], wt, vo[j][q]);
     }
   }
 };
 
 // prior draws: the column set through its stages; finished positions of f (below the current column) are parked in the
 // shared-memory rows of z1 they no longer need
-template <int W0, int WC>
-__device__ __forceinline__ void sfn_prior_chain(int n, int n8, int lane, double (&col)[WC], double (&v)[WC], double (&f)[SFN_NG][WC],
-                                                double& ginv, bool& ok, int ng, int nld, double* zs) {
+template <int W0, int WC, int NGT>
+__device__ __forceinline__ void sfn_prior_chain(int n, int n8, int lane, double (&col)[WC], double (&v)[WC], double (&f)[NGT][WC],
+                                                double& ginv, bool& ok, int nld, double* zs) {
   constexpr int baseC = 32 * (W0 - WC);
   constexpr int K1 = (WC > 1) ? baseC + 16 * WC : 32 * W0;
   double da[1] = {0.0}, db[1] = {0.0};
-  OpPriorDraw<WC> op{ng, nld, lane, zs, f};
-  sfn_segment<WC, 1, false>(n, baseC, (K1 < n8) ? K1 : n8, baseC, lane, col, v, da, db, ginv, ok, op);
+  {
+    OpPriorDraw<WC, NGT> op{nld, lane, zs, f};
+    sfn_segment<WC, 1, false>(n, baseC, (K1 < n8) ? K1 : n8, baseC, lane, col, v, da, db, ginv, ok, op);
+  }
   if constexpr (WC > 1) {
     if (K1 < n8 && ok) {
       __syncwarp();
       if (lane < 16) {
 #pragma unroll
-        for (int j = 0; j < SFN_NG; ++j)
-          if (j < ng) {
+        for (int j = 0; j < NGT; ++j)
 #pragma unroll
-            for (int q = 0; q < WC; ++q) zs[j * nld + baseC + WC * lane + q] = f[j][q];
-          }
+          for (int q = 0; q < WC; ++q) zs[j * nld + baseC + WC * lane + q] = f[j][q];
       }
-      double col2[WC / 2], v2[WC / 2], f2[SFN_NG][WC / 2];
+      double col2[WC / 2], v2[WC / 2], f2[NGT][WC / 2];
       schur_repack<WC>(col, col2, lane);
       schur_repack<WC>(v, v2, lane);
 #pragma unroll
-      for (int j = 0; j < SFN_NG; ++j) schur_repack<WC>(f[j], f2[j], lane);
-      sfn_prior_chain<W0, WC / 2>(n, n8, lane, col2, v2, f2, ginv, ok, ng, nld, zs);
+      for (int j = 0; j < NGT; ++j) schur_repack<WC>(f[j], f2[j], lane);
+      sfn_prior_chain<W0, WC / 2, NGT>(n, n8, lane, col2, v2, f2, ginv, ok, nld, zs);
       return;
     }
   }
   __syncwarp();
 #pragma unroll
-  for (int j = 0; j < SFN_NG; ++j)
-    if (j < ng) {
+  for (int j = 0; j < NGT; ++j)
 #pragma unroll
-      for (int q = 0; q < WC; ++q) {
-        const int p = baseC + WC * lane + q;
-        if (p < nld) zs[j * nld + p] = f[j][q];
-      }
+    for (int q = 0; q < WC; ++q) {
+      const int p = baseC + WC * lane + q;
+      if (p < nld) zs[j * nld + p] = f[j][q];
     }
 }
 
 // the embedded recursion through the stages of both sets (compile-time schedule: K0 = first step of this segment)
-template <int W0, int WC, int WA, int K0>
+template <int W0, int WC, int WA, int K0, int NM>
 __device__ __forceinline__ void sfn_solve_chain(int n, int n8, int lane, double (&col)[WC], double (&v)[WC], double (&a)[WA], double (&b)[WA],
-                                                double (&rq)[SFN_NC][WC], double (&vo)[SFN_NC][WA], double& ginv, bool& ok, int nm,
-                                                double (&vout)[SFN_NC][W0]) {
+                                                double (&rq)[NM][WC], double (&vo)[NM][WA], double& ginv, bool& ok, double (&vout)[NM][W0]) {
   constexpr int baseC = 32 * (W0 - WC);
   constexpr int kc = (WC > 1) ? baseC + 16 * WC : (1 << 30);      // the column set is re-dealt here
   constexpr int ka = (WA < W0) ? 32 * WA - 8 : (1 << 30);         // the inverse set is spread out here
   constexpr int kx = (kc < ka) ? kc : ka;
   constexpr int K1 = (kx < 32 * W0) ? kx : 32 * W0;
   {
-    OpSolve<WC, WA> op{n, nm, rq, vo};
+    OpSolve<WC, WA, NM> op{n, rq, vo};
     sfn_segment<WC, WA, true>(n, K0, (K1 < n8) ? K1 : n8, baseC, lane, col, v, a, b, ginv, ok, op);
   }
   if constexpr (K1 < 32 * W0) {
     if (K1 < n8 && ok) {
       if constexpr (ka < kc) {
-        double a2[2 * WA], b2[2 * WA], vo2[SFN_NC][2 * WA];
+        double a2[2 * WA], b2[2 * WA], vo2[NM][2 * WA];
         sfn_expand<WA>(a, a2, lane);
         sfn_expand<WA>(b, b2, lane);
 #pragma unroll
-        for (int j = 0; j < SFN_NC; ++j) sfn_expand<WA>(vo[j], vo2[j], lane);
-        sfn_solve_chain<W0, WC, 2 * WA, K1>(n, n8, lane, col, v, a2, b2, rq, vo2, ginv, ok, nm, vout);
+        for (int j = 0; j < NM; ++j) sfn_expand<WA>(vo[j], vo2[j], lane);
+        sfn_solve_chain<W0, WC, 2 * WA, K1, NM>(n, n8, lane, col, v, a2, b2, rq, vo2, ginv, ok, vout);
       } else {
-        double col2[WC / 2], v2[WC / 2], rq2[SFN_NC][WC / 2];
+        double col2[WC / 2], v2[WC / 2], rq2[NM][WC / 2];
         schur_repack<WC>(col, col2, lane);
         schur_repack<WC>(v, v2, lane);
 #pragma unroll
-        for (int j = 0; j < SFN_NC; ++j) schur_repack<WC>(rq[j], rq2[j], lane);
-        sfn_solve_chain<W0, WC / 2, WA, K1>(n, n8, lane, col2, v2, a, b, rq2, vo, ginv, ok, nm, vout);
+        for (int j = 0; j < NM; ++j) schur_repack<WC>(rq[j], rq2[j], lane);
+        sfn_solve_chain<W0, WC / 2, WA, K1, NM>(n, n8, lane, col2, v2, a, b, rq2, vo, ginv, ok, vout);
       }
       return;
     }
   }
 #pragma unroll
-  for (int j = 0; j < SFN_NC; ++j)
+  for (int j = 0; j < NM; ++j)
 #pragma unroll
     for (int q = 0; q < W0; ++q) {
       if constexpr (WA == W0) vout[j][q] = vo[j][q];
@@ -279,6 +272,45 @@ __device__ __forceinline__ void sfn_normals(const Stream& rng, unsigned gch, uns
   }
 }
 
+// prior draws of NGT functions (rows of zs: z1 in, f = L_B z1 out); false on breakdown
+template <int W0, int NGT>
+__device__ __forceinline__ bool sfn_prior(const CtxDev& c, int n, int nld, int lane, double sigma, double ls, double diag_add, double* zs) {
+  double col[W0], v[W0], f[NGT][W0];
+  bool ok;
+  double ginv = sfn_init<W0>(c, n, sigma, ls, 1.0, diag_add, col, v, lane, ok);
+#pragma unroll
+  for (int j = 0; j < NGT; ++j)
+#pragma unroll
+    for (int q = 0; q < W0; ++q) f[j][q] = 0.0;
+  if (ok) sfn_prior_chain<W0, W0, NGT>(n, nld, lane, col, v, f, ginv, ok, nld, zs);
+  return ok;
+}
+
+// v = C^-1 q for NM right-hand sides (rows mem[0..NM) of zs) by the embedded recursion; false on breakdown
+template <int W0, int NM>
+__device__ __forceinline__ bool sfn_solve(const CtxDev& c, int n, int nld, int lane, double sigma, double ls, double cc, double diag_add,
+                                          const double* zs, const int* mem, double (&vout)[SFN_NC][W0]) {
+  double rq[NM][W0], vo[NM][1], vres[NM][W0];
+#pragma unroll
+  for (int j = 0; j < NM; ++j) {
+#pragma unroll
+    for (int q = 0; q < W0; ++q) rq[j][q] = (W0 * lane + q < nld) ? zs[mem[j] * nld + W0 * lane + q] : 0.0;
+    vo[j][0] = 0.0;
+  }
+  double col[W0], v[W0], ia[1], ib[1];
+  bool ok;
+  double ginv = sfn_init<W0>(c, n, sigma, ls, cc, diag_add, col, v, lane, ok);
+  ia[0] = ib[0] = (lane == 0) ? 1.0 : 0.0;          // generator rows [e0 e0] (times the scale sqrt(t0) of the column set)
+  if (ok) sfn_solve_chain<W0, W0, 1, 0, NM>(n, nld, lane, col, v, ia, ib, rq, vo, ginv, ok, vres);
+  if (ok) {
+#pragma unroll
+    for (int j = 0; j < NM; ++j)
+#pragma unroll
+      for (int q = 0; q < W0; ++q) vout[j][q] = vres[j][q];
+  }
+  return ok;
+}
+
 // one (prior group, chain) item at W0 slots per lane
 template <int W0>
 __device__ __forceinline__ void sfn_item(const CtxDev& c, const SchurFnArgs& a, const Stream& rng, int ch, int g, int lane, double* zs) {
@@ -306,22 +338,23 @@ __device__ __forceinline__ void sfn_item(const CtxDev& c, const SchurFnArgs& a, 
   double jitter = 0.0;
   for (;;) {
     __syncwarp();
-    for (int j = 0; j < ng; ++j) {                 // z1 (regenerated on a retry: finished draws overwrite it)
+#pragma unroll
+    for (int j = 0; j < SFN_NG; ++j) {             // z1 (regenerated on a retry: finished draws overwrite it); absent rows zero
       double z[W0];
-      sfn_normals<W0>(rng, gch, a.sweep, sid[j], 0, n, lane, z);
+      if (j < ng) sfn_normals<W0>(rng, gch, a.sweep, sid[j], 0, n, lane, z);
+      else {
+#pragma unroll
+        for (int q = 0; q < W0; ++q) z[q] = 0.0;
+      }
 #pragma unroll
       for (int q = 0; q < W0; ++q)
         if (W0 * lane + q < nld) zs[j * nld + W0 * lane + q] = z[q];
     }
     __syncwarp();
-    double col[W0], v[W0], f[SFN_NG][W0];
     bool ok;
-    double ginv = sfn_init<W0>(c, n, sigma, ls, 1.0, c.offset + jitter, col, v, lane, ok);
-#pragma unroll
-    for (int j = 0; j < SFN_NG; ++j)
-#pragma unroll
-      for (int q = 0; q < W0; ++q) f[j][q] = 0.0;
-    if (ok) sfn_prior_chain<W0, W0>(n, nld, lane, col, v, f, ginv, ok, ng, nld, zs);
+    if (ng == 1) ok = sfn_prior<W0, 1>(c, n, nld, lane, sigma, ls, c.offset + jitter, zs);
+    else if (ng == 2) ok = sfn_prior<W0, 2>(c, n, nld, lane, sigma, ls, c.offset + jitter, zs);
+    else ok = sfn_prior<W0, SFN_NG>(c, n, nld, lane, sigma, ls, c.offset + jitter, zs);
     if (ok) { code = tries; break; }
     const double dm = sigma + c.offset;                // jitchol ladder (linalg.py:41-54)
     if (tries == 0) {
@@ -362,25 +395,24 @@ __device__ __forceinline__ void sfn_item(const CtxDev& c, const SchurFnArgs& a, 
       const double isc = 1.0 / sqrt(cc);
       for (int m0 = 0; m0 < nmem; m0 += SFN_NC) {
         const int nm = (nmem - m0 < SFN_NC) ? nmem - m0 : SFN_NC;
-        double rq[SFN_NC][W0], vo[SFN_NC][1], vout[SFN_NC][W0];
+        double vout[SFN_NC][W0];
+        int mm[SFN_NC];
 #pragma unroll
         for (int j = 0; j < SFN_NC; ++j) {
+          mm[j] = mem[(m0 + j < nmem) ? m0 + j : m0];
 #pragma unroll
-          for (int q = 0; q < W0; ++q) rq[j][q] = (j < nm && W0 * lane + q < nld) ? zs[mem[m0 + j] * nld + W0 * lane + q] : 0.0;
-          vo[j][0] = 0.0;
+          for (int q = 0; q < W0; ++q) vout[j][q] = 0.0;
         }
-        double col[W0], v[W0], ia[1], ib[1];
-        bool ok;
-        double ginv = sfn_init<W0>(c, n, sigma, ls, cc, 1.0 + cc * (c.offset + jitter), col, v, lane, ok);
-        ia[0] = ib[0] = (lane == 0) ? 1.0 : 0.0;          // generator rows [e0 e0] (times the scale sqrt(t0) of the column set)
-        if (ok) sfn_solve_chain<W0, W0, 1, 0>(n, nld, lane, col, v, ia, ib, rq, vo, ginv, ok, nm, vout);
+        const double dadd = 1.0 + cc * (c.offset + jitter);
+        const bool ok = (nm == 1) ? sfn_solve<W0, 1>(c, n, nld, lane, sigma, ls, cc, dadd, zs, mm, vout)
+                                  : sfn_solve<W0, SFN_NC>(c, n, nld, lane, sigma, ls, cc, dadd, zs, mm, vout);
         ++nfact;
         if (!ok) { code = GPF_STATUS_NOT_PD; break; }
         // ---------------- 4. beta_j = ybar_j - (z2_j + v_j) / sqrt(c) ----------------
 #pragma unroll
         for (int j = 0; j < SFN_NC; ++j)
           if (j < nm) {
-            const int gj = mem[m0 + j];
+            const int gj = mm[j];
             double z2[W0];
             sfn_normals<W0>(rng, gch, a.sweep, sid[gj], n, 2 * n, lane, z2);
             const double* yb = c.bhat + (size_t)gf[gj] * n;

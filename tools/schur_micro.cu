@@ -3,6 +3,9 @@
 //   variant 1 = schur_eval_staged (scaled generator, 8 -> 4 -> 2 -> 1 slots per lane)
 // timed alone on the SM (latency: one warp per SM) and at the kernel's occupancy (444 CTAs x 4 warps), values compared.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-extended-lambda -lineinfo -I../gpfanova_b200/csrc -o schur_micro schur_micro.cu
+#ifndef MINB
+#define MINB 3
+#endif
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
@@ -13,7 +16,7 @@
 using namespace gpf;
 
 template <int VAR, int NG>
-__global__ void __launch_bounds__(128, 3) k_micro(CtxDev c, int ng, int reps, int nchain, double* out) {
+__global__ void __launch_bounds__(128, MINB) k_micro(CtxDev c, int ng, int reps, int nchain, double* out) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wid = __reduce_max_sync(FULLMASK, blockIdx.x * (blockDim.x >> 5) + warp), nw = gridDim.x * (blockDim.x >> 5);
   const int* fns = c.group_fns;
@@ -52,7 +55,7 @@ float run(CtxDev c, int ng, int reps, int nchain, int grid, int block, double* o
 
 int main(int argc, char** argv) {
   const int n = argc > 1 ? atoi(argv[1]) : 256;
-  const int C = 4096, f = 4;
+  const int C = 148 * 48, f = 4;      // 4 rounds at 12 warps per SM, 3 at 16
   std::vector<double> d2(n), F((size_t)C * f * n), hy(C);
   for (int k = 0; k < n; ++k) { const double d = 2.0 * k / (n - 1); d2[k] = d * d; }
   srand(1);
@@ -79,13 +82,13 @@ int main(int argc, char** argv) {
   auto report = [&](const char* name, int ng, float ms_lat, float ms_thr) {
     // latency: 148 warps each doing reps evaluations; throughput: 4096 chains x reps over the whole GPU
     printf("%-28s ng=%d  alone: %8.0f cycles/eval   full: %7.3f ms for %d evals = %6.1f cycles/eval/SM-warp-slot (%.2f us/eval/GPU)\n",
-           name, ng, ms_lat * 1e-3 * ghz * 1e9 / reps, ms_thr, C * reps, ms_thr * 1e-3 * ghz * 1e9 / (C * reps / (148.0 * 12)),
+           name, ng, ms_lat * 1e-3 * ghz * 1e9 / reps, ms_thr, C * reps, ms_thr * 1e-3 * ghz * 1e9 / (C * reps / (148.0 * 4 * MINB)),
            ms_thr * 1e3 / (C * reps));
   };
 #define BOTH(NG, ngv)                                                                                         \
   {                                                                                                           \
-    float l0 = run<0, NG>(c, ngv, reps, 148, 148, 32, dout0), t0 = run<0, NG>(c, ngv, reps, C, 444, 128, dout0); \
-    float l1 = run<1, NG>(c, ngv, reps, 148, 148, 32, dout1), t1 = run<1, NG>(c, ngv, reps, C, 444, 128, dout1); \
+    float l0 = run<0, NG>(c, ngv, reps, 148, 148, 32, dout0), t0 = run<0, NG>(c, ngv, reps, C, 148 * MINB, 128, dout0); \
+    float l1 = run<1, NG>(c, ngv, reps, 148, 148, 32, dout1), t1 = run<1, NG>(c, ngv, reps, C, 148 * MINB, 128, dout1); \
     report("normalised, 8 slots", ngv, l0, t0);                                                               \
     report("scaled, staged", ngv, l1, t1);                                                                    \
     std::vector<double> o0(3 * C), o1(3 * C);                                                                 \
