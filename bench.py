@@ -4,8 +4,9 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 A step is one Gibbs sweep (all samplers of base.py:57-84: 1 + f + 2P blocks) of every chain.  Workload: BASELINE
-config 5 -- two-way 3x3 FANOVA with interaction, 5 replicates (m=45, f=9, P=4), n=256 time points, 4096 chains in total
-(strong scaling: chains are split across the N ranks, no collective on the sampling path).
+config 5 -- two-way 3x3 FANOVA with interaction, 5 replicates (m=45, f=9, P=4), n=256 time points, 4096 chains per GPU
+(chains are independent units: every rank samples its own 4096, no collective on the sampling path -- weak scaling;
+--scaling strong splits ONE set of 4096 chains over the N ranks instead).
 Metric: posterior function draws/s = chains * f * sweeps / time, FP64.
 """
 import argparse
@@ -241,7 +242,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--chains", type=int, default=0, help="total chains (default: the workload's 4096)")
+    ap.add_argument("--chains", type=int, default=0, help="chains (per GPU when weak, in total when strong; default: the workload's 4096)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default): every GPU samples the workload's 4096 chains -- chains are independent units, no "
+                         "collective on the path; strong: the 4096 chains are split over the GPUs")
     ap.add_argument("--n", type=int, default=256)
     ap.add_argument("--burnin", type=int, default=20, help="untimed sweeps before warm-up (chains leave their start state)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -266,7 +270,7 @@ def main():
         res = run_cpu_arm(args.n, max(1, args.steps), max(0, args.warmup), args.cpu_procs or None)
         line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": res["ms_per_sweep_per_chain"], "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+                "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
                 "config": {"workload": WORKLOAD, "n": args.n, "m": 45, "f": 9, "P": 4, "chains": res["cores"],
                            "note": "reference CPU sampler, one chain per core"},
                 "cpu_baseline": res,
@@ -287,7 +291,11 @@ def main():
     x, eff, inter, hc, total_chains = problem(args.n)
     if args.chains:
         total_chains = args.chains
-    C = total_chains // world                       # strong scaling: the workload's chains are split over the ranks
+    if args.scaling == "weak":
+        C = total_chains                            # weak scaling: every rank samples a full workload of independent chains
+        total_chains = C * world
+    else:
+        C = total_chains // world                   # strong scaling: the workload's chains are split over the ranks
     first = rank * C
     model = fanova.FANOVA(x, np.zeros((args.n, eff.shape[0])), eff, interactions=inter, helmertConvert=hc, chains=C,
                           seed=20261019, device=local, store_chains=True)
@@ -431,7 +439,7 @@ def main():
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "n": n, "m": int(eff.shape[0]), "f": int(f), "P": P, "chains": total_chains,
                            "chains_per_gpu": C, "parallelism": "chains sharded over %d GPU(s), no collective" % world,

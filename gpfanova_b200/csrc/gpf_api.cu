@@ -16,6 +16,7 @@
 #include "gpf_ops.cuh"
 #include "gpf_schur.cuh"
 #include "gpf_schurfn.cuh"
+#include "gpf_sweepk.cuh"
 
 using namespace gpf;
 
@@ -60,6 +61,14 @@ struct gpf_ctx {
   double* d_kinv_tmp = nullptr;       // scratch of the K_inv operator (gpf_group_kinv with an output buffer)
   bool schurfn_ok = false;            // uniform grid, balanced design, n <= 256, groups of at most 4: O(n^2) function step
   int use_schurfn = 1;
+  int use_sweepk = 0;                 // whole sweeps in one launch, no device-wide barriers (k_chain_sweeps) where it applies;
+                                      // off by default: its instruction footprint (function step + three slice variants in
+                                      // flight on every SM) misses the 32 KB instruction cache -- measured 4x slower
+  int* d_swk = nullptr;               // its per-chain progress words: prog[C], done[C], err
+  unsigned* d_sid_sigma = nullptr;    // sampler id of prior{g}_sigma per group
+  std::vector<unsigned> h_sid_sigma;
+  double* d_slice_w = nullptr;
+  int* d_slice_m = nullptr;
   std::vector<int> schur_warps;       // per group: warps per CTA of the Schur slice kernel (0: dense engine)
   int use_schur = 1;
   int batch = 1;                       // batch independent function draws / K_inv of all groups into one launch
@@ -274,6 +283,76 @@ int launch_prior(gpf_ctx* c, int g, int mode, const double* cand, double* outv, 
   ++c->launches;
   CK(c, cudaGetLastError());
   if (mode >= 2) c->lb_valid[g] = 0;
+  return GPF_OK;
+}
+
+// whole sweeps in one launch (gpf_sweepk.cuh): balanced design on a uniform grid, every group on the register-resident
+// Schur kernels, reference order of the samplers
+bool sweepk_active(const gpf_ctx* c) {
+  if (!c->use_sweepk || !c->indep || !c->batch || !schurfn_active(c) || c->dev.bhat == nullptr || c->profile == 1) return false;
+  if (c->dev.n > 256) return false;
+  for (int g = 0; g < c->dev.P; ++g)
+    if (!uses_schur(c, g) || c->groups[g].size() > 4) return false;
+  return true;
+}
+
+int launch_chain_sweeps(gpf_ctx* c, int n_sweeps, int thin, unsigned sweep0, double* d_history, long long cap, long long* rows) {
+  const CtxDev& v = c->dev;
+  const int ns = (int)c->order.size();
+  if (!c->d_swk) {
+    int rc;
+    if ((rc = dev_alloc(c, &c->d_swk, (size_t)2 * v.C + 1)) || (rc = dev_alloc(c, &c->d_sid_sigma, (size_t)v.P)) ||
+        (rc = dev_alloc(c, &c->d_slice_w, (size_t)v.H)) || (rc = dev_alloc(c, &c->d_slice_m, (size_t)v.H)))
+      return rc;
+    CK(c, cudaMemset(c->d_swk + 2 * v.C, 0, sizeof(int)));
+  }
+  std::vector<unsigned> sid((size_t)v.P, 0u);
+  for (int k = 0; k < ns; ++k)
+    if (c->order[k].kind == 0 && c->order[k].arg >= 1 && (c->order[k].arg - 1) % 2 == 0) sid[(c->order[k].arg - 1) / 2] = (unsigned)k;
+  if (sid != c->h_sid_sigma) {
+    CK(c, cudaStreamSynchronize(c->stream));
+    CK(c, cudaMemcpy(c->d_sid_sigma, sid.data(), sizeof(unsigned) * sid.size(), cudaMemcpyHostToDevice));
+    CK(c, cudaMemcpy(c->d_slice_w, c->slice_w.data(), sizeof(double) * v.H, cudaMemcpyHostToDevice));
+    CK(c, cudaMemcpy(c->d_slice_m, c->slice_m.data(), sizeof(int) * v.H, cudaMemcpyHostToDevice));
+    c->h_sid_sigma = sid;
+  }
+  const int step = thin <= 0 ? 1 : thin;
+  long long kmax = ((1ll << 31) - 1 - v.C) / ((long long)v.C * v.P) - 1;     // tickets of one launch fit an int
+  kmax -= kmax % step;
+  if (kmax < step) { c->err = "gpf_sweep: thinning interval too large for one launch"; return GPF_ERR_ARG; }
+  const int nld = ((v.n + 7) / 8) * 8;
+  const size_t smem = (size_t)4 * SFN_NG * nld * sizeof(double);
+  const int grid = (int)std::min<long long>(((long long)v.C * v.P + 3) / 4, (long long)GPF_SFN_MINB * c->sms);
+  int done = 0;
+  while (done < n_sweeps) {
+    const int k = (int)std::min<long long>(kmax, n_sweeps - done);
+    const long long nrows = d_history ? (thin <= 0 ? k : k / step) : 0;
+    if (d_history && *rows + nrows > cap) { c->err = "gpf_sweep: history buffer full"; return GPF_ERR_ARG; }
+    Timer t(c, 2);
+    CK(c, cudaMemsetAsync(v.sched, 0, sizeof(int), c->stream));
+    CK(c, cudaMemsetAsync(c->d_swk, 0, sizeof(int) * 2 * v.C, c->stream));
+    SweepKArgs a{};
+    a.fn = SchurFnArgs{c->d_gorder, c->share ? c->d_gcls_off : c->d_gcls1_off, c->share ? c->d_cls_off : c->d_cls1_off, c->d_cls_fn,
+                       c->d_cls_sid, 0u};
+    a.sweep0 = sweep0 + (unsigned)done;
+    a.n_sweeps = k;
+    a.thin = thin;
+    a.history = d_history ? d_history + (size_t)(*rows) * v.C * ((size_t)v.H + (size_t)v.f * v.n) : nullptr;
+    a.rows_cap = nrows;
+    a.sid_sigma = c->d_sid_sigma;
+    a.slice_w = c->d_slice_w;
+    a.slice_m = c->d_slice_m;
+    a.sid_y = 0u;
+    a.prog = c->d_swk;
+    a.done = c->d_swk + v.C;
+    a.err = c->d_swk + 2 * v.C;
+    k_chain_sweeps<<<grid, 128, smem, c->stream>>>(v, a);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+    *rows += nrows;
+    done += k;
+  }
+  for (int g = 0; g < v.P; ++g) c->lb_valid[g] = 0;
   return GPF_OK;
 }
 
@@ -990,6 +1069,11 @@ int gpf_get_status(gpf_ctx* c, int* h_status, int clear) {
   CK(c, cudaMemcpyAsync(tmp.data(), c->dev.status, sizeof(int) * c->dev.C, cudaMemcpyDeviceToHost, c->stream));
   if (clear) CK(c, cudaMemsetAsync(c->dev.status, 0, sizeof(int) * c->dev.C, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
+  if (c->d_swk) {
+    int e = 0;
+    CK(c, cudaMemcpy(&e, c->d_swk + 2 * c->dev.C, sizeof(int), cudaMemcpyDeviceToHost));
+    if (e) { c->err = "k_chain_sweeps: a unit waited too long for its chain's y_sigma step (internal error)"; return GPF_ERR_CUDA; }
+  }
   bool bad = false;
   for (int i = 0; i < c->dev.C; ++i) {
     if (h_status) h_status[i] = tmp[i];
@@ -1072,7 +1156,12 @@ int gpf_sweep(gpf_ctx* c, int n_sweeps, int thin, unsigned sweep0, const int* h_
     cudaEventCreate(&t0); cudaEventCreate(&t1);
     cudaEventRecord(t0, c->stream);
   }
-  for (int s = 0; s < n_sweeps; ++s) {
+  const bool one_launch = !h_order && sweepk_active(c);
+  if (one_launch) {
+    int rc = launch_chain_sweeps(c, n_sweeps, thin, sweep0, d_history, history_capacity_rows, &rows);
+    if (rc) return rc;
+  }
+  for (int s = 0; s < n_sweeps && !one_launch; ++s) {
     const unsigned sweep = sweep0 + (unsigned)s;
     if (!h_order && c->indep && c->batch) {
       // Balanced design, nothing missing: given the hyper-parameters the function draws of a sweep do not depend on
@@ -1161,6 +1250,7 @@ int gpf_set_option(gpf_ctx* c, int option, int value) {
   }
   if (option == 4) { c->dev.bhat = value ? c->d_bhat : nullptr; return GPF_OK; }
   if (option == 5) { c->use_schurfn = value; return GPF_OK; }
+  if (option == 7) { c->use_sweepk = value; return GPF_OK; }
   c->err = "gpf_set_option: unknown option";
   return GPF_ERR_ARG;
 }
@@ -1175,6 +1265,7 @@ int gpf_get_option(gpf_ctx* c, int option) {
     case 4: return c->dev.bhat != nullptr;
     case 5: return schurfn_active(c) ? 1 : 0;
     case 6: return c->indep ? 1 : 0;       // (read-only) balanced design, nothing missing
+    case 7: return sweepk_active(c) ? 1 : 0;
     default: return -1;
   }
 }

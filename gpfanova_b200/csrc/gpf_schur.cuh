@@ -310,7 +310,7 @@ __device__ __forceinline__ SchurOut schur_eval_entry(const CtxDev& c, int n, int
 #pragma unroll
     for (int q = 0; q < W0; ++q) {
       const int i = lane * W0 + q;
-      r[qq][q] = (qq < ng && i < n) ? Fc[(size_t)fns[qq] * n + i] : 0.0;
+      r[qq][q] = (qq < ng && i < n) ? __ldcg(Fc + (size_t)fns[qq] * n + i) : 0.0;
     }
   SchurScal sc{rcp_nr(t0), 1.0, 0.0, 0, true};
   schur_chain<W0, NG>(n, 0, lane, col, v, r, sc);
@@ -343,22 +343,20 @@ __device__ __forceinline__ int next_chain_warp(int* sched, int lane) {
 #endif
 __host__ __device__ constexpr int schur_minb(int NG) { return NG == 0 ? 2 : (NG <= 2 ? GPF_SCHUR_MINB_SMALL : 3); }
 
+// one chain's slice step(s) on the hyper-parameters of prior group a.g (all lanes of the warp; modes as k_prior)
 template <int NG>   // NG > 0: register-resident evaluation (n <= 256, group size <= NG); 0: shared-memory evaluation
-__global__ void __launch_bounds__(NG > 0 ? 128 : NTHR, schur_minb(NG)) k_prior_schur(CtxDev c, PriorArgs a) {
-  extern __shared__ __align__(16) double gpf_smem_schur[];
+__device__ __forceinline__ void schur_slice_chain(const CtxDev& c, const PriorArgs& a, int ch, int lane, double* us, double* v, double* ev,
+                                                  double* r) {
   const int n = c.n, g = a.g, mode = a.mode;
   const int ng = c.group_off[g + 1] - c.group_off[g];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* base = gpf_smem_schur + (size_t)warp * schur_warp_doubles(n, ng);
-  double *us = base, *v = base + n, *ev = base + 2 * n, *r = base + 4 * n;   // base + 3n: spare (alignment of r)
   const int* fns = c.group_fns + c.group_off[g];
   const Stream rng{c.k0, c.k1};
   const double lb = c.prior_lb, ub = c.prior_ub, lprior = -log(ub - lb), nlog2pi = (double)n * LOG2PI;
-  for (int ch = next_chain_warp(c.sched, lane); ch < c.C; ch = next_chain_warp(c.sched, lane)) {
+  {
     const unsigned gch = (unsigned)(ch + c.chain_offset);
     const double* Fc = c.F + (size_t)ch * c.f * n;
-    const double cur_s = c.hyper[(size_t)ch * c.H + 1 + 2 * g];
-    const double cur_l = c.hyper[(size_t)ch * c.H + 2 + 2 * g];
+    const double cur_s = __ldcg(c.hyper + (size_t)ch * c.H + 1 + 2 * g);   // (L2: another SM may have written it)
+    const double cur_l = __ldcg(c.hyper + (size_t)ch * c.H + 2 + 2 * g);
     const unsigned sid_l = a.sampler_id + (mode == 4 ? 1u : 0u);
     auto unif_s = [&](int k) {
       return (a.u_inject && mode == 2 && k < a.n_inject) ? a.u_inject[(size_t)ch * a.n_inject + k]
@@ -442,6 +440,18 @@ __global__ void __launch_bounds__(NG > 0 ? 128 : NTHR, schur_minb(NG)) k_prior_s
     }
     __syncwarp();
   }
+}
+
+template <int NG>
+__global__ void __launch_bounds__(NG > 0 ? 128 : NTHR, schur_minb(NG)) k_prior_schur(CtxDev c, PriorArgs a) {
+  extern __shared__ __align__(16) double gpf_smem_schur[];
+  const int n = c.n, g = a.g;
+  const int ng = c.group_off[g + 1] - c.group_off[g];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* base = gpf_smem_schur + (size_t)warp * schur_warp_doubles(n, ng);
+  double *us = base, *v = base + n, *ev = base + 2 * n, *r = base + 4 * n;   // base + 3n: spare (alignment of r)
+  for (int ch = next_chain_warp(c.sched, lane); ch < c.C; ch = next_chain_warp(c.sched, lane))
+    schur_slice_chain<NG>(c, a, ch, lane, us, v, ev, r);
 }
 
 }  // namespace gpf

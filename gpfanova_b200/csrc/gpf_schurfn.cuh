@@ -316,9 +316,9 @@ template <int W0>
 __device__ __forceinline__ void sfn_item(const CtxDev& c, const SchurFnArgs& a, const Stream& rng, int ch, int g, int lane, double* zs) {
   const int n = c.n, nld = ((n + 7) >> 3) << 3;
   const unsigned gch = (unsigned)(ch + c.chain_offset);
-  const double sigma = exp10(c.hyper[(size_t)ch * c.H + 1 + 2 * g]);
-  const double ls = exp10(c.hyper[(size_t)ch * c.H + 2 + 2 * g]);
-  const double yinv = 1.0 / (exp10(c.hyper[(size_t)ch * c.H]) + c.offset);
+  const double sigma = exp10(__ldcg(c.hyper + (size_t)ch * c.H + 1 + 2 * g));      // (L2: written by other SMs in the sweep kernel)
+  const double ls = exp10(__ldcg(c.hyper + (size_t)ch * c.H + 2 + 2 * g));
+  const double yinv = 1.0 / (exp10(__ldcg(c.hyper + (size_t)ch * c.H)) + c.offset);
   const int f0 = c.group_off[g], ng = c.group_off[g + 1] - f0;          // functions of the group: group_fns[f0 .. f0+ng)
   const int* gf = c.group_fns + f0;
   // sampler id of every function of the group (from the class lists) and its class's c
@@ -447,7 +447,20 @@ __global__ void __launch_bounds__(128, GPF_SFN_MINB) k_group_schurfn(CtxDev c, S
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Stream rng{c.k0, c.k1};
   double* zs = gpf_smem_sfn + (size_t)warp * (SFN_NG * nld);
-  for (int item = next_chain_warp(c.sched, lane); item < c.C * c.P; item = next_chain_warp(c.sched, lane)) {
+  // Items are handed out FOUR AT A TIME to a CTA (consecutive chains of one prior group): its warps then run the same
+  // recursion loops side by side.  The loops of this kernel add up to several times the 32 KB instruction cache; with warps
+  // taking items one by one every warp of an SM sat in a different loop (ncu: 87 % instruction-cache hits, 0.8 no-instruction
+  // stall cycles per issue).
+  __shared__ int s_ticket;
+  const int nitem = c.C * c.P;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(c.sched, 1);
+    __syncthreads();
+    const int base = s_ticket * 4;
+    if (base >= nitem) break;
+    const int item = (int)__reduce_max_sync(FULLMASK, (unsigned)(base + warp));
+    if (item >= nitem) continue;
     const int ch = item % c.C, g = a.gorder[item / c.C];
     if (n > 128) sfn_item<8>(c, a, rng, ch, g, lane, zs);
     else if (n > 64) sfn_item<4>(c, a, rng, ch, g, lane, zs);

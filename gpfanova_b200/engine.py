@@ -334,6 +334,15 @@ def _prefault_pool():
     return _PREFAULT
 
 
+def _env_options():
+    out = []
+    for item in os.environ.get("GPFANOVA_B200_OPTIONS", "").split(","):
+        if "=" in item:
+            k, v = item.split("=")
+            out.append((int(k), int(v)))
+    return out
+
+
 class ChainEngine(object):
     """C chains of  y (n x m) = F (n x f) X^T + noise  on one GPU.
 
@@ -388,6 +397,8 @@ class ChainEngine(object):
         self._h = h
         self.sweeps_done = 0
         self._dev_hist = None
+        for opt, val in _env_options():                       # GPFANOVA_B200_OPTIONS="7=1,3=0": A/B runs of the same program
+            self.set_option(opt, val)
 
     # -- lifetime ------------------------------------------------------------------------------
     def close(self):
@@ -544,11 +555,12 @@ class ChainEngine(object):
         for functions with identical conditional precision; 3: centrosymmetric split on uniform grids (even n >= 64): all
         n^3 work of the function step on the two half-size blocks; 4: observation likelihood about the
         least-squares fit (balanced designs, nothing missing); 5: function step by the O(n^2) Schur algorithm (uniform grid,
-        balanced design, n <= 256, prior groups of at most four functions)"""
+        balanced design, n <= 256, prior groups of at most four functions); 7: all sweeps of a call in one launch without
+        device-wide barriers (chain-resident sweep kernel) where option 5 applies to every prior group"""
         self._ck(self._lib.gpf_set_option(self._h, int(option), int(value)))
 
     def get_option(self, option):
-        """effective value of an option (5: O(n^2) Schur function step active; 3: split factors of K_o; 6: balanced design)"""
+        """effective value of an option (5: O(n^2) Schur function step active; 3: split factors of K_o; 6: balanced design; 7: one-launch sweeps active)"""
         return int(self._lib.gpf_get_option(self._h, int(option)))
 
     def sweep_host(self, n_sweeps=1, thin=0, order=None, stage_bytes=96 << 20, max_chunk_sweeps=None, on_chunk=None):

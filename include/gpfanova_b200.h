@@ -253,6 +253,13 @@ int gpf_sweep(gpf_ctx* ctx, int n_sweeps, int thin, unsigned sweep0, const int* 
  * 5 = uniform grid, balanced design with nothing missing, n <= 256 and at most four functions per prior group: K_o and
  * C = I + c K_o are symmetric positive definite Toeplitz matrices and the whole function step runs on the Schur
  * algorithm, O(n^2) per function, one warp per (prior group, chain) (default 1 where it applies; 0 = dense fused kernel).
+ * 7 = where option 5 applies to every prior group and the samplers run in the reference's fixed order: all sweeps of a
+ * gpf_sweep call run in ONE launch with no device-wide barrier between samplers or sweeps -- warps take (sweep, group, chain)
+ * units from a ticket counter, a chain's y_sigma step and history row are done by whichever warp finishes the chain's last
+ * group of a sweep, chains drift apart freely (csrc/gpf_sweepk.cuh; bit-identical to option 7 = 0, which launches one kernel per
+ * sampler stage and sweep; per-kernel profiling, gpf_set_profile(ctx, 1), implies 0).  DEFAULT 0: with the function step and
+ * three slice variants in flight on every SM the kernel's hot loops miss the 32 KB instruction cache (ncu: 47 % hit rate, 23
+ * no-instruction stall cycles per issue) and it runs four times slower than the per-stage kernels.
  * Where option 5 applies, option 3 defaults to 0: the prior draw then uses the full Cholesky factor of K_o in every
  * kernel of the context; setting option 3 to 1 selects the split factors and with them the dense kernels.
  * gpf_get_option returns the EFFECTIVE value (option 6, read-only: 1 if the design is balanced with nothing missing). */
