@@ -211,12 +211,15 @@ def ncu_traffic(kernel_file, n, chains_per_gpu):
 
 def flops_model(n, f, P, ng_list, counts, schur, schurfn):
     """algorithmic FP64 flops of what was executed (counted by the kernels), DESIGN.md 5.
-    Schur recursion on an n x n Toeplitz matrix: one hyperbolic rotation per step, 6 flops per live position = 3 n^2;
-    every right-hand side riding along adds n^2 (forward substitution, 2 flops per position).
-      slice evaluation               (3 + |g|) n^2        (rotation + quadratic forms of the group's functions)
-      function step, K_o pass        3 n^2 + n^2 per function of the group (prior draw f = L_B z1 accumulated)
-      function step, C pass          6 n^2 (rotation of the Toeplitz generator and of the inverse-factor rows)
+    Schur recursion on an n x n Toeplitz matrix in the scaled (square-root-free) form: per step and live position
+    u' = u - rho v, v' = e v - rho u' = two multiply-adds and one multiply = 5 flops, n^2/2 live positions = 2.5 n^2;
+    every right-hand side riding along adds n^2 (forward substitution, one multiply-add per live position).
+      slice evaluation               (2.5 + |g|) n^2      (rotation + quadratic forms of the group's functions)
+      function step, K_o pass        2.5 n^2 + n^2 per function of the group (prior draw f = L_B z1 accumulated)
+      function step, C pass          5 n^2 (rotation of the Toeplitz generator and of the inverse-factor rows)
                                      + 2 n^2 per function (forward substitution + accumulation of v = L^-T y)
+    (the per-step scalars -- reflection coefficient, reciprocal, pivots -- and the dead lanes of the SIMD layout are NOT
+    counted: they are overhead of the implementation, which is why the FP64 pipe is busier than these numbers say)
     Dense paths (non-uniform grids, n > 256, large groups): factor of K_o per (group, chain, sweep) and of C per class
     n^3/3 each (centrosymmetric split: two half-size blocks, n^3/12); per draw two triangular solves and one to three
     triangular products ~ 5 n^2; dense slice factorisation n^3/3 + |g| n^2.  K_inv operator (not on the sweep path) n^3."""
@@ -225,13 +228,13 @@ def flops_model(n, f, P, ng_list, counts, schur, schurfn):
     fchol = counts.get("function_chol", counts["draws"])       # passes over C: functions with the same precision share one
     inv = counts["inverses"] * n3
     if schurfn:
-        draws = bfact * 3 * n2 + counts["draws"] * n2 + fchol * 6 * n2 + counts["draws"] * 2 * n2
+        draws = bfact * 2.5 * n2 + counts["draws"] * n2 + fchol * 5 * n2 + counts["draws"] * 2 * n2
     else:
         split = schur and n % 2 == 0 and n >= 64
         draws = (bfact + fchol) * (n3 / 12 if split else n3 / 3) + counts["draws"] * (2.5 if split else 5.0) * n2
     prior_facts = counts["chol"] - counts["inverses"] - fchol - bfact
     gbar = float(np.mean(ng_list))
-    per = (3.0 + gbar) * n2 if schur else (n3 / 3 + gbar * n2)
+    per = (2.5 + gbar) * n2 if schur else (n3 / 3 + gbar * n2)
     return {"kinv": inv, "function": draws, "prior_slice": prior_facts * per, "prior_factorisations": prior_facts,
             "total": inv + draws + prior_facts * per}
 
