@@ -61,6 +61,8 @@ struct gpf_ctx {
   double* d_kinv_tmp = nullptr;       // scratch of the K_inv operator (gpf_group_kinv with an output buffer)
   bool schurfn_ok = false;            // uniform grid, balanced design, n <= 256, groups of at most 4: O(n^2) function step
   int use_schurfn = 1;
+  int pipelines = 1;                  // balanced sweeps on the Schur kernels: functions -> slices of each group on its own stream
+  std::vector<int> h_gorder;
   int use_sweepk = 0;                 // whole sweeps in one launch, no device-wide barriers (k_chain_sweeps) where it applies;
                                       // off by default: its instruction footprint (function step + three slice variants in
                                       // flight on every SM) misses the 32 KB instruction cache -- measured 4x slower
@@ -227,7 +229,7 @@ int launch_all_functions(gpf_ctx* c, unsigned sweep) {
   if (schurfn_active(c)) {
     // uniform grid: both K_o and C = I + c K_o are Toeplitz -- O(n^2) Schur recursions, one warp per (group, chain)
     SchurFnArgs a{c->d_gorder, c->share ? c->d_gcls_off : c->d_gcls1_off, c->share ? c->d_cls_off : c->d_cls1_off, c->d_cls_fn,
-                  c->d_cls_sid, sweep};
+                  c->d_cls_sid, sweep, 0};
     const int nld = ((c->dev.n + 7) / 8) * 8;
     const size_t smem = (size_t)4 * SFN_NG * nld * sizeof(double);
     const int grid = std::min((c->dev.C * c->dev.P + 3) / 4, GPF_SFN_MINB * c->sms);
@@ -244,6 +246,26 @@ int launch_all_functions(gpf_ctx* c, unsigned sweep) {
   if (mode == 2) k_group_fused<2><<<grid, NTHR, sm, c->stream>>>(c->dev, a);
   else if (mode == 1) k_group_fused<1><<<grid, NTHR, sm, c->stream>>>(c->dev, a);
   else k_group_fused<0><<<grid, NTHR, sm, c->stream>>>(c->dev, a);
+  ++c->launches;
+  CK(c, cudaGetLastError());
+  return GPF_OK;
+}
+
+// the functions of ONE prior group on auxiliary stream `slot` (own hand-out counter): its slice kernel follows on the same
+// stream, so a group's slices start when its functions are done while other groups are still drawing functions
+int launch_group_functions(gpf_ctx* c, int g, unsigned sweep, int slot) {
+  Timer t(c, 2);
+  int gi = 0;
+  while (gi < (int)c->h_gorder.size() && c->h_gorder[gi] != g) ++gi;
+  CtxDev dev = c->dev;
+  dev.sched = c->dev.sched + 1 + slot;
+  CK(c, cudaMemsetAsync(dev.sched, 0, sizeof(int), c->aux[slot]));
+  SchurFnArgs a{c->d_gorder + gi, c->share ? c->d_gcls_off : c->d_gcls1_off, c->share ? c->d_cls_off : c->d_cls1_off, c->d_cls_fn,
+                c->d_cls_sid, sweep, 1};
+  const int nld = ((c->dev.n + 7) / 8) * 8;
+  const size_t smem = (size_t)4 * SFN_NG * nld * sizeof(double);
+  const int grid = std::min((c->dev.C + 3) / 4, GPF_SFN_MINB * c->sms);
+  k_group_schurfn<<<grid, 128, smem, c->aux[slot]>>>(dev, a);
   ++c->launches;
   CK(c, cudaGetLastError());
   return GPF_OK;
@@ -333,7 +355,7 @@ int launch_chain_sweeps(gpf_ctx* c, int n_sweeps, int thin, unsigned sweep0, dou
     CK(c, cudaMemsetAsync(c->d_swk, 0, sizeof(int) * 2 * v.C, c->stream));
     SweepKArgs a{};
     a.fn = SchurFnArgs{c->d_gorder, c->share ? c->d_gcls_off : c->d_gcls1_off, c->share ? c->d_cls_off : c->d_cls1_off, c->d_cls_fn,
-                       c->d_cls_sid, 0u};
+                       c->d_cls_sid, 0u, 0};
     a.sweep0 = sweep0 + (unsigned)done;
     a.n_sweeps = k;
     a.thin = thin;
@@ -951,6 +973,7 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
     cudaMemcpy(c->d_cls1_off, coff1.data(), sizeof(int) * coff1.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(c->d_gcls1_off, gcoff1.data(), sizeof(int) * gcoff1.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(c->d_gorder, gorder.data(), sizeof(int) * gorder.size(), cudaMemcpyHostToDevice);
+    c->h_gorder = gorder;
   }
   cudaError_t e = cudaMemcpy(dx, d->h_x, sizeof(double) * d->n * d->p, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(dyT, yT.data(), sizeof(double) * yT.size(), cudaMemcpyHostToDevice);
@@ -1169,7 +1192,10 @@ int gpf_sweep(gpf_ctx* c, int n_sweeps, int thin, unsigned sweep0, const int* h_
       // order  y_sigma, [functions, sigma, lengthscale] per group  is reproduced exactly by
       //   y_sigma | K_inv of all groups | all functions | slices per group   (same Philox counters, same inputs)
       int rc = launch_slice(c, 0, 1, nullptr, nullptr, 0u, sweep, nullptr, 0, nullptr);
-      if (!rc) rc = launch_all_functions(c, sweep);
+      bool conc0 = c->profile != 1;
+      for (int g = 0; g < c->dev.P; ++g) conc0 = conc0 && uses_schur(c, g);
+      const bool pipe = conc0 && c->pipelines && schurfn_active(c);     // functions of a group on that group's stream
+      if (!rc && !pipe) rc = launch_all_functions(c, sweep);
       // the groups' slice kernels are independent of each other: run them concurrently on auxiliary streams (a small
       // chain count does not fill the GPU alone; a large one leaves a tail of long slice steps that the next group's
       // CTAs fill) -- unless per-kernel timing is on: the timers sit on the main stream
@@ -1189,7 +1215,8 @@ int gpf_sweep(gpf_ctx* c, int n_sweeps, int thin, unsigned sweep0, const int* h_
       for (size_t q = 0; q < todo.size() && !rc; ++q) {
         const int k = todo[q].first, g = todo[q].second, slot = conc ? g % 4 : -1;
         if (conc && !forked[slot]) { CK(c, cudaStreamWaitEvent(c->aux[slot], c->ev_fork, 0)); forked[slot] = 1; ++used; }
-        rc = launch_prior(c, g, 4, nullptr, nullptr, (unsigned)k, sweep, nullptr, 0, nullptr, slot);
+        if (pipe) rc = launch_group_functions(c, g, sweep, slot);
+        if (!rc) rc = launch_prior(c, g, 4, nullptr, nullptr, (unsigned)k, sweep, nullptr, 0, nullptr, slot);
       }
       if (conc && !rc)
         for (int i = 0; i < 4; ++i)
@@ -1251,6 +1278,7 @@ int gpf_set_option(gpf_ctx* c, int option, int value) {
   if (option == 4) { c->dev.bhat = value ? c->d_bhat : nullptr; return GPF_OK; }
   if (option == 5) { c->use_schurfn = value; return GPF_OK; }
   if (option == 7) { c->use_sweepk = value; return GPF_OK; }
+  if (option == 8) { c->pipelines = value; return GPF_OK; }
   c->err = "gpf_set_option: unknown option";
   return GPF_ERR_ARG;
 }
@@ -1266,6 +1294,7 @@ int gpf_get_option(gpf_ctx* c, int option) {
     case 5: return schurfn_active(c) ? 1 : 0;
     case 6: return c->indep ? 1 : 0;       // (read-only) balanced design, nothing missing
     case 7: return sweepk_active(c) ? 1 : 0;
+    case 8: return c->pipelines;
     default: return -1;
   }
 }

@@ -35,6 +35,7 @@ struct SchurFnArgs {
   const int* cls_fn;
   const unsigned* cls_sid;
   unsigned sweep;
+  int ngroups;            // groups of this launch: gorder[0 .. ngroups)  (0: all P groups)
 };
 
 // Register layouts.  The recursion works on two sets of vectors that only meet in the scalars rho, e, 1/g of a step:
@@ -452,7 +453,7 @@ __global__ void __launch_bounds__(128, GPF_SFN_MINB) k_group_schurfn(CtxDev c, S
   // taking items one by one every warp of an SM sat in a different loop (ncu: 87 % instruction-cache hits, 0.8 no-instruction
   // stall cycles per issue).
   __shared__ int s_ticket;
-  const int nitem = c.C * c.P;
+  const int nitem = c.C * (a.ngroups > 0 ? a.ngroups : c.P);
   for (;;) {
     __syncthreads();
     if (threadIdx.x == 0) s_ticket = atomicAdd(c.sched, 1);

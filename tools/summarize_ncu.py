@@ -18,7 +18,12 @@ RAW = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "lau
        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
        "lts__t_sector_hit_rate.pct", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-       "dram__bytes_read.sum", "dram__bytes_write.sum", "smsp__inst_executed.sum"]
+       "dram__bytes_read.sum", "dram__bytes_write.sum", "smsp__inst_executed.sum", "sm__icc_request_hit_rate.pct",
+       "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+       "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+       "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+       "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
+       "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio"]
 
 
 def launches(path):
