@@ -62,6 +62,12 @@ struct gpf_ctx {
   bool schurfn_ok = false;            // uniform grid, balanced design, n <= 256, groups of at most 4: O(n^2) function step
   int use_schurfn = 1;
   int pipelines = 1;                  // balanced sweeps on the Schur kernels: functions -> slices of each group on its own stream
+  int cohorts = 1;                    // ... and the chains in this many independent cohorts, each with its own streams (1 or 2;
+                                      // two were SLOWER at every chain count: more kernel variants per SM, smaller grids)
+  struct Lane {                       // streams / events of the second cohort (the first uses stream, aux, ev_fork, ev_join)
+    cudaStream_t st = nullptr, aux[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t fork = nullptr, join[4] = {nullptr, nullptr, nullptr, nullptr}, begin = nullptr, end = nullptr;
+  } lane2;
   std::vector<int> h_gorder;
   int use_sweepk = 0;                 // whole sweeps in one launch, no device-wide barriers (k_chain_sweeps) where it applies;
                                       // off by default: its instruction footprint (function step + three slice variants in
@@ -231,7 +237,7 @@ int launch_all_functions(gpf_ctx* c, unsigned sweep) {
     SchurFnArgs a{c->d_gorder, c->share ? c->d_gcls_off : c->d_gcls1_off, c->share ? c->d_cls_off : c->d_cls1_off, c->d_cls_fn,
                   c->d_cls_sid, sweep, 0};
     const int nld = ((c->dev.n + 7) / 8) * 8;
-    const size_t smem = (size_t)4 * SFN_NG * nld * sizeof(double);
+    const size_t smem = (size_t)4 * SFN_SMEM_ROWS * nld * sizeof(double);
     const int grid = std::min((c->dev.C * c->dev.P + 3) / 4, GPF_SFN_MINB * c->sms);
     k_group_schurfn<<<grid, 128, smem, c->stream>>>(c->dev, a);
     ++c->launches;
@@ -246,26 +252,6 @@ int launch_all_functions(gpf_ctx* c, unsigned sweep) {
   if (mode == 2) k_group_fused<2><<<grid, NTHR, sm, c->stream>>>(c->dev, a);
   else if (mode == 1) k_group_fused<1><<<grid, NTHR, sm, c->stream>>>(c->dev, a);
   else k_group_fused<0><<<grid, NTHR, sm, c->stream>>>(c->dev, a);
-  ++c->launches;
-  CK(c, cudaGetLastError());
-  return GPF_OK;
-}
-
-// the functions of ONE prior group on auxiliary stream `slot` (own hand-out counter): its slice kernel follows on the same
-// stream, so a group's slices start when its functions are done while other groups are still drawing functions
-int launch_group_functions(gpf_ctx* c, int g, unsigned sweep, int slot) {
-  Timer t(c, 2);
-  int gi = 0;
-  while (gi < (int)c->h_gorder.size() && c->h_gorder[gi] != g) ++gi;
-  CtxDev dev = c->dev;
-  dev.sched = c->dev.sched + 1 + slot;
-  CK(c, cudaMemsetAsync(dev.sched, 0, sizeof(int), c->aux[slot]));
-  SchurFnArgs a{c->d_gorder + gi, c->share ? c->d_gcls_off : c->d_gcls1_off, c->share ? c->d_cls_off : c->d_cls1_off, c->d_cls_fn,
-                c->d_cls_sid, sweep, 1};
-  const int nld = ((c->dev.n + 7) / 8) * 8;
-  const size_t smem = (size_t)4 * SFN_NG * nld * sizeof(double);
-  const int grid = std::min((c->dev.C + 3) / 4, GPF_SFN_MINB * c->sms);
-  k_group_schurfn<<<grid, 128, smem, c->aux[slot]>>>(dev, a);
   ++c->launches;
   CK(c, cudaGetLastError());
   return GPF_OK;
@@ -343,7 +329,7 @@ int launch_chain_sweeps(gpf_ctx* c, int n_sweeps, int thin, unsigned sweep0, dou
   kmax -= kmax % step;
   if (kmax < step) { c->err = "gpf_sweep: thinning interval too large for one launch"; return GPF_ERR_ARG; }
   const int nld = ((v.n + 7) / 8) * 8;
-  const size_t smem = (size_t)4 * SFN_NG * nld * sizeof(double);
+  const size_t smem = (size_t)4 * SFN_SMEM_ROWS * nld * sizeof(double);
   const int grid = (int)std::min<long long>(((long long)v.C * v.P + 3) / 4, (long long)GPF_SFN_MINB * c->sms);
   int done = 0;
   while (done < n_sweeps) {
@@ -373,6 +359,111 @@ int launch_chain_sweeps(gpf_ctx* c, int n_sweeps, int thin, unsigned sweep0, dou
     CK(c, cudaGetLastError());
     *rows += nrows;
     done += k;
+  }
+  for (int g = 0; g < v.P; ++g) c->lb_valid[g] = 0;
+  return GPF_OK;
+}
+
+// Balanced design on a uniform grid, every group on the register-resident Schur kernels: one sweep of the chains
+// [c0, c0 + cnt) enqueued on one cohort's streams --  y_sigma | per group on its own stream: functions -> sigma + lengthscale
+// slices | join.  Cohorts are independent (chains never interact), so the stage boundaries of one cohort (each waits for
+// the slowest of its chains) are filled by the other cohort's kernels.
+bool pipe_active(const gpf_ctx* c) {
+  if (!c->pipelines || !c->indep || !c->batch || !schurfn_active(c) || c->profile == 1 || c->dev.n > 256) return false;
+  for (int g = 0; g < c->dev.P; ++g)
+    if (!uses_schur(c, g) || c->groups[g].size() > 4) return false;
+  return true;
+}
+
+int enqueue_schur_sweep(gpf_ctx* c, int q, int c0, int cnt, unsigned sweep, const std::vector<std::pair<int, int>>& todo) {
+  cudaStream_t st = q ? c->lane2.st : c->stream;
+  cudaStream_t* aux = q ? c->lane2.aux : c->aux;
+  cudaEvent_t fork = q ? c->lane2.fork : c->ev_fork;
+  cudaEvent_t* join = q ? c->lane2.join : c->ev_join;
+  CtxDev dv = c->dev;
+  dv.C = cnt;
+  dv.F += (size_t)c0 * dv.f * dv.n;
+  dv.hyper += (size_t)c0 * dv.H;
+  dv.status += c0;
+  dv.chain_offset += c0;
+  int* sched = c->dev.sched + 8 * q;
+  k_obs<<<std::min(cnt, c->sms * 8), NTHR, 0, st>>>(dv, 1, nullptr, nullptr, c->slice_w[0], c->slice_m[0], 0u, sweep, nullptr, 0, nullptr);
+  ++c->launches;
+  CK(c, cudaGetLastError());
+  CK(c, cudaEventRecord(fork, st));
+  const int nld = ((dv.n + 7) / 8) * 8;
+  const size_t smem = (size_t)4 * SFN_SMEM_ROWS * nld * sizeof(double);
+  bool forked[4] = {false, false, false, false};
+  for (size_t i = 0; i < todo.size(); ++i) {
+    const int k = todo[i].first, g = todo[i].second, slot = g % 4;
+    if (!forked[slot]) { CK(c, cudaStreamWaitEvent(aux[slot], fork, 0)); forked[slot] = true; }
+    CtxDev d2 = dv;
+    d2.sched = sched + 1 + slot;
+    int gi = 0;
+    while (gi < (int)c->h_gorder.size() && c->h_gorder[gi] != g) ++gi;
+    CK(c, cudaMemsetAsync(d2.sched, 0, sizeof(int), aux[slot]));
+    SchurFnArgs fa{c->d_gorder + gi, c->share ? c->d_gcls_off : c->d_gcls1_off, c->share ? c->d_cls_off : c->d_cls1_off, c->d_cls_fn,
+                   c->d_cls_sid, sweep, 1};
+    k_group_schurfn<<<std::min((cnt + 3) / 4, GPF_SFN_MINB * c->sms), 128, smem, aux[slot]>>>(d2, fa);
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemsetAsync(d2.sched, 0, sizeof(int), aux[slot]));
+    PriorArgs pa{g, 4, nullptr, nullptr, c->slice_w[1 + 2 * g], c->slice_w[2 + 2 * g], c->slice_m[1 + 2 * g], c->slice_m[2 + 2 * g],
+                 (unsigned)k, sweep, nullptr, 0, nullptr};
+    const int ng = (int)c->groups[g].size();
+    const int grid = std::min((cnt + 3) / 4, schur_minb(ng <= 2 ? ng : 4) * c->sms);
+    if (ng == 1) k_prior_schur<1><<<grid, 128, 0, aux[slot]>>>(d2, pa);
+    else if (ng == 2) k_prior_schur<2><<<grid, 128, 0, aux[slot]>>>(d2, pa);
+    else k_prior_schur<4><<<grid, 128, 0, aux[slot]>>>(d2, pa);
+    CK(c, cudaGetLastError());
+    c->launches += 2;
+  }
+  for (int i = 0; i < 4; ++i)
+    if (forked[i]) {
+      CK(c, cudaEventRecord(join[i], aux[i]));
+      CK(c, cudaStreamWaitEvent(st, join[i], 0));
+    }
+  return GPF_OK;
+}
+
+// n_sweeps sweeps of every chain through enqueue_schur_sweep, rows stored per cohort on the cohort's own stream
+int pipelined_sweeps(gpf_ctx* c, int n_sweeps, int thin, unsigned sweep0, double* d_history, long long cap, long long* rows) {
+  const CtxDev& v = c->dev;
+  const int ns = (int)c->order.size();
+  const size_t cols = (size_t)v.H + (size_t)v.f * v.n;
+  std::vector<std::pair<int, int>> todo;     // (sampler index of prior{g}_sigma, group), largest groups first
+  for (int k = 0; k < ns; ++k)
+    if (c->order[k].kind == 0 && c->order[k].arg >= 1 && (c->order[k].arg - 1) % 2 == 0) todo.push_back({k, (c->order[k].arg - 1) / 2});
+  std::stable_sort(todo.begin(), todo.end(), [&](const std::pair<int, int>& a, const std::pair<int, int>& b) {
+    return c->groups[a.second].size() > c->groups[b.second].size();
+  });
+  const int ncoh = (c->cohorts >= 2 && v.C >= 64) ? 2 : 1;
+  int start[3] = {0, v.C, v.C};
+  if (ncoh == 2) start[1] = ((v.C / 2 + 3) / 4) * 4;
+  if (ncoh == 2) {      // the second cohort starts behind everything queued so far on the context's stream
+    CK(c, cudaEventRecord(c->lane2.begin, c->stream));
+    CK(c, cudaStreamWaitEvent(c->lane2.st, c->lane2.begin, 0));
+  }
+  for (int s = 0; s < n_sweeps; ++s) {
+    const bool store = d_history && (thin <= 0 || (s + 1) % thin == 0);
+    if (store && *rows >= cap) { c->err = "gpf_sweep: history buffer full"; return GPF_ERR_ARG; }
+    for (int q = 0; q < ncoh; ++q) {
+      const int c0 = start[q], cnt = start[q + 1] - start[q];
+      int rc = enqueue_schur_sweep(c, q, c0, cnt, sweep0 + (unsigned)s, todo);
+      if (rc) return rc;
+      if (store) {
+        cudaStream_t st = q ? c->lane2.st : c->stream;
+        double* row = d_history + ((size_t)(*rows) * v.C + c0) * cols;
+        CK(c, cudaMemcpy2DAsync(row, cols * sizeof(double), v.hyper + (size_t)c0 * v.H, v.H * sizeof(double), v.H * sizeof(double), cnt,
+                                cudaMemcpyDeviceToDevice, st));
+        CK(c, cudaMemcpy2DAsync(row + v.H, cols * sizeof(double), v.F + (size_t)c0 * v.f * v.n, (size_t)v.f * v.n * sizeof(double),
+                                (size_t)v.f * v.n * sizeof(double), cnt, cudaMemcpyDeviceToDevice, st));
+      }
+    }
+    if (store) ++*rows;
+  }
+  if (ncoh == 2) {
+    CK(c, cudaEventRecord(c->lane2.end, c->lane2.st));
+    CK(c, cudaStreamWaitEvent(c->stream, c->lane2.end, 0));
   }
   for (int g = 0; g < v.P; ++g) c->lb_valid[g] = 0;
   return GPF_OK;
@@ -729,6 +820,14 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
       if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_user[i], cudaEventDisableTiming | cudaEventBlockingSync);
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->lane2.st, cudaStreamNonBlocking);
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i) {
+      e = cudaStreamCreateWithFlags(&c->lane2.aux[i], cudaStreamNonBlocking);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->lane2.join[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->lane2.fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->lane2.begin, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->lane2.end, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming);
     if (e != cudaSuccess) { c->err = cudaGetErrorString(e); return fail(GPF_ERR_CUDA); }
@@ -882,7 +981,8 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
     if (e == cudaSuccess) e = allow_smem(k_prior<true>, sp);
     if (e == cudaSuccess) e = allow_smem(k_prior<false>, sp);
     if (e == cudaSuccess) e = allow_smem(k_prior_schur<0>, 112 * 1024);
-    if (e == cudaSuccess) e = allow_smem(k_group_schurfn, (size_t)4 * SFN_NG * 256 * sizeof(double));
+    if (e == cudaSuccess) e = allow_smem(k_group_schurfn, (size_t)4 * SFN_SMEM_ROWS * 256 * sizeof(double));
+    if (e == cudaSuccess) e = allow_smem(k_chain_sweeps, (size_t)4 * SFN_SMEM_ROWS * 256 * sizeof(double));
     if (e != cudaSuccess) { c->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return fail(GPF_ERR_CUDA); }
   }
   c->grid = std::min(v.C, 2 * c->sms);
@@ -910,7 +1010,7 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
       (rc = dev_alloc(c, &dws, (size_t)ws_ctas * v.ws_stride)) || (rc = dev_alloc(c, &dgof, (size_t)d->f)) ||
       (rc = dev_alloc(c, &dgf, (size_t)d->f)) || (rc = dev_alloc(c, &dgo, (size_t)d->P + 1)) ||
       (rc = dev_alloc(c, &dst, (size_t)v.C)) || (rc = dev_alloc(c, &dcn, (size_t)CNT_N)) ||
-      (rc = dev_alloc(c, &dsched, (size_t)8)) || (rc = dev_alloc(c, &dd2, (size_t)d->n)) || (rc = dev_alloc(c, &dG, (size_t)d->f * d->f)) ||
+      (rc = dev_alloc(c, &dsched, (size_t)16)) || (rc = dev_alloc(c, &dd2, (size_t)d->n)) || (rc = dev_alloc(c, &dG, (size_t)d->f * d->f)) ||
       (rc = dev_alloc(c, &dZ, (size_t)d->f * d->n)) || (rc = dev_alloc(c, &dfull, (size_t)d->n)) ||
       (rc = dev_alloc(c, &dfws, (size_t)ws_ctas * v.fws_stride)))
     return fail(rc);
@@ -1011,6 +1111,14 @@ void gpf_destroy(gpf_ctx* c) {
     if (c->ev_user[i]) cudaEventDestroy(c->ev_user[i]);
   }
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  for (int i = 0; i < 4; ++i) {
+    if (c->lane2.aux[i]) { cudaStreamSynchronize(c->lane2.aux[i]); cudaStreamDestroy(c->lane2.aux[i]); }
+    if (c->lane2.join[i]) cudaEventDestroy(c->lane2.join[i]);
+  }
+  if (c->lane2.st) { cudaStreamSynchronize(c->lane2.st); cudaStreamDestroy(c->lane2.st); }
+  if (c->lane2.fork) cudaEventDestroy(c->lane2.fork);
+  if (c->lane2.begin) cudaEventDestroy(c->lane2.begin);
+  if (c->lane2.end) cudaEventDestroy(c->lane2.end);
   if (c->copy) { cudaStreamSynchronize(c->copy); cudaStreamDestroy(c->copy); }
   if (c->ev_copy) cudaEventDestroy(c->ev_copy);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -1179,10 +1287,14 @@ int gpf_sweep(gpf_ctx* c, int n_sweeps, int thin, unsigned sweep0, const int* h_
     cudaEventCreate(&t0); cudaEventCreate(&t1);
     cudaEventRecord(t0, c->stream);
   }
-  const bool one_launch = !h_order && sweepk_active(c);
+  bool one_launch = !h_order && sweepk_active(c);
   if (one_launch) {
     int rc = launch_chain_sweeps(c, n_sweeps, thin, sweep0, d_history, history_capacity_rows, &rows);
     if (rc) return rc;
+  } else if (!h_order && pipe_active(c)) {
+    int rc = pipelined_sweeps(c, n_sweeps, thin, sweep0, d_history, history_capacity_rows, &rows);
+    if (rc) return rc;
+    one_launch = true;          // (nothing left for the per-stage loop below)
   }
   for (int s = 0; s < n_sweeps && !one_launch; ++s) {
     const unsigned sweep = sweep0 + (unsigned)s;
@@ -1192,10 +1304,7 @@ int gpf_sweep(gpf_ctx* c, int n_sweeps, int thin, unsigned sweep0, const int* h_
       // order  y_sigma, [functions, sigma, lengthscale] per group  is reproduced exactly by
       //   y_sigma | K_inv of all groups | all functions | slices per group   (same Philox counters, same inputs)
       int rc = launch_slice(c, 0, 1, nullptr, nullptr, 0u, sweep, nullptr, 0, nullptr);
-      bool conc0 = c->profile != 1;
-      for (int g = 0; g < c->dev.P; ++g) conc0 = conc0 && uses_schur(c, g);
-      const bool pipe = conc0 && c->pipelines && schurfn_active(c);     // functions of a group on that group's stream
-      if (!rc && !pipe) rc = launch_all_functions(c, sweep);
+      if (!rc) rc = launch_all_functions(c, sweep);
       // the groups' slice kernels are independent of each other: run them concurrently on auxiliary streams (a small
       // chain count does not fill the GPU alone; a large one leaves a tail of long slice steps that the next group's
       // CTAs fill) -- unless per-kernel timing is on: the timers sit on the main stream
@@ -1215,8 +1324,7 @@ int gpf_sweep(gpf_ctx* c, int n_sweeps, int thin, unsigned sweep0, const int* h_
       for (size_t q = 0; q < todo.size() && !rc; ++q) {
         const int k = todo[q].first, g = todo[q].second, slot = conc ? g % 4 : -1;
         if (conc && !forked[slot]) { CK(c, cudaStreamWaitEvent(c->aux[slot], c->ev_fork, 0)); forked[slot] = 1; ++used; }
-        if (pipe) rc = launch_group_functions(c, g, sweep, slot);
-        if (!rc) rc = launch_prior(c, g, 4, nullptr, nullptr, (unsigned)k, sweep, nullptr, 0, nullptr, slot);
+        rc = launch_prior(c, g, 4, nullptr, nullptr, (unsigned)k, sweep, nullptr, 0, nullptr, slot);
       }
       if (conc && !rc)
         for (int i = 0; i < 4; ++i)
@@ -1279,6 +1387,7 @@ int gpf_set_option(gpf_ctx* c, int option, int value) {
   if (option == 5) { c->use_schurfn = value; return GPF_OK; }
   if (option == 7) { c->use_sweepk = value; return GPF_OK; }
   if (option == 8) { c->pipelines = value; return GPF_OK; }
+  if (option == 9) { c->cohorts = value < 1 ? 1 : (value > 2 ? 2 : value); return GPF_OK; }
   c->err = "gpf_set_option: unknown option";
   return GPF_ERR_ARG;
 }
@@ -1294,7 +1403,8 @@ int gpf_get_option(gpf_ctx* c, int option) {
     case 5: return schurfn_active(c) ? 1 : 0;
     case 6: return c->indep ? 1 : 0;       // (read-only) balanced design, nothing missing
     case 7: return sweepk_active(c) ? 1 : 0;
-    case 8: return c->pipelines;
+    case 8: return pipe_active(c) ? 1 : 0;
+    case 9: return c->cohorts;
     default: return -1;
   }
 }

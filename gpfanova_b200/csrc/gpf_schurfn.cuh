@@ -27,6 +27,8 @@ namespace gpf {
 
 constexpr int SFN_NG = 4;          // functions per prior group held in registers
 constexpr int SFN_NC = 2;          // right-hand sides per pass of the embedded recursion
+constexpr int SFN_SMEM_ROWS = SFN_NG;       // shared-memory rows of nld doubles per warp: z1 / f / q of every function
+// (keeping z2 in four more rows instead of regenerating it for step 4 was SLOWER: 64 KB per CTA leave too little L1)
 
 struct SchurFnArgs {
   const int* gorder;      // P groups, largest first
@@ -443,11 +445,11 @@ __device__ __forceinline__ void sfn_item(const CtxDev& c, const SchurFnArgs& a, 
 #define GPF_SFN_MINB 3
 #endif
 __global__ void __launch_bounds__(128, GPF_SFN_MINB) k_group_schurfn(CtxDev c, SchurFnArgs a) {
-  extern __shared__ __align__(16) double gpf_smem_sfn[];      // per warp: SFN_NG x nld (z1 / finished prior draws, then the right-hand sides q)
+  extern __shared__ __align__(16) double gpf_smem_sfn[];      // per warp: SFN_SMEM_ROWS x nld (z1 / finished prior draws, then the right-hand sides q)
   const int n = c.n, nld = ((n + 7) >> 3) << 3;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Stream rng{c.k0, c.k1};
-  double* zs = gpf_smem_sfn + (size_t)warp * (SFN_NG * nld);
+  double* zs = gpf_smem_sfn + (size_t)warp * (SFN_SMEM_ROWS * nld);
   // Items are handed out FOUR AT A TIME to a CTA (consecutive chains of one prior group): its warps then run the same
   // recursion loops side by side.  The loops of this kernel add up to several times the 32 KB instruction cache; with warps
   // taking items one by one every warp of an SM sat in a different loop (ncu: 87 % instruction-cache hits, 0.8 no-instruction

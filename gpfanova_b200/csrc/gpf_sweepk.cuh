@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(128, GPF_SFN_MINB) k_chain_sweeps(CtxDev c, Sw
   const int n = c.n, nld = ((n + 7) >> 3) << 3;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Stream rng{c.k0, c.k1};
-  double* zs = gpf_smem_swk + (size_t)warp * (SFN_NG * nld);
+  double* zs = gpf_smem_swk + (size_t)warp * (SFN_SMEM_ROWS * nld);
   const long long per_sweep = (long long)c.C * c.P;
   const long long total = (long long)c.C + per_sweep * a.n_sweeps;
   const size_t cols = (size_t)c.H + (size_t)c.f * n;

@@ -556,7 +556,9 @@ class ChainEngine(object):
         n^3 work of the function step on the two half-size blocks; 4: observation likelihood about the
         least-squares fit (balanced designs, nothing missing); 5: function step by the O(n^2) Schur algorithm (uniform grid,
         balanced design, n <= 256, prior groups of at most four functions); 7: all sweeps of a call in one launch without
-        device-wide barriers (chain-resident sweep kernel) where option 5 applies to every prior group"""
+        device-wide barriers (chain-resident sweep kernel) where option 5 applies to every prior group (default 0); 8: a group's
+        functions and slices back to back on the group's own stream (default 1); 9: chains in 1 or 2 independent cohorts of
+        streams (default 1)"""
         self._ck(self._lib.gpf_set_option(self._h, int(option), int(value)))
 
     def get_option(self, option):

@@ -260,6 +260,11 @@ int gpf_sweep(gpf_ctx* ctx, int n_sweeps, int thin, unsigned sweep0, const int* 
  * sampler stage and sweep; per-kernel profiling, gpf_set_profile(ctx, 1), implies 0).  DEFAULT 0: with the function step and
  * three slice variants in flight on every SM the kernel's hot loops miss the 32 KB instruction cache (ncu: 47 % hit rate, 23
  * no-instruction stall cycles per issue) and it runs four times slower than the per-stage kernels.
+ * 8 = where option 5 applies to every prior group: every group's functions and slice kernel run back to back on the group's
+ * own stream (a group's slices start while other groups still draw functions; default 1; bit-identical to 8 = 0);
+ * 9 = 2 additionally splits the chains into two cohorts with their own streams, so that the stage boundaries of one
+ * cohort are filled by the other's kernels (default 1 = one cohort: two measured slower at every chain count -- more
+ * kernel variants per SM for the instruction cache, smaller grids).
  * Where option 5 applies, option 3 defaults to 0: the prior draw then uses the full Cholesky factor of K_o in every
  * kernel of the context; setting option 3 to 1 selects the split factors and with them the dense kernels.
  * gpf_get_option returns the EFFECTIVE value (option 6, read-only: 1 if the design is balanced with nothing missing). */

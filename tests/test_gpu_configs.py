@@ -196,23 +196,29 @@ def test_dense_slice_path_with_many_functions(eng):
 
 
 @pytest.mark.parametrize("levels,reps,n,hc,C,S,thin", [
-    ((3, 3), 5, 256, False, 37, 5, 2),        # cfg5 shape: groups of 1, 2, 2, 4 functions
-    ((3, 3), 2, 100, False, 700, 4, 0),       # more units per sweep than resident warps: chains drift apart
+    ((3, 3), 5, 256, False, 37, 5, 2),        # cfg5 shape: groups of 1, 2, 2, 4 functions (one cohort: fewer than 64 chains)
+    ((3, 3), 2, 100, False, 700, 4, 0),       # more units per sweep than resident warps: chains drift apart; two cohorts
     ((3,), 5, 50, False, 1, 9, 3),            # cfg1 shape: one chain, two groups -- units wait for their chain's y_sigma step
-    ((3, 3), 2, 200, True, 6, 3, 1),          # helmertConvert: classes of 2, 2, 4 share a factorisation
+    ((3, 3), 2, 200, True, 66, 3, 1),         # helmertConvert: classes of 2, 2, 4 share a factorisation; cohorts of 36 + 30
     ((3, 3), 2, 31, False, 9, 4, 1),          # n <= 32: one slot per lane from the start
 ])
-def test_one_launch_sweeps_are_bit_identical(eng, levels, reps, n, hc, C, S, thin):
-    """gpf_set_option 7 (csrc/gpf_sweepk.cuh): all sweeps of a call in one launch, units handed to warps by ticket, a chain's
-    y_sigma step and history row done by the warp that finishes the chain's sweep -- no device-wide barrier anywhere.  Same
-    Philox counters, same arithmetic, same summation order: the stored rows, the final state and the counters must EQUAL
-    those of the kernel-per-sampler sweeps bit for bit (sample/container.py:29-78)."""
+def test_sweep_schedules_are_bit_identical(eng, levels, reps, n, hc, C, S, thin):
+    """Four ways to schedule the same sweeps (sample/container.py:29-78) on the Schur kernels:
+      per-stage kernels (gpf_set_option 8 = 0): y_sigma | all functions | the groups' slice kernels;
+      group pipelines (default): every group's functions -> slices on its own stream;
+      group pipelines with the chains in two independent cohorts of streams (9 = 2);
+      one launch (7 = 1, csrc/gpf_sweepk.cuh): units handed to warps by ticket, a chain's y_sigma step and history row done by
+      the warp that finishes the chain's sweep -- no device-wide barrier anywhere.
+    Same Philox counters, same arithmetic, same summation order: the stored rows, the final state and the counters must be
+    EQUAL bit for bit."""
     x, y, d, groups, F = make_problem(levels, reps, n, hc, seed=n + C)
     outs = []
-    for one_launch in (1, 0):
+    variants = [("stages", {8: 0}), ("pipelines", {}), ("two cohorts", {9: 2}), ("one launch", {7: 1})]
+    for name, opts in variants:
         e = eng.ChainEngine(x, y, d.X, groups, chains=C, seed=77, chain_offset=3)
-        e.set_option(7, one_launch)
-        assert e.get_option(5) == 1 and e.get_option(7) == one_launch
+        for k, v in opts.items():
+            e.set_option(k, v)
+        assert e.get_option(5) == 1 and e.get_option(7) == opts.get(7, 0) and e.get_option(8) == opts.get(8, 1)
         hyper = np.concatenate([np.full((C, 1), -2.0), np.random.default_rng(3).uniform(-0.7, 0.7, size=(C, e.H - 1))], axis=1)
         e.set_state(F=np.zeros((C, e.f, n)), hyper=hyper)
         rows = S if thin <= 0 else S // thin
@@ -222,17 +228,17 @@ def test_one_launch_sweeps_are_bit_identical(eng, levels, reps, n, hc, C, S, thi
         e.status()
         assert got == rows
         launches = e.profile()[1]
-        # a second call continues the same chains (sweep counter, state) -- the launch's first y_sigma units
-        got2 = e.sweep(2, thin=0, history=hist[:min(2, rows)].clone())
+        # a second call continues the same chains (sweep counter, state)
+        e.sweep(2, thin=0, history=hist[:min(2, rows)].clone())
         e.sync()
         e.status()
         F1, h1 = e.get_state()
-        cnt = e.counters()
-        outs.append((hist[:rows].cpu().numpy(), F1, h1, cnt, launches))
+        outs.append((hist[:rows].cpu().numpy(), F1, h1, e.counters(), launches))
         e.close()
-    a, b = outs
-    assert np.isfinite(a[0]).all()
-    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
-    for k in ("chol", "logp", "draws", "slice_steps", "function_chol", "ko_factor", "jitter"):
-        assert a[3][k] == b[3][k], k
-    assert a[4] < b[4] and a[4] <= 2                     # one launch for the whole call
+    ref = outs[0]
+    assert np.isfinite(ref[0]).all()
+    for (name, _), o in zip(variants[1:], outs[1:]):
+        assert np.array_equal(o[0], ref[0]) and np.array_equal(o[1], ref[1]) and np.array_equal(o[2], ref[2]), name
+        for k in ("chol", "logp", "draws", "slice_steps", "function_chol", "ko_factor", "jitter"):
+            assert o[3][k] == ref[3][k], (name, k)
+    assert outs[3][4] <= 2 and outs[3][4] < ref[4]         # one launch for the whole call
