@@ -390,6 +390,13 @@ class Base(SamplerContainer):
             order[s] = [dev_ids[i] for i in ids if i in dev_ids]
         return order
 
+    def prepare(self, n=1, thin=0):
+        """Optional: allocate page-locked result memory for an upcoming sample(n, thin) call (additive; the reference has
+        no counterpart).  The stored states of that call then reach the host by DMA alone -- no staging copy, no page
+        faults -- which is what keeps several GPUs of one box from queueing on the host's memory system.  Returns the
+        bytes pinned."""
+        return self.engine().prepare_results(int(n), thin=int(thin))
+
     def sample(self, n=1, thin=0, verbose=False, random=False):
         """n sweeps of every chain on the device; every `thin`-th state is stored (thin=0: every sweep)."""
         eng = self._push_state()

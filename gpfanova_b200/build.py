@@ -13,10 +13,10 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libgpfanova_b200.so")
-SOURCES = ["gpf_api.cu"]
+SOURCES = ["gpf_api.cu", "gpf_schur_tu.cu", "gpf_sweepk_tu.cu"]      # compiled side by side, then linked
 DEPS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh")))     # every source under csrc/
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "--expt-extended-lambda", "-Xcompiler", "-fPIC", "-shared"]
+              "--expt-extended-lambda", "-Xcompiler", "-fPIC"]
 
 
 def _nvcc():
@@ -39,12 +39,26 @@ def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    objdir = os.path.join(LIBDIR, "obj")
+    os.makedirs(objdir, exist_ok=True)
+    nvcc = _nvcc()
+    procs = []
+    for src in SOURCES:                                  # one nvcc per translation unit, all at once
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        procs.append((cmd, obj, subprocess.Popen(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    objs = []
+    for cmd, obj, pr in procs:
+        _, err = pr.communicate()
+        if verbose:
+            sys.stderr.write(err)
+        if pr.returncode != 0:
+            raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), err[-4000:]))
+        objs.append(obj)
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
-    if verbose:
-        sys.stderr.write(res.stderr)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), res.stderr[-4000:]))
+        raise RuntimeError("link failed:\n%s\n%s" % (" ".join(cmd), res.stderr[-4000:]))
     return LIB
 
 

@@ -14,9 +14,7 @@
 #include "gpf_kernels.cuh"
 #include "gpf_cond.cuh"
 #include "gpf_ops.cuh"
-#include "gpf_schur.cuh"
-#include "gpf_schurfn.cuh"
-#include "gpf_sweepk.cuh"
+#include "gpf_schur_args.cuh"
 
 using namespace gpf;
 
@@ -239,9 +237,8 @@ int launch_all_functions(gpf_ctx* c, unsigned sweep) {
     const int nld = ((c->dev.n + 7) / 8) * 8;
     const size_t smem = (size_t)4 * SFN_SMEM_ROWS * nld * sizeof(double);
     const int grid = std::min((c->dev.C * c->dev.P + 3) / 4, GPF_SFN_MINB * c->sms);
-    k_group_schurfn<<<grid, 128, smem, c->stream>>>(c->dev, a);
+    CK(c, schur_launch_functions(grid, smem, c->stream, c->dev, a));
     ++c->launches;
-    CK(c, cudaGetLastError());
     return GPF_OK;
   }
   const int grid = std::min(c->dev.C * c->dev.P, 2 * c->sms);
@@ -277,14 +274,12 @@ int launch_prior(gpf_ctx* c, int g, int mode, const double* cand, double* outv, 
     const int ng = (int)c->groups[g].size();
     if (c->dev.n <= 256 && ng <= 4) {       // vectors in registers
       const int grid = std::min((c->dev.C + 3) / 4, schur_minb(ng <= 2 ? ng : 4) * c->sms);   // 4 warps per CTA
-      if (ng == 1) k_prior_schur<1><<<grid, 128, 0, st>>>(dev, a);
-      else if (ng == 2) k_prior_schur<2><<<grid, 128, 0, st>>>(dev, a);
-      else k_prior_schur<4><<<grid, 128, 0, st>>>(dev, a);
+      CK(c, schur_launch_prior(ng <= 2 ? ng : 4, grid, 128, 0, st, dev, a));
     } else {
       const int wpc = c->schur_warps[g];
       const size_t smem = (size_t)wpc * schur_warp_doubles(c->dev.n, ng) * sizeof(double);
       const int grid = std::min((c->dev.C + wpc - 1) / wpc, 2 * c->sms);
-      k_prior_schur<0><<<grid, wpc * 32, smem, st>>>(dev, a);
+      CK(c, schur_launch_prior(0, grid, wpc * 32, smem, st, dev, a));
     }
   } else if (c->toeplitz) k_prior<true><<<c->grid, NTHR, c->smem_prior[g], st>>>(dev, a);
   else k_prior<false><<<c->grid, NTHR, c->smem_prior[g], st>>>(dev, a);
@@ -354,9 +349,8 @@ int launch_chain_sweeps(gpf_ctx* c, int n_sweeps, int thin, unsigned sweep0, dou
     a.prog = c->d_swk;
     a.done = c->d_swk + v.C;
     a.err = c->d_swk + 2 * v.C;
-    k_chain_sweeps<<<grid, 128, smem, c->stream>>>(v, a);
+    CK(c, schur_launch_chain_sweeps(grid, smem, c->stream, v, a));
     ++c->launches;
-    CK(c, cudaGetLastError());
     *rows += nrows;
     done += k;
   }
@@ -404,17 +398,13 @@ int enqueue_schur_sweep(gpf_ctx* c, int q, int c0, int cnt, unsigned sweep, cons
     CK(c, cudaMemsetAsync(d2.sched, 0, sizeof(int), aux[slot]));
     SchurFnArgs fa{c->d_gorder + gi, c->share ? c->d_gcls_off : c->d_gcls1_off, c->share ? c->d_cls_off : c->d_cls1_off, c->d_cls_fn,
                    c->d_cls_sid, sweep, 1};
-    k_group_schurfn<<<std::min((cnt + 3) / 4, GPF_SFN_MINB * c->sms), 128, smem, aux[slot]>>>(d2, fa);
-    CK(c, cudaGetLastError());
+    CK(c, schur_launch_functions(std::min((cnt + 3) / 4, GPF_SFN_MINB * c->sms), smem, aux[slot], d2, fa));
     CK(c, cudaMemsetAsync(d2.sched, 0, sizeof(int), aux[slot]));
     PriorArgs pa{g, 4, nullptr, nullptr, c->slice_w[1 + 2 * g], c->slice_w[2 + 2 * g], c->slice_m[1 + 2 * g], c->slice_m[2 + 2 * g],
                  (unsigned)k, sweep, nullptr, 0, nullptr};
     const int ng = (int)c->groups[g].size();
     const int grid = std::min((cnt + 3) / 4, schur_minb(ng <= 2 ? ng : 4) * c->sms);
-    if (ng == 1) k_prior_schur<1><<<grid, 128, 0, aux[slot]>>>(d2, pa);
-    else if (ng == 2) k_prior_schur<2><<<grid, 128, 0, aux[slot]>>>(d2, pa);
-    else k_prior_schur<4><<<grid, 128, 0, aux[slot]>>>(d2, pa);
-    CK(c, cudaGetLastError());
+    CK(c, schur_launch_prior(ng <= 2 ? ng : 4, grid, 128, 0, aux[slot], d2, pa));
     c->launches += 2;
   }
   for (int i = 0; i < 4; ++i)
@@ -980,9 +970,8 @@ int gpf_create(gpf_ctx** out, const gpf_model_desc* d) {
     if (e == cudaSuccess) e = allow_smem(k_group_fused<2>, c->smem_fused[2]);
     if (e == cudaSuccess) e = allow_smem(k_prior<true>, sp);
     if (e == cudaSuccess) e = allow_smem(k_prior<false>, sp);
-    if (e == cudaSuccess) e = allow_smem(k_prior_schur<0>, 112 * 1024);
-    if (e == cudaSuccess) e = allow_smem(k_group_schurfn, (size_t)4 * SFN_SMEM_ROWS * 256 * sizeof(double));
-    if (e == cudaSuccess) e = allow_smem(k_chain_sweeps, (size_t)4 * SFN_SMEM_ROWS * 256 * sizeof(double));
+    if (e == cudaSuccess) e = schur_set_attributes();
+    if (e == cudaSuccess) e = sweepk_set_attributes();
     if (e != cudaSuccess) { c->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return fail(GPF_ERR_CUDA); }
   }
   c->grid = std::min(v.C, 2 * c->sms);

@@ -266,4 +266,33 @@ struct SliceSM {
   }
 };
 
+// ---- shared by the dense kernels (gpf_kernels.cuh, gpf_cond.cuh) and the Schur kernels (gpf_schur*.cuh) ----
+// Base.observationLikelihood (base.py:196-214) for one candidate, given the sum of squared residuals
+__device__ __forceinline__ double obs_loglik_eval(double sse, double nobs, double x, double lb, double ub) {
+  const double sd = sqrt(exp10(x));
+  if (sd < lb || sd > ub) return -(double)INFINITY;
+  return -0.5 * sse / (sd * sd) - nobs * (log(sd) + 0.5 * LOG2PI) - log(ub - lb);
+}
+
+
+// arguments of the prior slice kernels (k_prior, k_prior_schur): modes in gpf_kernels.cuh
+struct PriorArgs {
+  int g, mode;
+  const double* cand;
+  double* outv;
+  double w_s, w_l;
+  int m_s, m_l;
+  unsigned sampler_id, sweep;
+  const double* u_inject;
+  int n_inject;
+  int* nevals;       // mode 2/3: evaluations of that step; mode 4: sigma step, nevals[C + ch]: lengthscale step
+};
+
+// element e of the 2n standard normals of one function draw (z1 = elements [0, n), z2 = [n, 2n)): Box-Muller pair e >> 1
+__device__ __forceinline__ double normal_elem(const Stream& rng, unsigned gch, unsigned sweep, unsigned sid, int e) {
+  double z0, z1;
+  rng.normal_pair(gch, sweep, sid, (unsigned)(e >> 1), z0, z1);
+  return (e & 1) ? z1 : z0;
+}
+
 }  // namespace gpf

@@ -46,12 +46,6 @@ __device__ unsigned long long gpf_ftrace[8];
 #define FT_COUNT
 #endif
 
-// element e of the 2n standard normals of one function draw (z1 = elements [0, n), z2 = [n, 2n)): Box-Muller pair e >> 1
-__device__ __forceinline__ double normal_elem(const Stream& rng, unsigned gch, unsigned sweep, unsigned sid, int e) {
-  double z0, z1;
-  rng.normal_pair(gch, sweep, sid, (unsigned)(e >> 1), z0, z1);
-  return (e & 1) ? z1 : z0;
-}
 
 // ---------------------------------------------------------------------------------------------------------
 // jitchol(K_g + offset I) of every chain (kernel.pyx:55-56 with rbf.pyx:16-19 generated on chip), kept in c.LB for the

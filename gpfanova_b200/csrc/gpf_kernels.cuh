@@ -311,12 +311,6 @@ __global__ void __launch_bounds__(NTHR, 2) k_group_kinv(CtxDev c, int g_first, i
 // which every candidate is O(1):  -N (log sd + log(2 pi)/2) - SSE / (2 sd^2) + log U(lb,ub)(sd),  sd = sqrt(10^x).
 // mode 0: evaluate at cand[ch] -> out[ch].   mode 1: slice step on y_sigma (sample/slice.pyx:24-62).
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double obs_loglik_eval(double sse, double nobs, double x, double lb, double ub) {
-  const double sd = sqrt(exp10(x));
-  if (sd < lb || sd > ub) return -(double)INFINITY;
-  return -0.5 * sse / (sd * sd) - nobs * (log(sd) + 0.5 * LOG2PI) - log(ub - lb);
-}
-
 __global__ void __launch_bounds__(NTHR) k_obs(CtxDev c, int mode, const double* __restrict__ cand, double* __restrict__ outv,
                                               double w, int mstep, unsigned sampler_id, unsigned sweep,
                                               const double* __restrict__ u_inject, int n_inject, int* __restrict__ nevals) {
@@ -385,17 +379,6 @@ __global__ void __launch_bounds__(NTHR) k_obs(CtxDev c, int mode, const double* 
 //   mode 2: slice step on prior{g}_sigma                      mode 3: slice step on prior{g}_lengthscale
 //   mode 4: sigma slice followed by lengthscale slice (sampler ids sampler_id, sampler_id + 1)
 // ---------------------------------------------------------------------------------------------------------
-struct PriorArgs {
-  int g, mode;
-  const double* cand;
-  double* outv;
-  double w_s, w_l;
-  int m_s, m_l;
-  unsigned sampler_id, sweep;
-  const double* u_inject;
-  int n_inject;
-  int* nevals;       // mode 2/3: evaluations of that step; mode 4: sigma step, nevals[C + ch]: lengthscale step
-};
 
 // slice-step state of one chain, kept in shared memory and advanced by thread 0 only (keeps the registers of the
 // other 255 threads for the factorisation)

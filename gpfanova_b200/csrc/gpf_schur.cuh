@@ -16,11 +16,10 @@
 // algorithms" (1995) -- for positive definite T the computed factor satisfies a Cholesky-like backward error bound.
 #pragma once
 #include "gpf_common.cuh"
+#include "gpf_schur_args.cuh"
 
 namespace gpf {
 
-// shared memory per warp, in doubles: us, v, e (rotation 1 - rho^2 per step), tab, r[ng][n]
-__host__ __device__ inline size_t schur_warp_doubles(int n, int ng) { return (size_t)(4 + ng) * n; }
 
 struct SchurOut { double logdet, quad; bool ok; };
 
@@ -336,12 +335,6 @@ __device__ __forceinline__ int next_chain_warp(int* sched, int lane) {
   return (int)__reduce_max_sync(FULLMASK, t);      // (REDUX writes a uniform register: the chain loop is provably convergent)
 }
 
-// same modes as k_prior (PriorArgs): 0/1 evaluate sigma / lengthscale candidate, 2/3 slice step, 4 fused sigma + ls
-// resident CTAs per SM of the register-resident variants: groups of one or two functions need fewer registers
-#ifndef GPF_SCHUR_MINB_SMALL
-#define GPF_SCHUR_MINB_SMALL 3
-#endif
-__host__ __device__ constexpr int schur_minb(int NG) { return NG == 0 ? 2 : (NG <= 2 ? GPF_SCHUR_MINB_SMALL : 3); }
 
 // one chain's slice step(s) on the hyper-parameters of prior group a.g (all lanes of the warp; modes as k_prior)
 template <int NG>   // NG > 0: register-resident evaluation (n <= 256, group size <= NG); 0: shared-memory evaluation

@@ -21,24 +21,9 @@
 // like a failed dpotrf.
 #pragma once
 #include "gpf_schur.cuh"
-#include "gpf_cond.cuh"
 
 namespace gpf {
 
-constexpr int SFN_NG = 4;          // functions per prior group held in registers
-constexpr int SFN_NC = 2;          // right-hand sides per pass of the embedded recursion
-constexpr int SFN_SMEM_ROWS = SFN_NG;       // shared-memory rows of nld doubles per warp: z1 / f / q of every function
-// (keeping z2 in four more rows instead of regenerating it for step 4 was SLOWER: 64 KB per CTA leave too little L1)
-
-struct SchurFnArgs {
-  const int* gorder;      // P groups, largest first
-  const int* gcls_off;    // P+1
-  const int* cls_off;     // CSR offsets of the classes into cls_fn / cls_sid
-  const int* cls_fn;
-  const unsigned* cls_sid;
-  unsigned sweep;
-  int ngroups;            // groups of this launch: gorder[0 .. ngroups)  (0: all P groups)
-};
 
 // Register layouts.  The recursion works on two sets of vectors that only meet in the scalars rho, e, 1/g of a step:
 //   * the COLUMN set (column k of L, v, right-hand sides / prior-draw accumulators) is live on positions >= k: it starts at
@@ -441,9 +426,7 @@ __device__ __forceinline__ void sfn_item(const CtxDev& c, const SchurFnArgs& a, 
   __syncwarp();
 }
 
-#ifndef GPF_SFN_MINB
-#define GPF_SFN_MINB 3
-#endif
+#ifndef GPF_NO_SCHURFN_KERNEL      // (translation units that only need sfn_item: gpf_sweepk_tu.cu)
 __global__ void __launch_bounds__(128, GPF_SFN_MINB) k_group_schurfn(CtxDev c, SchurFnArgs a) {
   extern __shared__ __align__(16) double gpf_smem_sfn[];      // per warp: SFN_SMEM_ROWS x nld (z1 / finished prior draws, then the right-hand sides q)
   const int n = c.n, nld = ((n + 7) >> 3) << 3;
@@ -471,5 +454,7 @@ __global__ void __launch_bounds__(128, GPF_SFN_MINB) k_group_schurfn(CtxDev c, S
     else sfn_item<1>(c, a, rng, ch, g, lane, zs);
   }
 }
+
+#endif
 
 }  // namespace gpf

@@ -20,20 +20,6 @@
 
 namespace gpf {
 
-struct SweepKArgs {
-  SchurFnArgs fn;            // class lists of the function step (fn.sweep unused)
-  unsigned sweep0;           // Philox sweep counter of the launch's first sweep
-  int n_sweeps, thin;        // thin <= 0: every sweep is stored
-  double* history;           // rows x C x (H + f n), or null
-  long long rows_cap;
-  const unsigned* sid_sigma; // P: sampler id of prior{g}_sigma (lengthscale: + 1)
-  const double* slice_w;     // 1 + 2P slice widths / step budgets in hyper order
-  const int* slice_m;
-  unsigned sid_y;
-  int* prog;                 // C: number of sweeps of this launch whose y_sigma step is done (zeroed before the launch)
-  int* done;                 // C: group units of this launch finished (zeroed before the launch)
-  int* err;                  // set if a wait ran out of patience (never in a correct run; keeps a bug from hanging the GPU)
-};
 
 // the y_sigma slice step of one chain by one warp; the residual sum of squares in k_obs's summation order
 __device__ __forceinline__ void sweepk_ysigma(const CtxDev& c, const SweepKArgs& a, const Stream& rng, int ch, unsigned sweep, int lane) {

@@ -216,7 +216,7 @@ __device__ __forceinline__ void sts2(unsigned a, double x, double y) {
 // only needs that lane's values), so the dependent chain per column is mul -> fma -> shfl -> rsqrt.  dpotf2's failure
 // rule (pivot <= 0 or NaN) is evaluated once from the running minimum.  A separate (noinline) function on purpose:
 // it gets its own register allocation instead of competing with the caller's live state (measured 3x faster).
-__device__ __noinline__ bool potrf_tile(double* DT_, double* rinv_, double* piv_) {
+static __device__ __noinline__ bool potrf_tile(double* DT_, double* rinv_, double* piv_) {
   const int lane = threadIdx.x & 31;
   const unsigned DT = smem_u32(DT_), rinv_out = smem_u32(rinv_), piv_out = smem_u32(piv_);
   double a[32];
@@ -257,7 +257,7 @@ __device__ __noinline__ bool potrf_tile(double* DT_, double* rinv_, double* piv_
 // X <- X L^-T for one 32-row block held in a shared-memory panel slot (row stride PS), in place; lane = row.
 // DT: L column-major (DT[c*32 + r] = L[r][c]), rinv[c] = 1/L[c][c].  Rows with zero_row set are replaced by zeros.
 // Returns the sum of squares of the lane's solved row.  Separate function for the same reason as potrf_tile.
-__device__ __noinline__ double trsm_slot(double* slot_, const double* DT_, const double* rinv_, bool zero_row) {
+static __device__ __noinline__ double trsm_slot(double* slot_, const double* DT_, const double* rinv_, bool zero_row) {
   const int lane = threadIdx.x & 31;
   const unsigned row = smem_u32(slot_) + 8u * (lane * PS), DT = smem_u32(DT_), rinv = smem_u32(rinv_);
   double a[32];

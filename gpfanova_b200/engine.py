@@ -397,6 +397,7 @@ class ChainEngine(object):
         self._h = h
         self.sweeps_done = 0
         self._dev_hist = None
+        self._pinned = []                                     # result blocks from prepare_results()
         for opt, val in _env_options():                       # GPFANOVA_B200_OPTIONS="7=1,3=0": A/B runs of the same program
             self.set_option(opt, val)
 
@@ -565,6 +566,26 @@ class ChainEngine(object):
         """effective value of an option (5: O(n^2) Schur function step active; 3: split factors of K_o; 6: balanced design; 7: one-launch sweeps active)"""
         return int(self._lib.gpf_get_option(self._h, int(option)))
 
+    def prepare_results(self, n_sweeps, thin=0):
+        """Page-locked result memory for an upcoming sweep_host(n_sweeps, thin) call, allocated NOW (cudaHostAlloc costs
+        ~0.4 s per GB -- too much to pay inside a sampling call, so nothing is pinned behind the caller's back).  A prepared
+        block is consumed by the next sweep_host call it is large enough for: the stored rows then go device -> result by
+        DMA alone.  Without one, results land in ordinary pageable memory through the staging pipeline."""
+        step = 1 if thin <= 0 else int(thin)
+        rows = int(n_sweeps) // step
+        if rows <= 0:
+            return 0
+        nel = rows * self.C * (self.H + self.f * self.n)
+        self._pinned.append(torch.empty(nel, dtype=torch.float64, pin_memory=True))
+        return nel * 8
+
+    def _take_pinned(self, nel):
+        best = None
+        for k, t in enumerate(self._pinned):
+            if t.numel() >= nel and (best is None or t.numel() < self._pinned[best].numel()):
+                best = k
+        return None if best is None else self._pinned.pop(best)
+
     def sweep_host(self, n_sweeps=1, thin=0, order=None, stage_bytes=96 << 20, max_chunk_sweeps=None, on_chunk=None):
         """sweep() with the stored states delivered to the host as ONE numpy array (rows, C, H + f*n).
 
@@ -587,10 +608,44 @@ class ChainEngine(object):
         crow = max(1, min(cap, -(-rows_total // 4)))
         if max_chunk_sweeps:
             crow = max(1, min(crow, int(max_chunk_sweeps) // step))
-        if getattr(self, "_stage", None) is None or self._stage[0].shape[0] < cap:
-            self._stage = [torch.empty((cap, self.C, cols), dtype=torch.float64, pin_memory=True) for _ in range(2)]
+        if self._dev_hist is None or self._dev_hist[0].shape[0] < cap:
             self._dev_hist = [torch.empty((cap, self.C, cols), dtype=torch.float64, device=self.dev) for _ in range(2)]
         t_begin = time.perf_counter()
+        pinned = self._take_pinned(rows_total * self.C * cols)
+        if pinned is not None:
+            # ---- prepared result memory (prepare_results): every chunk goes device -> result by DMA on the copy stream; no
+            # staging copy, no page faults, no host threads -- the path that scales when eight ranks share one host
+            out_t = pinned[:rows_total * self.C * cols].view(rows_total, self.C, cols)
+            base_ptr = out_t.data_ptr()
+            inflight, done, row0, i = [], 0, 0, 0
+            while done < n_sweeps:
+                k = min(crow * step, n_sweeps - done)
+                rows = k // step
+                b = i % 2
+                if len(inflight) == 2:                         # buffer b is free once its copy (chunk i-2) has landed
+                    self._ck(self._lib.gpf_wait_event(self._h, inflight.pop(0)))
+                sub = None if order is None else order[done:done + k]
+                if rows == 0:
+                    self.sweep(k, thin=step, order=sub)
+                else:
+                    got = self.sweep(k, thin=step, history=self._dev_hist[b][:rows], order=sub)
+                    self._ck(self._lib.gpf_memcpy_d2h_event(self._h, C.c_void_p(base_ptr + row0 * rowbytes),
+                                                            _ptr(self._dev_hist[b]), got * rowbytes, b))
+                    inflight.append(b)
+                    row0 += got
+                    i += 1
+                done += k
+                if on_chunk is not None:
+                    on_chunk(done)
+            for b in inflight:
+                self._ck(self._lib.gpf_wait_event(self._h, b))
+            self.sync()
+            if os.environ.get("GPFANOVA_B200_TIMING"):
+                sys.stderr.write("sweep_host: rows %d chunk rows %d  prepared (pinned) result  total %.3f s\n" % (
+                    row0, crow, time.perf_counter() - t_begin))
+            return out_t.numpy()[:row0]
+        if getattr(self, "_stage", None) is None or self._stage[0].shape[0] < cap:
+            self._stage = [torch.empty((cap, self.C, cols), dtype=torch.float64, pin_memory=True) for _ in range(2)]
         out = np.empty((rows_total, self.C, cols))
         # Fresh pageable memory: the first write to every 4 KB page faults (~2 GB/s for ONE thread, but the faults of
         # several threads run side by side: 26 GB/s with eight, tools/pagefault_probe.py).  Background threads touch the
@@ -761,6 +816,9 @@ class EngineGroup(object):
             for k, v in e.counters(clear=clear).items():
                 out[k] = out.get(k, 0) + v
         return out
+
+    def prepare_results(self, n_sweeps, thin=0):
+        return sum(e.prepare_results(n_sweeps, thin=thin) for e in self.engines)
 
     def sweep_host(self, n_sweeps=1, thin=0, order=None, on_chunk=None, **kw):
         from concurrent.futures import ThreadPoolExecutor

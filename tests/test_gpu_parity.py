@@ -651,3 +651,26 @@ def test_history_pipeline_chunking(eng):
     e = make_engine(eng, c, chains=C, seed=9)
     assert e.sweep_host(3, thin=5).shape[0] == 0
     e.close()
+
+
+def test_prepared_results_equal_staged_results(eng):
+    """ChainEngine.prepare_results / Base.prepare: stored rows delivered by DMA straight into page-locked result memory
+    must equal the rows delivered through the pinned-staging + host-copy pipeline, with thinning and a partial last chunk;
+    a prepared block is consumed by one call, and a block that is too small is left alone."""
+    c = load_case("oneway_n50")
+    C, S, thin = 3, 23, 2
+    outs = []
+    for prepared in (False, True):
+        e = make_engine(eng, c, chains=C, seed=9)
+        if prepared:
+            assert e.prepare_results(4, thin=thin) > 0          # too small for the call below: stays in the pool
+            assert e.prepare_results(S, thin=thin) == (S // thin) * C * (e.H + e.f * e.n) * 8
+        out = e.sweep_host(S, thin=thin, stage_bytes=4 * C * (5 + 3 * 50) * 8)
+        e.status()
+        if prepared:
+            assert len(e._pinned) == 1 and e._pinned[0].numel() == (4 // thin) * C * (e.H + e.f * e.n)
+            out2 = e.sweep_host(4, thin=thin)                   # consumes the small block
+            assert len(e._pinned) == 0 and out2.shape[0] == 2
+        outs.append(np.array(out, copy=True))
+        e.close()
+    assert outs[0].shape == (S // thin, C, outs[0].shape[2]) and np.array_equal(outs[0], outs[1])
