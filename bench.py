@@ -209,6 +209,20 @@ def ncu_traffic(kernel_file, n, chains_per_gpu):
         return None
 
 
+def ncu_metric(kernel_file, metric, n, chains_per_gpu):
+    """first value of `metric` in the committed ncu summary of the dominant kernel (same capture as ncu_traffic)"""
+    if n != 256 or chains_per_gpu != 4096:
+        return None
+    try:
+        for line in open(os.path.join(ROOT, "profiles", kernel_file)):
+            t = line.split()
+            if len(t) >= 2 and t[0] == metric:
+                return float(t[1])
+    except (OSError, ValueError):
+        pass
+    return None
+
+
 def flops_model(n, f, P, ng_list, counts, schur, schurfn):
     """algorithmic FP64 flops of what was executed (counted by the kernels), DESIGN.md 5.
     Schur recursion on an n x n Toeplitz matrix in the scaled (square-root-free) form: per step and live position
@@ -367,14 +381,18 @@ def main():
                             "k_prior (sigma+lengthscale slice steps: dense GP log-likelihood)", P * args.steps)}
     dom = max(("kinv", "function", "prior_slice"), key=lambda k: prof[k])
     tf = {k: (fm[k] / (prof[k] * 1e-3) / 1e12 if prof[k] > 0 else 0.0) for k in kern}
-    ncu_file = {"function": "ncu_r02_k_group_schurfn.txt" if schurfn else "ncu_r02_k_group_fused.txt",
-                "prior_slice": "ncu_r02_k_prior_schur.txt"}.get(dom, "")
+    ncu_file = {"function": "ncu_r02_final_k_group_schurfn.txt" if schurfn else "ncu_r02_k_group_fused.txt",
+                "prior_slice": "ncu_r02_final_k_prior_schur.txt"}.get(dom, "")
     roofline = {"bound": "tensor", "kernel": kern[dom][0], "achieved": tf[dom], "peak": peak, "unit": "TFLOP/s",
                 "frac": tf[dom] / peak,
                 "bound_note": "FP64 pipe: B200 issues FP64 FMA and FP64 tensor (DMMA) work at the same rate (measured 33.98 / "
                               "37.09 TFLOP/s sustained, profiles/fp64_peak_r02.json); the Schur kernels are FMA work, the dense "
                               "kernels DMMA -- one denominator for both",
                 "traffic": ncu_traffic(ncu_file, n, C),
+                "fp64_pipe_active_pct_ncu": ncu_metric(ncu_file, "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", n, C),
+                "pipe_note": "achieved/frac count ALGORITHMIC flops only (live positions of the recursion); the per-step scalars and "
+                             "the dead SIMD lanes of the register layout also occupy the FP64 pipe, which ncu sees busy for "
+                             "fp64_pipe_active_pct_ncu percent of the cycles",
                 "traffic_note": "bytes per launch from profiles/%s (one ncu --set full capture of this workload).  Algorithmic "
                                 "HBM bytes per sweep: the function values written (%.0f MB) and read back by the slice kernels "
                                 "and the y_sigma kernel; every matrix is generated and consumed in registers" % (

@@ -575,9 +575,18 @@ class ChainEngine(object):
         rows = int(n_sweeps) // step
         if rows <= 0:
             return 0
-        nel = rows * self.C * (self.H + self.f * self.n)
+        cols = self.H + self.f * self.n
+        nel = rows * self.C * cols
         self._pinned.append(torch.empty(nel, dtype=torch.float64, pin_memory=True))
+        self._ensure_dev_hist(max(1, int(self._STAGE_BYTES // (self.C * cols * 8))), 4)     # (cudaMalloc belongs here too)
         return nel * 8
+
+    _STAGE_BYTES = 96 << 20
+
+    def _ensure_dev_hist(self, cap, nbuf):
+        cols = self.H + self.f * self.n
+        if self._dev_hist is None or self._dev_hist[0].shape[0] < cap or len(self._dev_hist) < nbuf:
+            self._dev_hist = [torch.empty((cap, self.C, cols), dtype=torch.float64, device=self.dev) for _ in range(nbuf)]
 
     def _take_pinned(self, nel):
         best = None
@@ -586,7 +595,7 @@ class ChainEngine(object):
                 best = k
         return None if best is None else self._pinned.pop(best)
 
-    def sweep_host(self, n_sweeps=1, thin=0, order=None, stage_bytes=96 << 20, max_chunk_sweeps=None, on_chunk=None):
+    def sweep_host(self, n_sweeps=1, thin=0, order=None, stage_bytes=_STAGE_BYTES, max_chunk_sweeps=None, on_chunk=None):
         """sweep() with the stored states delivered to the host as ONE numpy array (rows, C, H + f*n).
 
         Double-buffered pipeline: the stored rows of a chunk of sweeps are copied device -> PINNED staging buffer on the
@@ -608,21 +617,23 @@ class ChainEngine(object):
         crow = max(1, min(cap, -(-rows_total // 4)))
         if max_chunk_sweeps:
             crow = max(1, min(crow, int(max_chunk_sweeps) // step))
-        if self._dev_hist is None or self._dev_hist[0].shape[0] < cap:
-            self._dev_hist = [torch.empty((cap, self.C, cols), dtype=torch.float64, device=self.dev) for _ in range(2)]
-        t_begin = time.perf_counter()
         pinned = self._take_pinned(rows_total * self.C * cols)
+        nbuf = 4 if pinned is not None else 2                  # device history buffers (= chunks that may be in flight)
+        self._ensure_dev_hist(cap, nbuf)
+        t_begin = time.perf_counter()
         if pinned is not None:
             # ---- prepared result memory (prepare_results): every chunk goes device -> result by DMA on the copy stream; no
-            # staging copy, no page faults, no host threads -- the path that scales when eight ranks share one host
+            # staging copy, no page faults, no host threads -- the path that scales when eight ranks share one host.  Four
+            # device buffers: the host queues up to three chunks ahead of the GPU, so a descheduled host thread does not
+            # leave the GPU idle between chunks
             out_t = pinned[:rows_total * self.C * cols].view(rows_total, self.C, cols)
             base_ptr = out_t.data_ptr()
             inflight, done, row0, i = [], 0, 0, 0
             while done < n_sweeps:
                 k = min(crow * step, n_sweeps - done)
                 rows = k // step
-                b = i % 2
-                if len(inflight) == 2:                         # buffer b is free once its copy (chunk i-2) has landed
+                b = i % 4
+                if len(inflight) == 4:                         # buffer b is free once its copy (chunk i-4) has landed
                     self._ck(self._lib.gpf_wait_event(self._h, inflight.pop(0)))
                 sub = None if order is None else order[done:done + k]
                 if rows == 0:
