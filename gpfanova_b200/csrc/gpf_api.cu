@@ -234,10 +234,7 @@ int launch_all_functions(gpf_ctx* c, unsigned sweep) {
     // uniform grid: both K_o and C = I + c K_o are Toeplitz -- O(n^2) Schur recursions, one warp per (group, chain)
     SchurFnArgs a{c->d_gorder, c->share ? c->d_gcls_off : c->d_gcls1_off, c->share ? c->d_cls_off : c->d_cls1_off, c->d_cls_fn,
                   c->d_cls_sid, sweep, 0};
-    const int nld = ((c->dev.n + 7) / 8) * 8;
-    const size_t smem = (size_t)4 * SFN_SMEM_ROWS * nld * sizeof(double);
-    const int grid = std::min((c->dev.C * c->dev.P + 3) / 4, GPF_SFN_MINB * c->sms);
-    CK(c, schur_launch_functions(grid, smem, c->stream, c->dev, a));
+    CK(c, schur_launch_functions(c->dev.C * c->dev.P, c->sms, c->stream, c->dev, a));
     ++c->launches;
     return GPF_OK;
   }
@@ -385,8 +382,6 @@ int enqueue_schur_sweep(gpf_ctx* c, int q, int c0, int cnt, unsigned sweep, cons
   ++c->launches;
   CK(c, cudaGetLastError());
   CK(c, cudaEventRecord(fork, st));
-  const int nld = ((dv.n + 7) / 8) * 8;
-  const size_t smem = (size_t)4 * SFN_SMEM_ROWS * nld * sizeof(double);
   bool forked[4] = {false, false, false, false};
   for (size_t i = 0; i < todo.size(); ++i) {
     const int k = todo[i].first, g = todo[i].second, slot = g % 4;
@@ -398,7 +393,7 @@ int enqueue_schur_sweep(gpf_ctx* c, int q, int c0, int cnt, unsigned sweep, cons
     CK(c, cudaMemsetAsync(d2.sched, 0, sizeof(int), aux[slot]));
     SchurFnArgs fa{c->d_gorder + gi, c->share ? c->d_gcls_off : c->d_gcls1_off, c->share ? c->d_cls_off : c->d_cls1_off, c->d_cls_fn,
                    c->d_cls_sid, sweep, 1};
-    CK(c, schur_launch_functions(std::min((cnt + 3) / 4, GPF_SFN_MINB * c->sms), smem, aux[slot], d2, fa));
+    CK(c, schur_launch_functions(cnt, c->sms, aux[slot], d2, fa));
     CK(c, cudaMemsetAsync(d2.sched, 0, sizeof(int), aux[slot]));
     PriorArgs pa{g, 4, nullptr, nullptr, c->slice_w[1 + 2 * g], c->slice_w[2 + 2 * g], c->slice_m[1 + 2 * g], c->slice_m[2 + 2 * g],
                  (unsigned)k, sweep, nullptr, 0, nullptr};

@@ -53,7 +53,8 @@ struct SweepKArgs {
 // ---- launchers (defined next to the kernels) ----
 // NG = 1, 2, 4: register-resident variants (block 128, no shared memory); 0: shared-memory variant
 cudaError_t schur_launch_prior(int NG, int grid, int block, size_t smem, cudaStream_t st, const CtxDev& dev, const PriorArgs& a);
-cudaError_t schur_launch_functions(int grid, size_t smem, cudaStream_t st, const CtxDev& dev, const SchurFnArgs& a);
+// items = chains x groups of the launch; block / grid / shared memory are chosen next to the kernel (GPF_SFN_WPB warps per CTA)
+cudaError_t schur_launch_functions(int items, int sms, cudaStream_t st, const CtxDev& dev, const SchurFnArgs& a);
 cudaError_t schur_launch_chain_sweeps(int grid, size_t smem, cudaStream_t st, const CtxDev& dev, const SweepKArgs& a);
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) of the kernels above
 cudaError_t schur_set_attributes();

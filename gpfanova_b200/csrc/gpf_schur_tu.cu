@@ -2,6 +2,7 @@
 #include "../../include/gpfanova_b200.h"
 #include "gpf_schur.cuh"
 #include "gpf_schurfn.cuh"
+#include <algorithm>
 
 namespace gpf {
 
@@ -13,15 +14,18 @@ cudaError_t schur_launch_prior(int NG, int grid, int block, size_t smem, cudaStr
   return cudaGetLastError();
 }
 
-cudaError_t schur_launch_functions(int grid, size_t smem, cudaStream_t st, const CtxDev& dev, const SchurFnArgs& a) {
-  k_group_schurfn<<<grid, 128, smem, st>>>(dev, a);
+cudaError_t schur_launch_functions(int items, int sms, cudaStream_t st, const CtxDev& dev, const SchurFnArgs& a) {
+  const int nld = ((dev.n + 7) / 8) * 8;
+  const size_t smem = (size_t)GPF_SFN_WPB * SFN_SMEM_ROWS * nld * sizeof(double);
+  const int grid = std::min((items + GPF_SFN_WPB - 1) / GPF_SFN_WPB, (12 / GPF_SFN_WPB) * sms);
+  k_group_schurfn<<<grid, 32 * GPF_SFN_WPB, smem, st>>>(dev, a);
   return cudaGetLastError();
 }
 
 cudaError_t schur_set_attributes() {
   cudaError_t e = cudaFuncSetAttribute(k_prior_schur<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(k_group_schurfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)4 * SFN_SMEM_ROWS * 256 * sizeof(double)));
+    e = cudaFuncSetAttribute(k_group_schurfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)GPF_SFN_WPB * SFN_SMEM_ROWS * 256 * sizeof(double)));
   return e;
 }
 

@@ -427,13 +427,16 @@ __device__ __forceinline__ void sfn_item(const CtxDev& c, const SchurFnArgs& a, 
 }
 
 #ifndef GPF_NO_SCHURFN_KERNEL      // (translation units that only need sfn_item: gpf_sweepk_tu.cu)
-__global__ void __launch_bounds__(128, GPF_SFN_MINB) k_group_schurfn(CtxDev c, SchurFnArgs a) {
+#ifndef GPF_SFN_WPB
+#define GPF_SFN_WPB 4              // warps per CTA (12 warps per SM by registers: 12 / GPF_SFN_WPB CTAs per SM)
+#endif
+__global__ void __launch_bounds__(32 * GPF_SFN_WPB, 12 / GPF_SFN_WPB) k_group_schurfn(CtxDev c, SchurFnArgs a) {
   extern __shared__ __align__(16) double gpf_smem_sfn[];      // per warp: SFN_SMEM_ROWS x nld (z1 / finished prior draws, then the right-hand sides q)
   const int n = c.n, nld = ((n + 7) >> 3) << 3;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Stream rng{c.k0, c.k1};
   double* zs = gpf_smem_sfn + (size_t)warp * (SFN_SMEM_ROWS * nld);
-  // Items are handed out FOUR AT A TIME to a CTA (consecutive chains of one prior group): its warps then run the same
+  // Items are handed out GPF_SFN_WPB AT A TIME to a CTA (consecutive chains of one prior group): its warps then run the same
   // recursion loops side by side.  The loops of this kernel add up to several times the 32 KB instruction cache; with warps
   // taking items one by one every warp of an SM sat in a different loop (ncu: 87 % instruction-cache hits, 0.8 no-instruction
   // stall cycles per issue).
@@ -443,7 +446,7 @@ __global__ void __launch_bounds__(128, GPF_SFN_MINB) k_group_schurfn(CtxDev c, S
     __syncthreads();
     if (threadIdx.x == 0) s_ticket = atomicAdd(c.sched, 1);
     __syncthreads();
-    const int base = s_ticket * 4;
+    const int base = s_ticket * GPF_SFN_WPB;
     if (base >= nitem) break;
     const int item = (int)__reduce_max_sync(FULLMASK, (unsigned)(base + warp));
     if (item >= nitem) continue;
