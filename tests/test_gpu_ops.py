@@ -319,3 +319,25 @@ def test_posterior_summaries_match_reference_long_chains_cfg2():
     zF = np.abs(gpu_F_mean - ref_F_mean) / np.sqrt(ref_F_se ** 2 + gpu_F_se ** 2 + (0.1 * post_sd_F) ** 2)
     assert zF.max() < 5.0, (zF.max(), np.unravel_index(zF.argmax(), zF.shape))
     assert np.sqrt(np.mean((gpu_F_mean - g["F_true"].T) ** 2)) < np.sqrt(np.mean((ref_F_mean - g["F_true"].T) ** 2)) + 0.02
+
+
+def test_prepare_keeps_results_identical_and_is_optional():
+    """FANOVA.prepare(n, thin) (additive API): page-locked result memory for the next sample() call.  Same seed, same data:
+    the stored histories with and without it are equal bit for bit; the second sample() call (nothing prepared) falls back to
+    the pageable path."""
+    import itertools
+    from gpfanova_b200 import fanova
+    n = 64
+    x = np.linspace(-1, 1, n)[:, None]
+    eff = np.array(list(itertools.product(range(2), range(2))) * 2)
+    rng = np.random.default_rng(4)
+    y = np.sin(3 * x) + 0.1 * rng.standard_normal((n, eff.shape[0]))
+    hist = []
+    for prepared in (False, True):
+        m = fanova.FANOVA(x, y, eff, interactions=True, chains=6, seed=12, device=0, store_chains=True)
+        if prepared:
+            assert m.prepare(8, thin=2) == 4 * 6 * (m.H + m.f * n) * 8
+        m.sample(8, thin=2)
+        m.sample(3, thin=1)
+        hist.append((m.chain_history(), m.parameter_history.to_numpy(dtype=float)))
+    assert hist[0][0].shape[0] == 7 and np.array_equal(hist[0][0], hist[1][0]) and np.array_equal(hist[0][1], hist[1][1])
