@@ -5,14 +5,19 @@ long chains must agree statistically").  TEST INFRASTRUCTURE ONLY.
 
     python oracle/make_posterior_summary.py [--case oneway_n16] [--chains 8] [--sweeps 4000] [--burn 300]   (~10 min, 8 cores)
     python oracle/make_posterior_summary.py --case twoway_n100 --chains 8 --sweeps 500 --burn 100            (~15 min, 8 cores)
+    python oracle/make_posterior_summary.py --case twoway_n256 --chains 8 --sweeps 500 --burn 100            (~10 min, 8 cores)
 
 Cases: oneway_n16 (one-way, 3 levels x 3 replicates, n = 16); twoway_n100 (BASELINE config 2: 3 x 3 levels with
-interaction, 5 replicates, n = 100 time points).
+interaction, 5 replicates, n = 100 time points); twoway_n256 (BASELINE config 5, the bench workload: the same design at
+n = 256 time points).
 """
 import argparse
 import multiprocessing as mp
 import os
 import sys
+
+for _v in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):      # one chain per core: BLAS threads set before
+    os.environ.setdefault(_v, "1")                                            # numpy loads (8 threads x 8 chains is 5x slower)
 
 import numpy as np
 
@@ -29,6 +34,8 @@ def problem(case="oneway_n16"):
         n, eff, inter = 16, synthetic.effects((3,), 3), False
     elif case == "twoway_n100":
         n, eff, inter = 100, synthetic.effects((3, 3), 5), True
+    elif case == "twoway_n256":
+        n, eff, inter = 256, synthetic.effects((3, 3), 5), True
     else:
         raise ValueError(case)
     x = np.linspace(-1, 1, n)[:, None]

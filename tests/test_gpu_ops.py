@@ -285,10 +285,12 @@ def test_model_diagnostics_and_large_history_pipeline():
 
 
 # ------------------------------------------------------------------------------------------------ statistical parity, cfg2 size
-def test_posterior_summaries_match_reference_long_chains_cfg2():
-    """two-way 3 x 3 with interaction, 5 replicates, n = 100 (BASELINE config 2): pooled posterior means of many GPU chains
-    against 8 long chains of the unmodified reference (tests/golden/posterior_twoway_n100.npz)"""
-    path = os.path.join(GOLDEN, "posterior_twoway_n100.npz")
+@pytest.mark.parametrize("case", ["twoway_n100", "twoway_n256"])
+def test_posterior_summaries_match_reference_long_chains_cfg2(case):
+    """two-way 3 x 3 with interaction, 5 replicates, n = 100 (BASELINE config 2) and n = 256 (config 5, the bench workload:
+    everything on the Schur kernels): pooled posterior means of many GPU chains against 8 long chains of the unmodified
+    reference (tests/golden/posterior_<case>.npz, oracle/make_posterior_summary.py)"""
+    path = os.path.join(GOLDEN, "posterior_%s.npz" % case)
     if not os.path.exists(path):
         pytest.skip("golden not minted")
     from gpfanova_b200 import fanova
