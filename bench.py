@@ -428,7 +428,10 @@ def main():
         torch.cuda.synchronize()
         first_s = time.perf_counter() - t0
         model.set_chain_state(hyper=start)           # the timed call re-uploads every chain's state from the host
-        pinned_bytes = model.prepare(ksteps, thin=1)  # page-locked result buffer for the timed call (allocated outside it)
+        try:
+            pinned_bytes = model.prepare(ksteps, thin=1)  # page-locked result buffer for the timed call (allocated outside it)
+        except RuntimeError:                              # (no page-locked memory to be had: pageable results, staged pipeline)
+            pinned_bytes = 0
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()

@@ -2,7 +2,7 @@
 //   variant 0 = schur_eval_reg (normalised generator, 8 slots per lane throughout)
 //   variant 1 = schur_eval_staged (scaled generator, 8 -> 4 -> 2 -> 1 slots per lane)
 // timed alone on the SM (latency: one warp per SM) and at the kernel's occupancy (444 CTAs x 4 warps), values compared.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-extended-lambda -lineinfo -I../gpfanova_b200/csrc -o schur_micro schur_micro.cu
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-extended-lambda -lineinfo -I../gpfanova_b200/csrc -I.. [-DMINB=2|3|4] -o schur_micro schur_micro.cu
 #ifndef MINB
 #define MINB 3
 #endif
