@@ -52,6 +52,7 @@ SHAPES = [
     ("odd_n101",             (3, 3),  2,    101, False, "uniform",    3,      2,      (0,)),        # no split: full-size fused kernel
     ("nonuniform_n72",       (3, 3),  2,    72,  False, "random",     3,      2,      (2,)),        # element-wise RBF source
     ("cokol9x9_hc_n200",     (9, 9),  1,    200, True,  "uniform",    2,      1,      (1,)),        # cfg4 shape: 64-function class
+    ("threeway_n40",         (2, 2, 2), 2,  40,  False, "uniform",    4,      2,      (0, 3)),      # seven prior groups on four streams
 ]
 
 
@@ -201,6 +202,7 @@ def test_dense_slice_path_with_many_functions(eng):
     ((3,), 5, 50, False, 1, 9, 3),            # cfg1 shape: one chain, two groups -- units wait for their chain's y_sigma step
     ((3, 3), 2, 200, True, 66, 3, 1),         # helmertConvert: classes of 2, 2, 4 share a factorisation; cohorts of 36 + 30
     ((3, 3), 2, 31, False, 9, 4, 1),          # n <= 32: one slot per lane from the start
+    ((2, 2, 2), 2, 40, False, 70, 3, 1),      # seven prior groups of one function: groups share the four auxiliary streams
 ])
 def test_sweep_schedules_are_bit_identical(eng, levels, reps, n, hc, C, S, thin):
     """Four ways to schedule the same sweeps (sample/container.py:29-78) on the Schur kernels:
