@@ -53,6 +53,8 @@ SHAPES = [
     ("nonuniform_n72",       (3, 3),  2,    72,  False, "random",     3,      2,      (2,)),        # element-wise RBF source
     ("cokol9x9_hc_n200",     (9, 9),  1,    200, True,  "uniform",    2,      1,      (1,)),        # cfg4 shape: 64-function class
     ("threeway_n40",         (2, 2, 2), 2,  40,  False, "uniform",    4,      2,      (0, 3)),      # seven prior groups on four streams
+    ("oneway4_n60",          (4,),    3,    60,  False, "uniform",    4,      2,      (0, 2)),      # a group of THREE functions in the four-function kernels
+    ("oneway4_hc_n130",      (4,),    3,    130, True,  "uniform",    3,      2,      (1,)),        # ... sharing one factorisation: passes of 2 + 1
 ]
 
 
