@@ -55,6 +55,8 @@ SHAPES = [
     ("threeway_n40",         (2, 2, 2), 2,  40,  False, "uniform",    4,      2,      (0, 3)),      # seven prior groups on four streams
     ("oneway4_n60",          (4,),    3,    60,  False, "uniform",    4,      2,      (0, 2)),      # a group of THREE functions in the four-function kernels
     ("oneway4_hc_n130",      (4,),    3,    130, True,  "uniform",    3,      2,      (1,)),        # ... sharing one factorisation: passes of 2 + 1
+] + [   # every boundary of the staged register layout (slots per lane 1 / 2 / 4 / 8 at n <= 32 / 64 / 128 / 256; padding to 8)
+    ("bnd_n%d" % nn,         (3,),    2,    nn,  False, "uniform",    2,      1,      (1,)) for nn in (8, 9, 32, 33, 64, 65, 127, 128, 129, 255)
 ]
 
 
