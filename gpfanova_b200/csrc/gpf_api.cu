@@ -59,7 +59,10 @@ struct gpf_ctx {
   double* d_kinv_tmp = nullptr;       // scratch of the K_inv operator (gpf_group_kinv with an output buffer)
   bool schurfn_ok = false;            // uniform grid, balanced design, n <= 256, groups of at most 4: O(n^2) function step
   int use_schurfn = 1;
-  int pipelines = 1;                  // balanced sweeps on the Schur kernels: functions -> slices of each group on its own stream
+  int pipelines = 1;                  // balanced sweeps on the Schur kernels: functions -> slices of each group on its own stream;
+                                      // 2: the slice kernels also store the rows and run the next y_sigma step (fold) -- fewer
+                                      // launches, but measured slower on the device (5.82 vs 5.71 ms): one warp per chain does
+                                      // at the end of the longest units what k_obs does for all chains at once
   int cohorts = 1;                    // ... and the chains in this many independent cohorts, each with its own streams (1 or 2;
                                       // two were SLOWER at every chain count: more kernel variants per SM, smaller grids)
   struct Lane {                       // streams / events of the second cohort (the first uses stream, aux, ev_fork, ev_join)
@@ -300,11 +303,15 @@ int launch_chain_sweeps(gpf_ctx* c, int n_sweeps, int thin, unsigned sweep0, dou
   const CtxDev& v = c->dev;
   const int ns = (int)c->order.size();
   if (!c->d_swk) {
-    int rc;
-    if ((rc = dev_alloc(c, &c->d_swk, (size_t)2 * v.C + 1)) || (rc = dev_alloc(c, &c->d_sid_sigma, (size_t)v.P)) ||
-        (rc = dev_alloc(c, &c->d_slice_w, (size_t)v.H)) || (rc = dev_alloc(c, &c->d_slice_m, (size_t)v.H)))
-      return rc;
+    int rc = dev_alloc(c, &c->d_swk, (size_t)2 * v.C + 1);
+    if (rc) return rc;
     CK(c, cudaMemset(c->d_swk + 2 * v.C, 0, sizeof(int)));
+  }
+  if (!c->d_sid_sigma) {
+    int rc;
+    if ((rc = dev_alloc(c, &c->d_sid_sigma, (size_t)v.P)) || (rc = dev_alloc(c, &c->d_slice_w, (size_t)v.H)) ||
+        (rc = dev_alloc(c, &c->d_slice_m, (size_t)v.H)))
+      return rc;
   }
   std::vector<unsigned> sid((size_t)v.P, 0u);
   for (int k = 0; k < ns; ++k)
@@ -366,7 +373,10 @@ bool pipe_active(const gpf_ctx* c) {
   return true;
 }
 
-int enqueue_schur_sweep(gpf_ctx* c, int q, int c0, int cnt, unsigned sweep, const std::vector<std::pair<int, int>>& todo) {
+struct FoldPlan { bool on; bool launch_y; int target; double* row; bool next_y; };
+
+int enqueue_schur_sweep(gpf_ctx* c, int q, int c0, int cnt, unsigned sweep, const std::vector<std::pair<int, int>>& todo,
+                        const FoldPlan& fp) {
   cudaStream_t st = q ? c->lane2.st : c->stream;
   cudaStream_t* aux = q ? c->lane2.aux : c->aux;
   cudaEvent_t fork = q ? c->lane2.fork : c->ev_fork;
@@ -378,9 +388,11 @@ int enqueue_schur_sweep(gpf_ctx* c, int q, int c0, int cnt, unsigned sweep, cons
   dv.status += c0;
   dv.chain_offset += c0;
   int* sched = c->dev.sched + 8 * q;
-  k_obs<<<std::min(cnt, c->sms * 8), NTHR, 0, st>>>(dv, 1, nullptr, nullptr, c->slice_w[0], c->slice_m[0], 0u, sweep, nullptr, 0, nullptr);
-  ++c->launches;
-  CK(c, cudaGetLastError());
+  if (fp.launch_y) {
+    k_obs<<<std::min(cnt, c->sms * 8), NTHR, 0, st>>>(dv, 1, nullptr, nullptr, c->slice_w[0], c->slice_m[0], 0u, sweep, nullptr, 0, nullptr);
+    ++c->launches;
+    CK(c, cudaGetLastError());
+  }
   CK(c, cudaEventRecord(fork, st));
   bool forked[4] = {false, false, false, false};
   for (size_t i = 0; i < todo.size(); ++i) {
@@ -397,6 +409,15 @@ int enqueue_schur_sweep(gpf_ctx* c, int q, int c0, int cnt, unsigned sweep, cons
     CK(c, cudaMemsetAsync(d2.sched, 0, sizeof(int), aux[slot]));
     PriorArgs pa{g, 4, nullptr, nullptr, c->slice_w[1 + 2 * g], c->slice_w[2 + 2 * g], c->slice_m[1 + 2 * g], c->slice_m[2 + 2 * g],
                  (unsigned)k, sweep, nullptr, 0, nullptr};
+    if (fp.on) {
+      pa.fold_done = c->d_swk + c->dev.C + c0;
+      pa.fold_target = fp.target;
+      pa.fold_row = fp.row;
+      pa.fold_cols = (size_t)dv.H + (size_t)dv.f * dv.n;
+      pa.fold_next_y = fp.next_y ? 1 : 0;
+      pa.w_y = c->slice_w[0];
+      pa.m_y = c->slice_m[0];
+    }
     const int ng = (int)c->groups[g].size();
     const int grid = std::min((cnt + 3) / 4, schur_minb(ng <= 2 ? ng : 4) * c->sms);
     CK(c, schur_launch_prior(ng <= 2 ? ng : 4, grid, 128, 0, aux[slot], d2, pa));
@@ -424,6 +445,18 @@ int pipelined_sweeps(gpf_ctx* c, int n_sweeps, int thin, unsigned sweep0, double
   const int ncoh = (c->cohorts >= 2 && v.C >= 64) ? 2 : 1;
   int start[3] = {0, v.C, v.C};
   if (ncoh == 2) start[1] = ((v.C / 2 + 3) / 4) * 4;
+  // fold: the slice kernels count the finished groups of every chain; the last one stores the row and runs the next y_sigma
+  // step, so only the first sweep of the call launches k_obs and no copy kernels are needed (needs the least-squares form of
+  // the observation likelihood, option 4)
+  const bool fold = c->pipelines >= 2 && v.bhat != nullptr;
+  if (fold) {
+    if (!c->d_swk) {
+      int rc = dev_alloc(c, &c->d_swk, (size_t)2 * v.C + 1);
+      if (rc) return rc;
+      CK(c, cudaMemset(c->d_swk + 2 * v.C, 0, sizeof(int)));
+    }
+    CK(c, cudaMemsetAsync(c->d_swk + v.C, 0, sizeof(int) * v.C, c->stream));     // before lane2.begin is recorded below
+  }
   if (ncoh == 2) {      // the second cohort starts behind everything queued so far on the context's stream
     CK(c, cudaEventRecord(c->lane2.begin, c->stream));
     CK(c, cudaStreamWaitEvent(c->lane2.st, c->lane2.begin, 0));
@@ -433,11 +466,12 @@ int pipelined_sweeps(gpf_ctx* c, int n_sweeps, int thin, unsigned sweep0, double
     if (store && *rows >= cap) { c->err = "gpf_sweep: history buffer full"; return GPF_ERR_ARG; }
     for (int q = 0; q < ncoh; ++q) {
       const int c0 = start[q], cnt = start[q + 1] - start[q];
-      int rc = enqueue_schur_sweep(c, q, c0, cnt, sweep0 + (unsigned)s, todo);
+      double* row = store ? d_history + ((size_t)(*rows) * v.C + c0) * cols : nullptr;
+      FoldPlan fp{fold, !fold || s == 0, v.P * (s + 1), row, s + 1 < n_sweeps};
+      int rc = enqueue_schur_sweep(c, q, c0, cnt, sweep0 + (unsigned)s, todo, fp);
       if (rc) return rc;
-      if (store) {
+      if (store && !fold) {
         cudaStream_t st = q ? c->lane2.st : c->stream;
-        double* row = d_history + ((size_t)(*rows) * v.C + c0) * cols;
         CK(c, cudaMemcpy2DAsync(row, cols * sizeof(double), v.hyper + (size_t)c0 * v.H, v.H * sizeof(double), v.H * sizeof(double), cnt,
                                 cudaMemcpyDeviceToDevice, st));
         CK(c, cudaMemcpy2DAsync(row + v.H, cols * sizeof(double), v.F + (size_t)c0 * v.f * v.n, (size_t)v.f * v.n * sizeof(double),
@@ -1387,7 +1421,7 @@ int gpf_get_option(gpf_ctx* c, int option) {
     case 5: return schurfn_active(c) ? 1 : 0;
     case 6: return c->indep ? 1 : 0;       // (read-only) balanced design, nothing missing
     case 7: return sweepk_active(c) ? 1 : 0;
-    case 8: return pipe_active(c) ? 1 : 0;
+    case 8: return pipe_active(c) ? c->pipelines : 0;
     case 9: return c->cohorts;
     default: return -1;
   }

@@ -286,6 +286,15 @@ struct PriorArgs {
   const double* u_inject;
   int n_inject;
   int* nevals;       // mode 2/3: evaluations of that step; mode 4: sigma step, nevals[C + ch]: lengthscale step
+  // "fold" (register-resident Schur kernels in a pipelined sweep, mode 4): the warp that finishes the LAST prior group of a
+  // chain's sweep stores the chain's history row and runs the y_sigma step of the next sweep itself
+  int* fold_done;    // per chain: group units finished since the start of the gpf_sweep call (null: no fold)
+  int fold_target;   // P * (sweeps finished including this one)
+  double* fold_row;  // history row of this sweep (chain 0 of the launch), or null
+  size_t fold_cols;  // its row stride per chain
+  int fold_next_y;   // run the y_sigma step of sweep + 1
+  double w_y;        // slice width / step budget of y_sigma
+  int m_y;
 };
 
 // element e of the 2n standard normals of one function draw (z1 = elements [0, n), z2 = [n, 2n)): Box-Muller pair e >> 1

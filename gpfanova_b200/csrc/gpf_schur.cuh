@@ -435,6 +435,59 @@ __device__ __forceinline__ void schur_slice_chain(const CtxDev& c, const PriorAr
   }
 }
 
+// the y_sigma slice step of one chain by one warp; the residual sum of squares in k_obs's summation order
+__device__ __forceinline__ void schur_ysigma_warp(const CtxDev& c, const Stream& rng, int ch, unsigned sweep, double w_y, int m_y,
+                                                  unsigned sid_y, int lane) {
+  const int n = c.n, fn_ = c.f * n;
+  const double* Fc = c.F + (size_t)ch * c.f * n;
+  double sse = 0.0;
+#pragma unroll
+  for (int vw = 0; vw < NW; ++vw) {              // virtual warp vw of k_obs's CTA: threads 32 vw + lane
+    double part = 0.0;
+    for (int e = 32 * vw + lane; e < fn_; e += NTHR) {
+      const int q = e / n;
+      const double dlt = __ldcg(Fc + e) - c.bhat[e];
+      part = fma(c.G[(size_t)q * c.f + q] * dlt, dlt, part);
+    }
+    if (vw == 0 && lane == 0) part += c.rss0;
+    sse += warp_sum(part);
+  }
+  const double cnt = (double)n * (double)c.m;
+  const unsigned gch = (unsigned)(ch + c.chain_offset);
+  int nev;
+  const double x0 = __ldcg(c.hyper + (size_t)ch * c.H);
+  const double x1 = slice_step(
+      x0, w_y, m_y, [&](double v) { return obs_loglik_eval(sse, cnt, v, c.prior_lb, c.prior_ub); },
+      [&](int k) { return rng.uniform(gch, sweep, sid_y, (unsigned)k); }, nev);
+  if (lane == 0) {
+    c.hyper[(size_t)ch * c.H] = x1;
+    atomicAdd(c.counters + CNT_LOGP, (unsigned long long)nev);
+    atomicAdd(c.counters + CNT_SLICE, 1ull);
+  }
+}
+
+
+// end of a chain's group unit in a pipelined sweep: count it; the last group of the chain's sweep stores the row and samples
+// y_sigma for the next sweep (the kernels of the next sweep start after all slice kernels of this one have finished)
+__device__ __forceinline__ void schur_fold_tail(const CtxDev& c, const PriorArgs& a, int ch, int lane) {
+  __threadfence();
+  __syncwarp();
+  int old = 0;
+  if (lane == 0) old = atomicAdd(a.fold_done + ch, 1);
+  old = __shfl_sync(FULLMASK, old, 0);
+  if (old + 1 != a.fold_target) return;
+  __threadfence();                                // the other groups' units counted before this one: their data is in L2
+  const int n = c.n;
+  if (a.fold_row != nullptr) {
+    double* dst = a.fold_row + (size_t)ch * a.fold_cols;
+    const double* hy = c.hyper + (size_t)ch * c.H;
+    const double* Fc = c.F + (size_t)ch * c.f * n;
+    for (int e = lane; e < c.H; e += 32) dst[e] = __ldcg(hy + e);
+    for (int e = lane; e < c.f * n; e += 32) __stcs(dst + c.H + e, __ldcg(Fc + e));
+  }
+  if (a.fold_next_y) schur_ysigma_warp(c, Stream{c.k0, c.k1}, ch, a.sweep + 1u, a.w_y, a.m_y, 0u, lane);
+}
+
 template <int NG>
 __global__ void __launch_bounds__(NG > 0 ? 128 : NTHR, schur_minb(NG)) k_prior_schur(CtxDev c, PriorArgs a) {
   extern __shared__ __align__(16) double gpf_smem_schur[];
@@ -443,8 +496,10 @@ __global__ void __launch_bounds__(NG > 0 ? 128 : NTHR, schur_minb(NG)) k_prior_s
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* base = gpf_smem_schur + (size_t)warp * schur_warp_doubles(n, ng);
   double *us = base, *v = base + n, *ev = base + 2 * n, *r = base + 4 * n;   // base + 3n: spare (alignment of r)
-  for (int ch = next_chain_warp(c.sched, lane); ch < c.C; ch = next_chain_warp(c.sched, lane))
+  for (int ch = next_chain_warp(c.sched, lane); ch < c.C; ch = next_chain_warp(c.sched, lane)) {
     schur_slice_chain<NG>(c, a, ch, lane, us, v, ev, r);
+    if (NG > 0 && a.fold_done != nullptr) schur_fold_tail(c, a, ch, lane);
+  }
 }
 
 }  // namespace gpf

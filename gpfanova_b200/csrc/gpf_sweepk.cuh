@@ -21,36 +21,6 @@
 namespace gpf {
 
 
-// the y_sigma slice step of one chain by one warp; the residual sum of squares in k_obs's summation order
-__device__ __forceinline__ void sweepk_ysigma(const CtxDev& c, const SweepKArgs& a, const Stream& rng, int ch, unsigned sweep, int lane) {
-  const int n = c.n, fn_ = c.f * n;
-  const double* Fc = c.F + (size_t)ch * c.f * n;
-  double sse = 0.0;
-#pragma unroll
-  for (int vw = 0; vw < NW; ++vw) {              // virtual warp vw of k_obs's CTA: threads 32 vw + lane
-    double part = 0.0;
-    for (int e = 32 * vw + lane; e < fn_; e += NTHR) {
-      const int q = e / n;
-      const double dlt = __ldcg(Fc + e) - c.bhat[e];
-      part = fma(c.G[(size_t)q * c.f + q] * dlt, dlt, part);
-    }
-    if (vw == 0 && lane == 0) part += c.rss0;
-    sse += warp_sum(part);
-  }
-  const double cnt = (double)n * (double)c.m;
-  const unsigned gch = (unsigned)(ch + c.chain_offset);
-  int nev;
-  const double x0 = __ldcg(c.hyper + (size_t)ch * c.H);
-  const double x1 = slice_step(
-      x0, a.slice_w[0], a.slice_m[0], [&](double v) { return obs_loglik_eval(sse, cnt, v, c.prior_lb, c.prior_ub); },
-      [&](int k) { return rng.uniform(gch, sweep, a.sid_y, (unsigned)k); }, nev);
-  if (lane == 0) {
-    c.hyper[(size_t)ch * c.H] = x1;
-    atomicAdd(c.counters + CNT_LOGP, (unsigned long long)nev);
-    atomicAdd(c.counters + CNT_SLICE, 1ull);
-  }
-}
-
 __device__ __forceinline__ int ld_acquire(const int* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -132,7 +102,7 @@ __global__ void __launch_bounds__(128, GPF_SFN_MINB) k_chain_sweeps(CtxDev c, Sw
         }
       }
       if (s + 1 < a.n_sweeps) {
-        sweepk_ysigma(c, a, rng, ch, a.sweep0 + (unsigned)(s + 1), lane);
+        schur_ysigma_warp(c, rng, ch, a.sweep0 + (unsigned)(s + 1), a.slice_w[0], a.slice_m[0], a.sid_y, lane);
         __syncwarp();
         if (lane == 0) {
           __threadfence();

@@ -261,7 +261,9 @@ int gpf_sweep(gpf_ctx* ctx, int n_sweeps, int thin, unsigned sweep0, const int* 
  * three slice variants in flight on every SM the kernel's hot loops miss the 32 KB instruction cache (ncu: 47 % hit rate, 23
  * no-instruction stall cycles per issue) and it runs four times slower than the per-stage kernels.
  * 8 = where option 5 applies to every prior group: every group's functions and slice kernel run back to back on the group's
- * own stream (a group's slices start while other groups still draw functions; default 1; bit-identical to 8 = 0);
+ * own stream (a group's slices start while other groups still draw functions; default 1; bit-identical to 8 = 0); 8 = 2:
+ * additionally the slice kernel that finishes the last group of a chain's sweep stores the chain's history row and runs the
+ * y_sigma step of the next sweep (needs option 4), so only the first sweep of a call launches the y_sigma kernel (fewer launches, but measured slower on the device);
  * 9 = 2 additionally splits the chains into two cohorts with their own streams, so that the stage boundaries of one
  * cohort are filled by the other's kernels (default 1 = one cohort: two measured slower at every chain count -- more
  * kernel variants per SM for the instruction cache, smaller grids).

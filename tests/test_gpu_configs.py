@@ -211,7 +211,9 @@ def test_dense_slice_path_with_many_functions(eng):
 def test_sweep_schedules_are_bit_identical(eng, levels, reps, n, hc, C, S, thin):
     """Four ways to schedule the same sweeps (sample/container.py:29-78) on the Schur kernels:
       per-stage kernels (gpf_set_option 8 = 0): y_sigma | all functions | the groups' slice kernels;
-      group pipelines (default): every group's functions -> slices on its own stream;
+      group pipelines (default, 8 = 1): every group's functions -> slices on its own stream;
+      ... with the fold (8 = 2): the slice kernel that finishes a chain's last group stores the row and runs the next
+      y_sigma step -- no k_obs launch and no copy kernels after the first sweep of a call;
       group pipelines with the chains in two independent cohorts of streams (9 = 2);
       one launch (7 = 1, csrc/gpf_sweepk.cuh): units handed to warps by ticket, a chain's y_sigma step and history row done by
       the warp that finishes the chain's sweep -- no device-wide barrier anywhere.
@@ -219,7 +221,7 @@ def test_sweep_schedules_are_bit_identical(eng, levels, reps, n, hc, C, S, thin)
     EQUAL bit for bit."""
     x, y, d, groups, F = make_problem(levels, reps, n, hc, seed=n + C)
     outs = []
-    variants = [("stages", {8: 0}), ("pipelines", {}), ("two cohorts", {9: 2}), ("one launch", {7: 1})]
+    variants = [("stages", {8: 0}), ("pipelines", {}), ("pipelines + fold", {8: 2}), ("two cohorts", {9: 2}), ("one launch", {7: 1})]
     for name, opts in variants:
         e = eng.ChainEngine(x, y, d.X, groups, chains=C, seed=77, chain_offset=3)
         for k, v in opts.items():
@@ -247,4 +249,4 @@ def test_sweep_schedules_are_bit_identical(eng, levels, reps, n, hc, C, S, thin)
         assert np.array_equal(o[0], ref[0]) and np.array_equal(o[1], ref[1]) and np.array_equal(o[2], ref[2]), name
         for k in ("chol", "logp", "draws", "slice_steps", "function_chol", "ko_factor", "jitter"):
             assert o[3][k] == ref[3][k], (name, k)
-    assert outs[3][4] <= 2 and outs[3][4] < ref[4]         # one launch for the whole call
+    assert outs[-1][4] <= 2 and outs[-1][4] < ref[4]       # one launch for the whole call
